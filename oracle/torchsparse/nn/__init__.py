@@ -1,0 +1,5 @@
+"""ORACLE: torchsparse.nn (v1.4.0)."""
+from . import functional, utils
+from .modules import BatchNorm, Conv3d, ReLU
+
+__all__ = ["Conv3d", "BatchNorm", "ReLU", "functional", "utils"]

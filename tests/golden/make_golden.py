@@ -1,0 +1,188 @@
+"""Generate tests/golden/*.npz in the BUILD container (needs /root/reference; never runs on the GPU box).
+
+What it pins:
+  scoring.npz    the reference's own ``score.sv_level.LiDAL.worker_func`` executed on synthetic
+                 prob / KD-tree / supervoxel files  == oracle.lidal_scoring.score_frame (exact).
+  selection.npz  the reference's own selection source (LiDAL.py:230-325, exec'd unmodified with a
+                 small ``train_point_num`` so the budget binds) == oracle.lidal_scoring.select_regions.
+  nets.npz       the reference's unmodified network/minkunet.py + network/spvcnn.py running on the
+                 oracle torchsparse restatement: logits slices + checksums, kernel-map sizes/checksums.
+  hash.npz       sphash known answers from an independent pure-Python-int FNV-1a.
+
+Run:  python tests/golden/make_golden.py
+"""
+import hashlib
+import io
+import os
+import pickle
+import sys
+import tempfile
+from contextlib import redirect_stdout
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "_stubs"), REF]
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from lidal_b200 import synth  # noqa: E402
+import lidal_scoring as orc  # noqa: E402
+
+
+def sha(*arrays):
+    h = hashlib.sha1()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def scoring_case():
+    """26 frames (minimum for the +-12 reflection rule is 25), 1500 pts, 19 classes."""
+    return dict(n_frames=26, kind="NU", seed=11, max_points=1500, n_cls=19, step=0.15)
+
+
+def build_scoring_inputs(case):
+    seq = synth.make_sequence(case["n_frames"], case["kind"], case["seed"], max_points=case["max_points"],
+                              step=case["step"])
+    probs = [synth.synthetic_probs(seq.xyz[i], case["n_cls"], 500 + i) for i in range(seq.n_frames)]
+    return seq, probs
+
+
+def gen_scoring():
+    from sklearn.neighbors import KDTree
+    import score.sv_level.LiDAL as ref            # the reference itself (nuscenes stub on sys.path)
+    case = scoring_case()
+    seq, probs = build_scoring_inputs(case)
+    with tempfile.TemporaryDirectory() as d:
+        pf, kf, sf = [], [], []
+        for i in range(seq.n_frames):
+            pf.append(f"{d}/p{i:06d}.npy"); np.save(pf[-1], probs[i])
+            kf.append(f"{d}/k{i:06d}.pickle")
+            with open(kf[-1], "wb") as f:
+                pickle.dump(KDTree(seq.xyz[i]), f)
+            sf.append(f"{d}/s{i:06d}.pickle")
+            with open(sf[-1], "wb") as f:
+                pickle.dump((seq.sv_id[i], seq.sv2point[i]), f)
+        ref.init_worker(False, 24, 0.1, "00", pf, kf, sf)
+        with redirect_stdout(io.StringIO()):
+            ref_out = [ref.worker_func(i) for i in range(seq.n_frames)]
+    trees = orc.build_trees(seq.xyz)
+    for i in range(seq.n_frames):
+        mine = orc.score_frame(i, probs, seq.xyz, trees, seq.sv_id[i], seq.sv2point[i])
+        for a, b in zip(ref_out[i], mine):
+            assert a.dtype == b.dtype and np.array_equal(a, b), f"oracle != reference at frame {i}"
+    # per-point values for finer-grained GPU parity
+    pts = []
+    for i in (0, 13, 25):
+        nids = orc.neighbour_ids(i, seq.n_frames)
+        d_, e_, c_ = orc.score_points(probs[i], seq.xyz[i], [probs[n] for n in nids], [trees[n] for n in nids])
+        pts.append((d_, e_, c_))
+    np.savez_compressed(
+        f"{OUT}/scoring.npz", case=np.array(list(case.items()), dtype=object),
+        input_sha=sha(*seq.xyz, *probs),
+        sv_id=np.stack([r[0] for r in ref_out]), sv_interds=np.stack([r[1] for r in ref_out]),
+        sv_interes=np.stack([r[2] for r in ref_out]), sv_pnums=np.stack([r[3] for r in ref_out]),
+        sv_centers=np.stack([r[4] for r in ref_out]),
+        pt_frames=np.array([0, 13, 25]),
+        **{f"pt_d{j}": p[0] for j, p in enumerate(pts)}, **{f"pt_e{j}": p[1] for j, p in enumerate(pts)},
+        **{f"pt_c{j}": p[2] for j, p in enumerate(pts)}, allow_pickle=True)
+    print("scoring.npz: oracle == reference worker_func on", seq.n_frames, "frames")
+    return ref_out
+
+
+def selection_inputs(seed=5, n=1200):
+    rng = np.random.default_rng(seed)
+    sv_flags = (rng.random(n) < 0.02).astype(np.float64)              # np.append result dtype
+    sv_flags[rng.random(n) < 0.05] = 2.0                               # stale pseudo labels from last round
+    sv_interds = rng.gamma(2.0, 0.05, n).astype(np.float32)
+    sv_interds[rng.random(n) < 0.03] = 0.0
+    sv_interes = rng.random(n).astype(np.float32)
+    sv_pnums = rng.integers(60, 80, n).astype(int)
+    t = np.linspace(0, 300, n)
+    sv_centers = np.stack([t + rng.normal(0, 3, n), rng.normal(0, 6, n), rng.normal(0, 0.5, n)], 1).astype(np.float32)
+    return sv_flags, sv_interds, sv_interes, sv_pnums, sv_centers
+
+
+def gen_selection():
+    src = open(f"{REF}/score/sv_level/LiDAL.py").read().split("\n")
+    block = "\n".join(line[4:] if line.startswith("    ") else line for line in src[224:325])   # lines 225..325
+    cases = {}
+    for name, tpn in (("tight", 700_000), ("loose", 100_000_000)):
+        sv_flags, d, e, pn, c = selection_inputs()
+        ns = dict(np=np, sv_flags=sv_flags.copy(), sv_interds=d, sv_interes=e, sv_pnums=pn, sv_centers=c,
+                  train_point_num=tpn)
+        with redirect_stdout(io.StringIO()):
+            exec(compile(block, "LiDAL.py[225:325]", "exec"), ns)
+        mine = orc.select_regions(sv_flags.copy(), d, e, pn, c, tpn)
+        assert np.array_equal(ns["sv_flags"], mine), name
+        cases[name] = (tpn, ns["sv_flags"])
+        print(f"selection[{name}]: oracle == reference block; flags1={int((mine == 1).sum())} flags2={int((mine == 2).sum())}")
+    sv_flags, d, e, pn, c = selection_inputs()
+    np.savez_compressed(f"{OUT}/selection.npz", sv_flags=sv_flags, sv_interds=d, sv_interes=e, sv_pnums=pn,
+                        sv_centers=c, tight_tpn=cases["tight"][0], tight_out=cases["tight"][1],
+                        loose_tpn=cases["loose"][0], loose_out=cases["loose"][1])
+
+
+def fnv_python(c4):
+    h = 14695981039346656037
+    for v in c4:
+        h ^= (int(v) & 0xFFFFFFFF)
+        h = (h * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return (h >> 60) ^ (h & 0x0FFFFFFFFFFFFFFF)
+
+
+def gen_hash():
+    import torch
+    import torchsparse.nn.functional as F
+    rng = np.random.default_rng(3)
+    coords = np.concatenate([rng.integers(0, 8192, (12, 3)), rng.integers(0, 8, (12, 1))], 1).astype(np.int32)
+    coords = np.concatenate([coords, [[0, 0, 0, 0], [8191, 8191, 8191, 7], [-1, -2, -3, 0], [1, 0, 0, 0]]], 0).astype(np.int32)
+    want = np.array([fnv_python(c) for c in coords], dtype=np.int64)
+    got = F.sphash(torch.from_numpy(coords)).numpy()
+    assert np.array_equal(want, got)
+    np.savez_compressed(f"{OUT}/hash.npz", coords=coords, hashes=want)
+    print("hash.npz: oracle sphash == pure-python FNV-1a on 16 coords")
+
+
+def gen_nets():
+    import torch
+    import torchsparse
+    from torchsparse import SparseTensor
+    from network.minkunet import MinkUNet          # reference, unmodified
+    from network.spvcnn import SPVCNN
+    from lidal_b200.network import seeded_state_dict
+    raw = synth.raycast_scan(42, "NU")
+    rs = np.random.RandomState(9)
+    coords, feats, inv = synth.collate_views([synth.score_transform(raw[::4], rs), synth.score_transform(raw[1::4], rs)])
+    out = dict(input_sha=sha(coords, feats), n_vox=coords.shape[0])
+    for name, cls, ncls in (("minkunet", MinkUNet, 19), ("spvcnn", SPVCNN, 16)):
+        model = cls(ncls)
+        sd = seeded_state_dict(model.state_dict(), seed=7122)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        x = SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords))
+        with torch.no_grad():
+            logits, feat = model(x)
+        logits, feat = logits.numpy(), feat.numpy()
+        out[f"{name}_keys"] = np.array([f"{k}:{tuple(v.shape)}" for k, v in sd.items()])
+        out[f"{name}_logits_head"] = logits[:512]
+        out[f"{name}_logits_sha"] = sha(logits)
+        out[f"{name}_logits_absmean"] = np.abs(logits).mean()
+        out[f"{name}_feat_head"] = feat[:64]
+        if name == "minkunet":
+            for key, km in x.kmaps.items():
+                tag = f"kmap_s{key[0][0]}_k{key[1][0]}_st{key[2][0]}"
+                out[tag + "_nbsizes"] = km[1].numpy()
+                out[tag + "_sha"] = sha(km[0].numpy().astype(np.int32))
+                out[tag + "_sizes"] = np.array(km[2])
+            for s, c in x.cmaps.items():
+                out[f"cmap_s{s[0]}_sha"] = sha(c.numpy().astype(np.int32))
+        print(f"nets.npz: {name} logits {logits.shape} |mean|={np.abs(logits).mean():.4f}")
+    np.savez_compressed(f"{OUT}/nets.npz", **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets"]
+    for w in which:
+        globals()[f"gen_{w}"]()
