@@ -1,0 +1,202 @@
+/*
+ * lidal_b200 -- C ABI of the B200-native hot path of hzykent/LiDAL.
+ *
+ * This is the drop-in boundary "B1-native" of SURVEY.md section 8(b): what the reference
+ * reaches through `torchsparse.backend.*` (torchsparse==1.4.0, docs/requirements.txt:191 --
+ * an un-vendored third-party extension) plus the device side of the scoring chain
+ * (score/prob_inference.py:100-113, score/sv_level/LiDAL.py:59-103,230-325).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless marked [host].
+ *   - the caller owns all memory including workspaces (`*_bytes` helpers size them);
+ *     no allocation, no host synchronisation and no global state inside a call
+ *     (the exceptions are marked "syncs").
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *   - return value: LB_OK or a negative LB_E* code; `lb_last_error()` has the text.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns LB_ECUDA.
+ *   - coordinates are int32 [N,4] = (x, y, z, batch), batch LAST (dataset/sk_dataset.py:191,209).
+ */
+#ifndef LIDAL_B200_H
+#define LIDAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_OK 0
+#define LB_EINVAL (-1) /* bad argument (null pointer, unsupported shape)          */
+#define LB_ECAP (-2)   /* capacity / workspace too small                          */
+#define LB_ECUDA (-3)  /* CUDA runtime error or no device                         */
+
+#define LB_ABI_VERSION 1
+
+int lb_abi_version(void);
+const char* lb_last_error(void); /* [host] thread-local text of the last failure */
+int lb_device_info(int* sm_count, int* cc_major, int* cc_minor); /* [host] outs */
+
+/* ------------------------------------------------------------------ hashing / kernel maps
+ * Replaces torchsparse.backend.hash_cuda / kernel_hash_cuda / hash_query_cuda, reached from
+ * F.sphash / F.sphashquery at network/utils.py:17,19,42,47-48,70-76 and from every kernel-map
+ * build inside spnn.Conv3d (network/utils.py:110-114,129-133,147-155). */
+
+/* 64-bit FNV-1a over (x,y,z,b) as uint32, folded to 60 bits.  out int64 [n]. */
+int lb_hash(const int32_t* coords, int64_t n, int64_t* out, void* stream);
+/* hash of (xyz + offsets[k], b); offsets int32 [k,3]; out int64 [k,n] (offset-major). */
+int lb_kernel_hash(const int32_t* coords, int64_t n, const int32_t* offsets, int k, int64_t* out, void* stream);
+
+/* Open-addressing table key(int64 >= 0) -> smallest row index holding that key. */
+size_t lb_hashtable_bytes(int64_t n_keys);
+int lb_hashtable_build(const int64_t* keys, int64_t n, void* table, size_t table_bytes, void* stream);
+/* out int64 [nq]: row index or -1 (F.sphashquery). */
+int lb_hashtable_query(const void* table, size_t table_bytes, const int64_t* queries, int64_t nq, int64_t* out,
+                       void* stream);
+
+/* F.spdownsample for stride in {1, kernel_size}: xyz <- floor(xyz / s) * s per axis (s = stride*tensor_stride),
+ * rows deduplicated and returned sorted by (b,x,y,z).  coords must lie in [0, 2^16) and batch in [0, 2^15).
+ * out_coords int32 [<=n,4]; n_out: device int32[1].  ws from lb_downsample_ws_bytes(n).  No host sync. */
+size_t lb_downsample_ws_bytes(int64_t n);
+int lb_downsample(const int32_t* coords, int64_t n, const int32_t sample_stride[3] /*[host]*/, int batch_bits,
+                  int32_t* out_coords, int32_t* n_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Fused kernel_hash + table lookup: nbr[k][o] = row of (out_coords[o].xyz + offsets[k], b) among the table's
+ * keys, or -1.  This is the `results` matrix of the reference's map build.  n_out_dev (device int32[1]) may be
+ * NULL, in which case all n_out_cap rows are valid; nbr int32 [k, n_out_cap]. */
+int lb_kmap_query(const void* table, size_t table_bytes, const int32_t* out_coords, int64_t n_out_cap,
+                  const int32_t* n_out_dev, const int32_t* offsets, int k, int32_t* nbr, void* stream);
+
+/* Compaction to the reference's (nbmaps, nbsizes): rows (in_idx, out_idx) enumerated k-major then o ascending.
+ * nbmaps int32 [k*n_out,2] (worst case), nbsizes int32 [k], total device int32[1]. */
+size_t lb_kmap_compact_ws_bytes(int64_t n_out, int k);
+int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t* nbmaps, int32_t* nbsizes, int32_t* total,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* Per-offset inverse of a neighbour table (transposed convolution / dgrad roles):
+ * nbr int32 [k, nbr_ld] with values in [0, n_in) or -1  ->  nbr_t int32 [k, n_in], nbr_t[k][nbr[k][o]] = o. */
+int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* nbr_t, int64_t n_in,
+                      void* stream);
+
+/* Stable LSD radix sort of (uint64 key, uint32 value) pairs on bits [0, end_bit). */
+size_t lb_sort_pairs_ws_bytes(int64_t n);
+int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ sparse convolution
+ * Replaces torchsparse.backend.convolution_forward_cuda (gather -> cuBLAS mm -> scatter per offset), reached from
+ * every spnn.Conv3d.forward: network/minkunet.py:23-84, network/spvcnn.py:21-81 via network/utils.py:105-172.
+ *
+ *   out[o, :] = epilogue( sum_k  in[nbr[k][o], :] @ W[k] )        rows with nbr < 0 contribute nothing
+ *   epilogue(v) = relu?( v * scale[c] + shift[c] + residual[o, c] )   (each part optional)
+ *
+ * Output-stationary implicit GEMM: no atomics, deterministic.  Activations are 16-bit (bf16 or fp16, fp32
+ * accumulate in TMEM); `ld_*` are row strides in ELEMENTS so tensors may be column slices of wider buffers
+ * (torchsparse.cat without a copy).  out_rows (optional int32 [n_out]) redirects row o to out_rows[o].
+ */
+#define LB_DT_BF16 0
+#define LB_DT_F16 1
+#define LB_DT_F32 2
+
+#define LB_CONV_RELU 1      /* apply ReLU last                                   */
+#define LB_CONV_FORCE_SIMT 2 /* use the CUDA-core kernel even where tcgen05 applies */
+
+typedef struct lb_conv_args {
+  const void* in;          /* [n_in, ld_in] act_dtype                                        */
+  int64_t n_in, ld_in;
+  void* out;               /* [n_out, ld_out] out_dtype                                      */
+  int64_t n_out, ld_out;
+  const int32_t* n_out_dev; /* optional device int32[1]: live row count (<= n_out)            */
+  const int32_t* nbr;      /* [k_vol, nbr_ld] neighbour table; NULL => identity (k_vol == 1) */
+  int64_t nbr_ld;
+  const int32_t* out_rows; /* optional row redirect                                          */
+  const void* weight;      /* packed by lb_conv_pack_weight: [k_vol][c_out][c_in] act_dtype  */
+  int k_vol, c_in, c_out;
+  const float* scale;      /* optional [c_out]                                               */
+  const float* shift;      /* optional [c_out]                                               */
+  const void* residual;    /* optional [n_out, ld_res] act_dtype                             */
+  int64_t ld_res;
+  int act_dtype;           /* LB_DT_BF16 | LB_DT_F16                                         */
+  int out_dtype;           /* LB_DT_BF16 | LB_DT_F16 | LB_DT_F32                             */
+  int flags;
+} lb_conv_args;
+
+/* fp32 [k_vol, c_in, c_out] (the `kernel` parameter layout of spnn.Conv3d) -> 16-bit [k_vol, c_out, c_in]. */
+int lb_conv_pack_weight(const float* kernel, int k_vol, int c_in, int c_out, int act_dtype, void* packed,
+                        void* stream);
+int lb_conv_fwd(const lb_conv_args* args /*[host]*/, void* stream);
+/* which kernel lb_conv_fwd would run for this shape: 1 = tcgen05 implicit GEMM, 0 = CUDA-core. */
+int lb_conv_uses_tensor_cores(int k_vol, int c_in, int c_out, int act_dtype);
+
+/* fp32 <-> 16-bit row-strided casts used at the fp32 torchsparse boundary. */
+int lb_cast(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows,
+            int64_t cols, void* stream);
+
+/* ------------------------------------------------------------------ point <-> voxel (SPVCNN)
+ * Replaces torchsparse.backend.count_cuda / voxelize_* / devoxelize_* reached from network/utils.py:20-25,49,56,77-95. */
+int lb_count(const int32_t* idx, int64_t n, int32_t* counts, int64_t m, void* stream);
+/* out[idx[i]] += feats[i] / counts[idx[i]]  (out zeroed inside).  feats f32 [n,c], out f32 [m,c]. */
+int lb_voxelize_fwd(const float* feats, const int32_t* idx, const int32_t* counts, int64_t n, int64_t m, int c,
+                    float* out, void* stream);
+int lb_voxelize_bwd(const float* grad_out, const int32_t* idx, const int32_t* counts, int64_t n, int64_t m, int c,
+                    float* grad_feats, void* stream);
+/* out[i] = sum_k w[i,k] * feats[idx[i,k]]; idx int32 [n,8], w f32 [n,8]. */
+int lb_devoxelize_fwd(const float* feats, const int32_t* idx, const float* w, int64_t n, int64_t m, int c, float* out,
+                      void* stream);
+int lb_devoxelize_bwd(const float* grad_out, const int32_t* idx, const float* w, int64_t n, int64_t m, int c,
+                      float* grad_feats, void* stream);
+/* F.calc_ti_weights: coords f32 [n, ld_c>=3], idx int64 [8,n] (corner-major), out f32 [8,n]. */
+int lb_ti_weights(const float* coords, int64_t ld_c, const int64_t* idx, int64_t n, float scale, float* out,
+                  void* stream);
+
+/* ------------------------------------------------------------------ prob_inference tail
+ * score/prob_inference.py:100-113: gather logits by inverse index, softmax, mean over views, argmax.
+ * logits f32 [n_vox, n_cls]; inverse int64 [reps*n_pts]; prob f32 [n_pts, n_cls]; pred int64 [n_pts]. */
+int lb_tta_softmax_mean_argmax(const float* logits, int64_t n_vox, int n_cls, const int64_t* inverse, int reps,
+                               int64_t n_pts, float* prob, int64_t* pred, void* stream);
+
+/* ------------------------------------------------------------------ inter-frame scoring
+ * score/sv_level/LiDAL.py:59-103.  One uniform grid per frame replaces the pickled sklearn KD-tree; the match rule
+ * is unchanged: exact nearest neighbour in float64, accepted iff sqrt(d2) <= dis_thresh. */
+size_t lb_frame_grid_bytes(int64_t n_pts);
+/* xyz f64 [n,3] registered coordinates (dataset/prepare_kdtree_sk.py:77-80); `cell` must exceed dis_thresh. */
+int lb_frame_grid_build(const double* xyz, int64_t n, double cell, void* grid, size_t grid_bytes, void* stream);
+
+typedef struct lb_frame_ref { /* one neighbouring frame, all device pointers */
+  const void* grid;    /* built by lb_frame_grid_build over `xyz`  */
+  const double* xyz;   /* [n,3]                                     */
+  const float* prob;   /* [n,n_cls] mean softmax (prob_inference)   */
+  int64_t n;
+} lb_frame_ref;
+
+/* worker_func's point loop (LiDAL.py:59-81) for ONE query frame against its neighbour window, fused:
+ * for each neighbour frame in the given order (nei_ids order): exact 1-NN, match iff dist <= dis_thresh,
+ * sum_prob += P_n[nn]; interd += sum_c kl_div(P_q+1e-5, P_n[nn]+1e-5); count += 1; then
+ * intere = entropy(sum_prob / count) and interd /= (count-1) where > 0.
+ * nbrs: [host] array of n_nbr (<= 32) frames.  Outputs: interd f64 [nq], intere f32 [nq]; optional
+ * count int32 [nq] (= matches) and nn_out int32 [n_nbr, nq] (matched row or -1) for parity tests. */
+int lb_interframe_score(const double* q_xyz, const float* q_prob, int64_t nq, int n_cls, const lb_frame_ref* nbrs,
+                        int n_nbr, double dis_thresh, double cell, double* interd, float* intere, int32_t* count,
+                        int32_t* nn_out, void* stream);
+
+/* LiDAL.py:87-98: per-region means over the ragged `sv2point` lists given in CSR form:
+ * region_ptr int32 [r+1], region_pts int32 [region_ptr[r]].  Outs: d,e f32 [r]; optional pnums i64 [r],
+ * centers f32 [r,3].  One block per region, fixed reduction order (deterministic). */
+int lb_region_reduce(const double* interd, const float* intere, const double* xyz, const int32_t* region_ptr,
+                     const int32_t* region_pts, int n_regions, float* sv_interds, float* sv_interes,
+                     int64_t* sv_pnums, float* sv_centers, void* stream);
+
+/* Ascending stable argsort of f32 keys (device radix sort; LiDAL.py:235,283); order int32 [n]. */
+size_t lb_argsort_ws_bytes(int64_t n);
+int lb_argsort_f32(const float* keys, int64_t n, int32_t* order, void* ws, size_t ws_bytes, void* stream);
+
+/* Regions whose centres lie within `radius` of each other, in the float32 arithmetic of LiDAL.py:252.
+ * Pass 1 (nbr_idx == NULL): row[i] = number of in-range regions of i.  Pass 2: row = exclusive offsets
+ * (caller scans), nbr_idx receives the lists (order within a row unspecified). */
+size_t lb_region_pairs_ws_bytes(int64_t n);
+int lb_region_pairs(const float* centers, int64_t n, float radius, int32_t* row, int32_t* nbr_idx, void* ws,
+                    size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDAL_B200_H */

@@ -1,0 +1,113 @@
+"""ctypes binding of the C-ABI library (include/lidal_b200.h).  PyTorch supplies device memory and
+streams only; every signature below is plain pointers and sizes.
+
+There is deliberately no fallback: if ``liblidal_b200.so`` cannot be loaded the import of any
+compute path raises, and every wrapper refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblidal_b200.so")
+
+LB_DT_BF16, LB_DT_F16, LB_DT_F32 = 0, 1, 2
+LB_CONV_RELU, LB_CONV_FORCE_SIMT = 1, 2
+DT_OF = {torch.bfloat16: LB_DT_BF16, torch.float16: LB_DT_F16, torch.float32: LB_DT_F32}
+
+vp, i64, i32, sz, dbl, flt = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double, C.c_float
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("inp", vp), ("n_in", i64), ("ld_in", i64), ("out", vp), ("n_out", i64), ("ld_out", i64),
+                ("n_out_dev", vp), ("nbr", vp), ("nbr_ld", i64), ("out_rows", vp), ("weight", vp),
+                ("k_vol", i32), ("c_in", i32), ("c_out", i32), ("scale", vp), ("shift", vp), ("residual", vp),
+                ("ld_res", i64), ("act_dtype", i32), ("out_dtype", i32), ("flags", i32)]
+
+
+class FrameRef(C.Structure):
+    _fields_ = [("grid", vp), ("xyz", vp), ("prob", vp), ("n", i64)]
+
+
+# name -> (restype, argtypes); must list every symbol include/lidal_b200.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "lb_abi_version": (i32, []),
+    "lb_last_error": (C.c_char_p, []),
+    "lb_device_info": (i32, [C.POINTER(i32)] * 3),
+    "lb_hash": (i32, [vp, i64, vp, vp]),
+    "lb_kernel_hash": (i32, [vp, i64, vp, i32, vp, vp]),
+    "lb_hashtable_bytes": (sz, [i64]),
+    "lb_hashtable_build": (i32, [vp, i64, vp, sz, vp]),
+    "lb_hashtable_query": (i32, [vp, sz, vp, i64, vp, vp]),
+    "lb_downsample_ws_bytes": (sz, [i64]),
+    "lb_downsample": (i32, [vp, i64, C.POINTER(i32), i32, vp, vp, vp, sz, vp]),
+    "lb_kmap_query": (i32, [vp, sz, vp, i64, vp, vp, i32, vp, vp]),
+    "lb_kmap_compact_ws_bytes": (sz, [i64, i32]),
+    "lb_kmap_compact": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
+    "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
+    "lb_sort_pairs_ws_bytes": (sz, [i64]),
+    "lb_sort_pairs": (i32, [vp, vp, i64, i32, vp, sz, vp]),
+    "lb_conv_pack_weight": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "lb_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
+    "lb_conv_uses_tensor_cores": (i32, [i32, i32, i32, i32]),
+    "lb_cast": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, vp]),
+    "lb_count": (i32, [vp, i64, vp, i64, vp]),
+    "lb_voxelize_fwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
+    "lb_voxelize_bwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
+    "lb_devoxelize_fwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
+    "lb_devoxelize_bwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
+    "lb_ti_weights": (i32, [vp, i64, vp, i64, flt, vp, vp]),
+    "lb_tta_softmax_mean_argmax": (i32, [vp, i64, i32, vp, i32, i64, vp, vp, vp]),
+    "lb_frame_grid_bytes": (sz, [i64]),
+    "lb_frame_grid_build": (i32, [vp, i64, dbl, vp, sz, vp]),
+    "lb_interframe_score": (i32, [vp, vp, i64, i32, C.POINTER(FrameRef), i32, dbl, dbl, vp, vp, vp, vp, vp]),
+    "lb_region_reduce": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    "lb_argsort_ws_bytes": (sz, [i64]),
+    "lb_argsort_f32": (i32, [vp, i64, vp, vp, sz, vp]),
+    "lb_region_pairs_ws_bytes": (sz, [i64]),
+    "lb_region_pairs": (i32, [vp, i64, flt, vp, vp, vp, sz, vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) the in-tree CUDA library; raise loudly if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m lidal_b200.build` (or __graft_entry__.build()). "
+                "lidal_b200 has no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+class LidalError(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        raise LidalError(f"lidal_b200 error {rc}: {lib().lb_last_error().decode()}")
+
+
+def ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise LidalError("lidal_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))

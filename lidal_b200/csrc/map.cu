@@ -1,0 +1,493 @@
+// Coordinate hashing, hash table, radix sort / scan primitives, strided downsample and kernel-map build.
+// Integer-only work: every result here is bit-exact against the oracle.
+// All kernels are HBM/L2-latency bound; grids are sized in multiples of the SM count.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace lb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+static inline int grid_for(int64_t n, int block, int per_thread = 1) {
+  int64_t blocks = (n + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
+  int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------ hash
+__global__ void hash_kernel(const int4* __restrict__ coords, int64_t n, int64_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = __ldg(&coords[i]);
+    out[i] = fnv60(c.x, c.y, c.z, c.w);
+  }
+}
+__global__ void kernel_hash_kernel(const int4* __restrict__ coords, int64_t n, const int* __restrict__ offsets, int k,
+                                   int64_t* __restrict__ out) {
+  extern __shared__ int s_off[];
+  for (int i = threadIdx.x; i < 3 * k; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = __ldg(&coords[i]);
+    for (int j = 0; j < k; ++j)   // coalesced across threads for every j
+      out[(int64_t)j * n + i] = fnv60(c.x + s_off[3 * j], c.y + s_off[3 * j + 1], c.z + s_off[3 * j + 2], c.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ table
+__global__ void table_build_kernel(const int64_t* __restrict__ keys, int64_t n, TableView t) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    table_insert(t, (uint64_t)__ldg(&keys[i]), (int)i);
+}
+__global__ void table_query_kernel(TableView t, const int64_t* __restrict__ q, int64_t n, int64_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int64_t)table_find(t, (uint64_t)__ldg(&q[i]));
+}
+
+// ------------------------------------------------------------------------------------------ scan
+// Three-phase exclusive scan: per-tile sums -> single-block scan of tile sums -> per-tile scan + offset.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& block_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    s_warp[lane] = wi - w;                 // exclusive warp offsets
+    if (lane == 31) s_warp[32] = wi;       // total
+  }
+  __syncthreads();
+  uint32_t res = s_warp[warp] + incl - v;
+  block_total = s_warp[32];
+  __syncthreads();
+  return res;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const uint32_t* __restrict__ in, int64_t n,
+                                                               uint32_t* __restrict__ sums) {
+  __shared__ uint32_t s_warp[33];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    int64_t i = base + j * SCAN_THREADS + threadIdx.x;
+    if (i < n) acc += __ldg(&in[i]);
+  }
+  uint32_t total;
+  block_exclusive_scan(acc, s_warp, total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) scan_sums_single(uint32_t* sums, int64_t m, uint32_t* total_out) {
+  __shared__ uint32_t s_warp[33];
+  uint32_t carry = 0;
+  for (int64_t base = 0; base < m; base += blockDim.x) {
+    int64_t i = base + threadIdx.x;
+    uint32_t v = i < m ? sums[i] : 0, tot;
+    uint32_t ex = block_exclusive_scan(v, s_warp, tot);
+    if (i < m) sums[i] = ex + carry;
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                int64_t n, const uint32_t* __restrict__ sums) {
+  __shared__ uint32_t s_warp[33];
+  // each thread owns SCAN_ITEMS consecutive elements so the scan order is the memory order
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], acc = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    v[j] = (base + j < n) ? __ldg(&in[base + j]) : 0;
+    acc += v[j];
+  }
+  uint32_t tot;
+  uint32_t ex = block_exclusive_scan(acc, s_warp, tot) + sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    if (base + j < n) out[base + j] = ex;
+    ex += v[j];
+  }
+}
+size_t scan_ws_bytes(int64_t n) { return (size_t)(ceil_div(n, SCAN_TILE) + 1) * 4 + 256; }
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* total, void* ws, cudaStream_t st) {
+  if (n <= 0) {
+    if (total) LB_CUDA(cudaMemsetAsync(total, 0, 4, st));
+    return LB_OK;
+  }
+  int tiles = ceil_div(n, SCAN_TILE);
+  uint32_t* sums = (uint32_t*)ws;
+  scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(in, n, sums);
+  scan_sums_single<<<1, 1024, 0, st>>>(sums, tiles, total);
+  scan_tile_apply<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, sums);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ radix sort
+// Stable LSD radix sort, 8 bits per pass.  Each block owns a contiguous tile; each warp a contiguous
+// sub-range of it, ranked with match_any so equal digits keep their input order.
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_PER_WARP = 512;                 // keys per warp per tile
+constexpr int RS_TILE = RS_WARPS * RS_PER_WARP;  // 4096 keys per block
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                      uint32_t* __restrict__ hist /*[256][tiles]*/, int tiles) {
+  __shared__ uint32_t s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  for (int j = threadIdx.x; j < RS_TILE; j += RS_THREADS) {
+    int64_t i = base + j;
+    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 255], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * tiles + blockIdx.x] = s_h[threadIdx.x];
+}
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t* __restrict__ keys_in,
+                                                         const uint32_t* __restrict__ vals_in,
+                                                         uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                         int64_t n, int shift, const uint32_t* __restrict__ hist_scan,
+                                                         int tiles) {
+  __shared__ uint32_t s_cnt[RS_WARPS][256];   // per-warp digit counts, then per-warp running offsets
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = threadIdx.x; j < RS_WARPS * 256; j += RS_THREADS) (&s_cnt[0][0])[j] = 0;
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * RS_PER_WARP;
+  // pass A: per-warp digit histogram
+  for (int j = lane; j < RS_PER_WARP; j += 32) {
+    int64_t i = wbase + j;
+    if (i < n) atomicAdd(&s_cnt[warp][(keys_in[i] >> shift) & 255], 1u);
+  }
+  __syncthreads();
+  // exclusive prefix over warps per digit + global base of this tile
+  {
+    int d = threadIdx.x;   // RS_THREADS == 256 digits
+    uint32_t run = hist_scan[(int64_t)d * tiles + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      uint32_t c = s_cnt[w][d];
+      s_cnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // pass B: stable ranking inside each warp's sub-range, 32 keys at a time
+  for (int j0 = 0; j0 < RS_PER_WARP; j0 += 32) {
+    int64_t i = wbase + j0 + lane;
+    bool ok = i < n;
+    uint64_t key = ok ? keys_in[i] : 0;
+    uint32_t digit = ok ? (uint32_t)((key >> shift) & 255) : 256u + lane;   // inactive lanes never match
+    uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    uint32_t rank = __popc(peers & ((1u << lane) - 1));
+    uint32_t pos = 0;
+    if (ok) pos = s_cnt[warp][digit] + rank;
+    __syncwarp();
+    if (ok && rank == __popc(peers) - 1) s_cnt[warp][digit] = pos + 1;   // last peer advances the counter
+    __syncwarp();
+    if (ok) {
+      keys_out[pos] = key;
+      if (vals_in) vals_out[pos] = vals_in[i];
+    }
+  }
+}
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" size_t lb_sort_pairs_ws_bytes(int64_t n) {
+  int tiles = ceil_div(n > 0 ? n : 1, RS_TILE);
+  return align256((size_t)n * 8) + align256((size_t)n * 4) + align256((size_t)256 * tiles * 4) +
+         align256(scan_ws_bytes((int64_t)256 * tiles)) + 1024;
+}
+extern "C" int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* ws, size_t ws_bytes,
+                             void* stream) {
+  LB_CHECK_ARG(keys && ws, "null pointer");
+  LB_CHECK_ARG(end_bit > 0 && end_bit <= 64, "end_bit out of range");
+  if (ws_bytes < lb_sort_pairs_ws_bytes(n)) { set_error("lb_sort_pairs: workspace too small"); return LB_ECAP; }
+  if (n <= 1) return LB_OK;
+  cudaStream_t st = as_stream(stream);
+  int tiles = ceil_div(n, RS_TILE);
+  char* p = (char*)ws;
+  uint64_t* k2 = (uint64_t*)p; p += align256((size_t)n * 8);
+  uint32_t* v2 = (uint32_t*)p; p += align256((size_t)n * 4);
+  uint32_t* hist = (uint32_t*)p; p += align256((size_t)256 * tiles * 4);
+  void* sws = p;
+  int passes = (end_bit + 7) / 8;
+  uint64_t *ka = keys, *kb = k2;
+  uint32_t *va = vals, *vb = v2;
+  for (int ps = 0; ps < passes; ++ps) {
+    rs_hist<<<tiles, RS_THREADS, 0, st>>>(ka, n, ps * 8, hist, tiles);
+    int rc = exclusive_scan_u32(hist, hist, (int64_t)256 * tiles, nullptr, sws, st);
+    if (rc != LB_OK) return rc;
+    rs_scatter<<<tiles, RS_THREADS, 0, st>>>(ka, vals ? va : nullptr, kb, vb, n, ps * 8, hist, tiles);
+    uint64_t* tk = ka; ka = kb; kb = tk;
+    uint32_t* tv = va; va = vb; vb = tv;
+  }
+  if (ka != keys) {
+    LB_CUDA(cudaMemcpyAsync(keys, ka, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    if (vals) LB_CUDA(cudaMemcpyAsync(vals, va, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ C ABI: hash + table
+extern "C" int lb_abi_version(void) { return LB_ABI_VERSION; }
+extern "C" const char* lb_last_error(void) { return lb::g_err; }
+extern "C" int lb_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  LB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  LB_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sms) *sms = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  return LB_OK;
+}
+extern "C" int lb_hash(const int32_t* coords, int64_t n, int64_t* out, void* stream) {
+  LB_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(coords && out, "null pointer");
+  LB_CHECK_ARG(((uintptr_t)coords & 15) == 0, "coords must be 16-byte aligned");
+  hash_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>((const int4*)coords, n, out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_kernel_hash(const int32_t* coords, int64_t n, const int32_t* offsets, int k, int64_t* out,
+                              void* stream) {
+  LB_CHECK_ARG(n >= 0 && k > 0 && k <= 1024, "bad n or k");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(coords && offsets && out, "null pointer");
+  LB_CHECK_ARG(((uintptr_t)coords & 15) == 0, "coords must be 16-byte aligned");
+  kernel_hash_kernel<<<grid_for(n, 256), 256, 3 * k * sizeof(int), as_stream(stream)>>>((const int4*)coords, n, offsets,
+                                                                                       k, out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" size_t lb_hashtable_bytes(int64_t n) { return (size_t)table_capacity(n > 0 ? n : 1) * 12; }
+extern "C" int lb_hashtable_build(const int64_t* keys, int64_t n, void* table, size_t bytes, void* stream) {
+  LB_CHECK_ARG(table && n >= 0, "null table or n < 0");
+  if (bytes < lb_hashtable_bytes(n) || (bytes / 12) & (bytes / 12 - 1)) {
+    set_error("lb_hashtable_build: table_bytes must be lb_hashtable_bytes(n) (12 * power of two)");
+    return LB_ECAP;
+  }
+  cudaStream_t st = as_stream(stream);
+  uint64_t cap = bytes / 12;
+  LB_CUDA(cudaMemsetAsync(table, 0xFF, cap * 8, st));
+  LB_CUDA(cudaMemsetAsync((char*)table + cap * 8, 0x7F, cap * 4, st));
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(keys, "null keys");
+  table_build_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, n, table_view(table, bytes));
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_hashtable_query(const void* table, size_t bytes, const int64_t* q, int64_t nq, int64_t* out,
+                                  void* stream) {
+  LB_CHECK_ARG(table && nq >= 0, "null table or nq < 0");
+  if (nq == 0) return LB_OK;
+  LB_CHECK_ARG(q && out, "null pointer");
+  table_query_kernel<<<grid_for(nq, 256), 256, 0, as_stream(stream)>>>(table_view(table, bytes), q, nq, out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ downsample
+namespace lb {
+// key = (b << 48) | (x << 32) | (y << 16) | z  -- ascending key order == (b,x,y,z) lexicographic order.
+__global__ void ds_pack(const int4* __restrict__ coords, int64_t n, int sx, int sy, int sz, uint64_t* __restrict__ keys,
+                        int* __restrict__ err) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = __ldg(&coords[i]);
+    if ((c.x | c.y | c.z) < 0 || (c.x | c.y | c.z) > 65535 || c.w < 0 || c.w > 32767) atomicOr(err, 1);
+    uint32_t x = (uint32_t)(c.x / sx) * sx, y = (uint32_t)(c.y / sy) * sy, z = (uint32_t)(c.z / sz) * sz;
+    keys[i] = ((uint64_t)(uint32_t)c.w << 48) | ((uint64_t)(x & 65535) << 32) | ((uint64_t)(y & 65535) << 16) |
+              (uint64_t)(z & 65535);
+  }
+}
+__global__ void ds_flags(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ flags) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void ds_emit(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ flags,
+                        const uint32_t* __restrict__ pos, int64_t n, int4* __restrict__ out,
+                        const int* __restrict__ err, int* __restrict__ n_out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && *err) *n_out = -1;   // out-of-range coordinate: reported as n_out = -1
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (flags[i]) {
+      uint64_t k = keys[i];
+      out[pos[i]] = make_int4((int)((k >> 32) & 65535), (int)((k >> 16) & 65535), (int)(k & 65535), (int)(k >> 48));
+    }
+  }
+}
+}  // namespace lb
+
+extern "C" size_t lb_downsample_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return align256((size_t)n * 8) + 2 * align256((size_t)n * 4) + align256(scan_ws_bytes(n)) +
+         align256(lb_sort_pairs_ws_bytes(n)) + 512;
+}
+extern "C" int lb_downsample(const int32_t* coords, int64_t n, const int32_t ss[3], int batch_bits, int32_t* out_coords,
+                             int32_t* n_out, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && ss && n_out && ws, "null pointer or n < 0");
+  LB_CHECK_ARG(ss[0] > 0 && ss[1] > 0 && ss[2] > 0, "sample stride must be positive");
+  LB_CHECK_ARG(batch_bits >= 1 && batch_bits <= 15, "batch_bits in [1,15]");
+  if (ws_bytes < lb_downsample_ws_bytes(n)) { set_error("lb_downsample: workspace too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) { LB_CUDA(cudaMemsetAsync(n_out, 0, 4, st)); return LB_OK; }
+  LB_CHECK_ARG(coords && out_coords, "null pointer");
+  char* p = (char*)ws;
+  uint64_t* keys = (uint64_t*)p; p += align256((size_t)n * 8);
+  uint32_t* flags = (uint32_t*)p; p += align256((size_t)n * 4);
+  uint32_t* pos = (uint32_t*)p; p += align256((size_t)n * 4);
+  void* scan_ws = p; p += align256(scan_ws_bytes(n));
+  void* sort_ws = p; p += align256(lb_sort_pairs_ws_bytes(n));
+  int* err = (int*)p;
+  LB_CUDA(cudaMemsetAsync(err, 0, 4, st));
+  int g = grid_for(n, 256);
+  ds_pack<<<g, 256, 0, st>>>((const int4*)coords, n, ss[0], ss[1], ss[2], keys, err);
+  int rc = lb_sort_pairs(keys, nullptr, n, 48 + batch_bits, sort_ws, lb_sort_pairs_ws_bytes(n), stream);
+  if (rc != LB_OK) return rc;
+  ds_flags<<<g, 256, 0, st>>>(keys, n, flags);
+  rc = exclusive_scan_u32(flags, pos, n, (uint32_t*)n_out, scan_ws, st);
+  if (rc != LB_OK) return rc;
+  ds_emit<<<g, 256, 0, st>>>(keys, flags, pos, n, (int4*)out_coords, err, n_out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ kernel map
+namespace lb {
+__global__ void kmap_query_kernel(TableView t, const int4* __restrict__ out_coords, int64_t cap,
+                                  const int* __restrict__ n_dev, const int* __restrict__ offsets, int k,
+                                  int* __restrict__ nbr) {
+  extern __shared__ int s_off[];
+  for (int i = threadIdx.x; i < 3 * k; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  const int64_t n = n_dev ? (int64_t)*n_dev : cap;
+  // one thread per (offset, row): consecutive threads walk consecutive rows -> coalesced nbr writes
+  const int64_t total = cap * k;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(idx / cap);
+    int64_t o = idx - (int64_t)j * cap;
+    int r = -1;
+    if (o < n) {
+      int4 c = __ldg(&out_coords[o]);
+      r = table_find(t, (uint64_t)fnv60(c.x + s_off[3 * j], c.y + s_off[3 * j + 1], c.z + s_off[3 * j + 2], c.w));
+    }
+    nbr[idx] = r;
+  }
+}
+__global__ void kmap_flags(const int* __restrict__ nbr, int64_t total, uint32_t* __restrict__ flags) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = nbr[i] >= 0 ? 1u : 0u;
+}
+__global__ void kmap_emit(const int* __restrict__ nbr, const uint32_t* __restrict__ pos, int64_t n_out, int k,
+                          int2* __restrict__ nbmaps, int* __restrict__ nbsizes, const uint32_t* __restrict__ total) {
+  const int64_t tot = n_out * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < tot; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = nbr[i];
+    if (r >= 0) nbmaps[pos[i]] = make_int2(r, (int)(i % n_out));
+    if (i % n_out == 0) {
+      int j = (int)(i / n_out);
+      uint32_t end = (j + 1 < k) ? pos[(int64_t)(j + 1) * n_out] : *total;
+      nbsizes[j] = (int)(end - pos[i]);
+    }
+  }
+}
+}  // namespace lb
+
+extern "C" int lb_kmap_query(const void* table, size_t bytes, const int32_t* out_coords, int64_t cap,
+                             const int32_t* n_dev, const int32_t* offsets, int k, int32_t* nbr, void* stream) {
+  LB_CHECK_ARG(cap >= 0 && k > 0 && k <= 1024, "bad sizes");
+  if (cap == 0) return LB_OK;
+  LB_CHECK_ARG(table && out_coords && offsets && nbr, "null pointer");
+  kmap_query_kernel<<<grid_for(cap * k, 256), 256, 3 * k * sizeof(int), as_stream(stream)>>>(
+      table_view(table, bytes), (const int4*)out_coords, cap, n_dev, offsets, k, nbr);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" size_t lb_kmap_compact_ws_bytes(int64_t n_out, int k) {
+  int64_t t = (n_out > 0 ? n_out : 1) * (int64_t)k;
+  return 2 * align256((size_t)t * 4) + align256(scan_ws_bytes(t)) + 256;
+}
+extern "C" int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t* nbmaps, int32_t* nbsizes,
+                               int32_t* total, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n_out >= 0 && k > 0 && nbsizes && total && ws, "bad arguments");
+  if (ws_bytes < lb_kmap_compact_ws_bytes(n_out, k)) { set_error("lb_kmap_compact: workspace too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  if (n_out == 0) {
+    LB_CUDA(cudaMemsetAsync(nbsizes, 0, (size_t)k * 4, st));
+    LB_CUDA(cudaMemsetAsync(total, 0, 4, st));
+    return LB_OK;
+  }
+  LB_CHECK_ARG(nbr && nbmaps, "null pointer");
+  int64_t t = n_out * k;
+  char* p = (char*)ws;
+  uint32_t* flags = (uint32_t*)p; p += align256((size_t)t * 4);
+  uint32_t* pos = (uint32_t*)p; p += align256((size_t)t * 4);
+  void* sws = p;
+  int g = grid_for(t, 256);
+  kmap_flags<<<g, 256, 0, st>>>(nbr, t, flags);
+  int rc = exclusive_scan_u32(flags, pos, t, (uint32_t*)total, sws, st);
+  if (rc != LB_OK) return rc;
+  kmap_emit<<<g, 256, 0, st>>>(nbr, pos, n_out, k, (int2*)nbmaps, nbsizes, (const uint32_t*)total);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+namespace lb {
+__global__ void kmap_transpose_kernel(const int* __restrict__ nbr, int64_t nbr_ld, int64_t n_out, int k,
+                                      int* __restrict__ nbr_t, int64_t n_in) {
+  const int64_t total = n_out * k;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(t / n_out);
+    int64_t o = t - (int64_t)j * n_out;
+    int i = __ldg(&nbr[(int64_t)j * nbr_ld + o]);
+    if (i >= 0 && i < n_in) nbr_t[(int64_t)j * n_in + i] = (int)o;
+  }
+}
+}  // namespace lb
+extern "C" int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* nbr_t, int64_t n_in,
+                                 void* stream) {
+  LB_CHECK_ARG(n_out >= 0 && n_in >= 0 && k > 0 && nbr_ld >= n_out, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  if (n_in > 0) { LB_CHECK_ARG(nbr_t, "null nbr_t"); LB_CUDA(cudaMemsetAsync(nbr_t, 0xFF, (size_t)n_in * k * 4, st)); }
+  if (n_out == 0 || n_in == 0) return LB_OK;
+  LB_CHECK_ARG(nbr, "null nbr");
+  kmap_transpose_kernel<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, nbr_t, n_in);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

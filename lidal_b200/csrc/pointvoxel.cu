@@ -1,0 +1,293 @@
+// SPVCNN point<->voxel kernels, dtype casts, and the prob_inference tail (row A8).
+// All of these are HBM-bound: one warp walks one feature row with float4 accesses so every global
+// transaction is a full 128-byte line; indices are read once per row, not once per channel.
+#include "common.cuh"
+
+namespace lb {
+
+static inline int rows_grid(int64_t rows, int warps_per_block) {
+  int64_t b = (rows + warps_per_block - 1) / warps_per_block;
+  int64_t cap = (int64_t)sm_count() * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------------------------------- count
+__global__ void count_kernel(const int* __restrict__ idx, int64_t n, int* __restrict__ counts, int64_t m) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int v = __ldg(&idx[i]);
+    if (v >= 0 && v < m) atomicAdd(&counts[v], 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- voxelize
+// out[idx[i]] += feats[i] / counts[idx[i]]   (torchsparse voxelize_forward: fp32 atomics)
+__global__ void voxelize_fwd_kernel(const float* __restrict__ feats, const int* __restrict__ idx,
+                                    const int* __restrict__ counts, int64_t n, int64_t m, int c,
+                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int v = __ldg(&idx[i]);
+    if (v < 0 || v >= m) continue;
+    int cnt = __ldg(&counts[v]);
+    if (cnt == 0) continue;
+    float fc = (float)cnt;
+    for (int j = lane; j < c; j += 32) atomicAdd(&out[(int64_t)v * c + j], feats[i * c + j] / fc);
+  }
+}
+// grad_feats[i] = grad_out[idx[i]] / counts[idx[i]]
+__global__ void voxelize_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ idx,
+                                    const int* __restrict__ counts, int64_t n, int64_t m, int c,
+                                    float* __restrict__ gf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int v = __ldg(&idx[i]);
+    bool ok = v >= 0 && v < m && __ldg(&counts[v]) != 0;
+    float fc = ok ? (float)__ldg(&counts[v]) : 1.f;
+    for (int j = lane; j < c; j += 32) gf[i * c + j] = ok ? gout[(int64_t)v * c + j] / fc : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- devoxelize
+// out[i] = sum_k w[i,k] * feats[idx[i,k]]  (corner order 0..7, skipping -1) -- deterministic, no atomics
+template <int VEC>
+__global__ void devoxelize_fwd_kernel(const float* __restrict__ feats, const int* __restrict__ idx,
+                                      const float* __restrict__ w, int64_t n, int64_t m, int c,
+                                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int my_idx = -1;
+    float my_w = 0.f;
+    if (lane < 8) {
+      my_idx = __ldg(&idx[i * 8 + lane]);
+      my_w = __ldg(&w[i * 8 + lane]);
+      if (my_idx >= m) my_idx = -1;
+    }
+    for (int j = lane * VEC; j < c; j += 32 * VEC) {
+      float acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int r = __shfl_sync(0xffffffffu, my_idx, k);
+        float wk = __shfl_sync(0xffffffffu, my_w, k);
+        if (r >= 0) {
+          if (VEC == 4) {
+            float4 f = __ldg((const float4*)&feats[(int64_t)r * c + j]);
+            acc[0] += wk * f.x; acc[1] += wk * f.y; acc[2] += wk * f.z; acc[3] += wk * f.w;
+          } else {
+            acc[0] += wk * __ldg(&feats[(int64_t)r * c + j]);
+          }
+        }
+      }
+      if (VEC == 4) *(float4*)&out[i * c + j] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else out[i * c + j] = acc[0];
+    }
+  }
+}
+// grad_feats[idx[i,k]] += w[i,k] * grad_out[i]
+__global__ void devoxelize_bwd_kernel(const float* __restrict__ gout, const int* __restrict__ idx,
+                                      const float* __restrict__ w, int64_t n, int64_t m, int c,
+                                      float* __restrict__ gf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    for (int k = 0; k < 8; ++k) {
+      int r = __ldg(&idx[i * 8 + k]);
+      if (r < 0 || r >= m) continue;
+      float wk = __ldg(&w[i * 8 + k]);
+      for (int j = lane; j < c; j += 32) atomicAdd(&gf[(int64_t)r * c + j], wk * gout[i * c + j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- trilinear weights
+// F.calc_ti_weights: fp32 arithmetic in the same operation order as the torch expression.
+__global__ void ti_weights_kernel(const float* __restrict__ coords, int64_t ld, const int64_t* __restrict__ idx,
+                                  int64_t n, float scale, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[3], pf[3], pc[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      p[a] = __ldg(&coords[i * ld + a]);
+      pf[a] = (scale != 1.f) ? __fmul_rn(floorf(__fdiv_rn(p[a], scale)), scale) : floorf(p[a]);
+      pc[a] = __fadd_rn(pf[a], scale);
+    }
+    float hx = __fsub_rn(pc[0], p[0]), lx = __fsub_rn(p[0], pf[0]);
+    float hy = __fsub_rn(pc[1], p[1]), ly = __fsub_rn(p[1], pf[1]);
+    float hz = __fsub_rn(pc[2], p[2]), lz = __fsub_rn(p[2], pf[2]);
+    float w[8];
+    w[0] = __fmul_rn(__fmul_rn(hx, hy), hz); w[1] = __fmul_rn(__fmul_rn(hx, hy), lz);
+    w[2] = __fmul_rn(__fmul_rn(hx, ly), hz); w[3] = __fmul_rn(__fmul_rn(hx, ly), lz);
+    w[4] = __fmul_rn(__fmul_rn(lx, hy), hz); w[5] = __fmul_rn(__fmul_rn(lx, hy), lz);
+    w[6] = __fmul_rn(__fmul_rn(lx, ly), hz); w[7] = __fmul_rn(__fmul_rn(lx, ly), lz);
+    const float s3 = scale * scale * scale;    // python: scale ** 3 on an int stride -> exact in fp32 here
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (scale != 1.f) w[k] = __fdiv_rn(w[k], s3);
+      if (__ldg(&idx[(int64_t)k * n + i]) == -1) w[k] = 0.f;
+      sum = __fadd_rn(sum, w[k]);
+    }
+    sum = __fadd_rn(sum, 1e-8f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[(int64_t)k * n + i] = __fdiv_rn(w[k], sum);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- casts
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, int64_t ld_s, D* __restrict__ dst, int64_t ld_d, int64_t rows,
+                            int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t / cols, c = t - r * cols;
+    dst[r * ld_d + c] = (D)(float)src[r * ld_s + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------- TTA tail
+// prob[p] = mean_v softmax(logits[inverse[v*n_pts + p]]); pred = argmax.  One warp per point: lane c owns
+// class c (n_cls <= 32); the 8 gathered logit rows are 76-byte segments -> 1-2 sectors each.
+__global__ void tta_kernel(const float* __restrict__ logits, int64_t n_vox, int n_cls, const int64_t* __restrict__ inv,
+                           int reps, int64_t n_pts, float* __restrict__ prob, int64_t* __restrict__ pred) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < n_pts; p += nwarps) {
+    float acc = 0.f;
+    for (int v = 0; v < reps; ++v) {
+      int64_t row = __ldg(&inv[(int64_t)v * n_pts + p]);
+      float x = (lane < n_cls && row >= 0 && row < n_vox) ? __ldg(&logits[row * n_cls + lane]) : -INFINITY;
+      float mx = x;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      float e = lane < n_cls ? expf(x - mx) : 0.f;
+      float s = e;
+#pragma unroll
+      for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      acc = __fadd_rn(acc, __fdiv_rn(e, s));            // np.mean(axis=0): sequential adds over views
+    }
+    float pm = __fdiv_rn(acc, (float)reps);
+    if (lane < n_cls) prob[p * n_cls + lane] = pm;
+    // argmax with first-index tie break (np.argmax)
+    float bv = lane < n_cls ? pm : -INFINITY;
+    int bi = lane;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, d);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) pred[p] = bi;
+  }
+}
+
+}  // namespace lb
+using namespace lb;
+
+extern "C" int lb_count(const int32_t* idx, int64_t n, int32_t* counts, int64_t m, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0, "negative size");
+  cudaStream_t st = as_stream(stream);
+  if (m > 0) { LB_CHECK_ARG(counts, "null counts"); LB_CUDA(cudaMemsetAsync(counts, 0, (size_t)m * 4, st)); }
+  if (n == 0 || m == 0) return LB_OK;
+  LB_CHECK_ARG(idx, "null idx");
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  count_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(idx, n, counts, m);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_voxelize_fwd(const float* feats, const int32_t* idx, const int32_t* counts, int64_t n, int64_t m,
+                               int c, float* out, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  if (m > 0) { LB_CHECK_ARG(out, "null out"); LB_CUDA(cudaMemsetAsync(out, 0, (size_t)m * c * 4, st)); }
+  if (n == 0 || m == 0) return LB_OK;
+  LB_CHECK_ARG(feats && idx && counts, "null pointer");
+  voxelize_fwd_kernel<<<rows_grid(n, 8), 256, 0, st>>>(feats, idx, counts, n, m, c, out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_voxelize_bwd(const float* gout, const int32_t* idx, const int32_t* counts, int64_t n, int64_t m,
+                               int c, float* gf, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0, "bad sizes");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(gout && idx && counts && gf, "null pointer");
+  voxelize_bwd_kernel<<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(gout, idx, counts, n, m, c, gf);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_devoxelize_fwd(const float* feats, const int32_t* idx, const float* w, int64_t n, int64_t m, int c,
+                                 float* out, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0, "bad sizes");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(feats && idx && w && out, "null pointer");
+  bool vec = (c % 4 == 0) && (((uintptr_t)feats | (uintptr_t)out) & 15) == 0;
+  if (vec) devoxelize_fwd_kernel<4><<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(feats, idx, w, n, m, c, out);
+  else devoxelize_fwd_kernel<1><<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(feats, idx, w, n, m, c, out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_devoxelize_bwd(const float* gout, const int32_t* idx, const float* w, int64_t n, int64_t m, int c,
+                                 float* gf, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  if (m > 0) { LB_CHECK_ARG(gf, "null grad"); LB_CUDA(cudaMemsetAsync(gf, 0, (size_t)m * c * 4, st)); }
+  if (n == 0 || m == 0) return LB_OK;
+  LB_CHECK_ARG(gout && idx && w, "null pointer");
+  devoxelize_bwd_kernel<<<rows_grid(n, 8), 256, 0, st>>>(gout, idx, w, n, m, c, gf);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_ti_weights(const float* coords, int64_t ld, const int64_t* idx, int64_t n, float scale, float* out,
+                             void* stream) {
+  LB_CHECK_ARG(n >= 0 && ld >= 3 && scale > 0.f, "bad sizes");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(coords && idx && out, "null pointer");
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  ti_weights_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(coords, ld, idx, n, scale, out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+template <typename S>
+static int cast_dispatch(const S* src, int64_t ld_s, void* dst, int dd, int64_t ld_d, int64_t rows, int64_t cols,
+                         cudaStream_t st) {
+  int64_t blocks = (rows * cols + 255) / 256, cap = (int64_t)sm_count() * 32;
+  int g = (int)(blocks > cap ? cap : blocks);
+  if (dd == LB_DT_F32) cast_kernel<S, float><<<g, 256, 0, st>>>(src, ld_s, (float*)dst, ld_d, rows, cols);
+  else if (dd == LB_DT_BF16) cast_kernel<S, __nv_bfloat16><<<g, 256, 0, st>>>(src, ld_s, (__nv_bfloat16*)dst, ld_d, rows, cols);
+  else if (dd == LB_DT_F16) cast_kernel<S, __half><<<g, 256, 0, st>>>(src, ld_s, (__half*)dst, ld_d, rows, cols);
+  else { set_error("lb_cast: bad dst dtype"); return LB_EINVAL; }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_cast(const void* src, int sd, int64_t ld_s, void* dst, int dd, int64_t ld_d, int64_t rows,
+                       int64_t cols, void* stream) {
+  LB_CHECK_ARG(rows >= 0 && cols >= 0 && ld_s >= cols && ld_d >= cols, "bad sizes");
+  if (rows == 0 || cols == 0) return LB_OK;
+  LB_CHECK_ARG(src && dst, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (sd == LB_DT_F32) return cast_dispatch((const float*)src, ld_s, dst, dd, ld_d, rows, cols, st);
+  if (sd == LB_DT_BF16) return cast_dispatch((const __nv_bfloat16*)src, ld_s, dst, dd, ld_d, rows, cols, st);
+  if (sd == LB_DT_F16) return cast_dispatch((const __half*)src, ld_s, dst, dd, ld_d, rows, cols, st);
+  set_error("lb_cast: bad src dtype");
+  return LB_EINVAL;
+}
+
+extern "C" int lb_tta_softmax_mean_argmax(const float* logits, int64_t n_vox, int n_cls, const int64_t* inverse,
+                                          int reps, int64_t n_pts, float* prob, int64_t* pred, void* stream) {
+  LB_CHECK_ARG(n_cls > 0 && n_cls <= 32, "n_cls must be in [1,32]");
+  LB_CHECK_ARG(reps > 0 && n_pts >= 0 && n_vox >= 0, "bad sizes");
+  if (n_pts == 0) return LB_OK;
+  LB_CHECK_ARG(logits && inverse && prob && pred, "null pointer");
+  tta_kernel<<<rows_grid(n_pts, 8), 256, 0, as_stream(stream)>>>(logits, n_vox, n_cls, inverse, reps, n_pts, prob, pred);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

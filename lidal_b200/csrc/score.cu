@@ -1,0 +1,376 @@
+// LiDAL inter-frame uncertainty scoring on device (SURVEY.md section 8 rows A9, A10, A11-device part).
+//
+// Restates score/sv_level/LiDAL.py:59-103.  The pickled float64 KD-tree of the reference is replaced by a
+// per-frame uniform hash grid, but the match rule is unchanged: the exact float64 nearest neighbour of
+// every query point in each neighbouring frame, accepted iff sqrt(d2) <= dis_thresh.  All floating-point
+// steps follow the reference's evaluation order and precisions so scores are reproducible to the last bit
+// wherever libm agrees:
+//   kl_div / entr : evaluated in double, rounded to float  (scipy ufunc loops d_dd__As_ff_f)
+//   np.sum(axis=1) over classes: float32 pairwise order of numpy (8 accumulators, tree, sequential tail)
+//   interd accumulates in double; sum_prob in float, neighbours in nei_ids order.
+// One warp owns one query point: lanes 0..26 probe the 27 surrounding cells, then lane c owns class c.
+#include "common.cuh"
+
+namespace lb {
+
+struct GridHeader {
+  double cell;
+  int64_t n;
+  uint64_t cap;
+  uint64_t pad;
+};
+struct GridView {
+  double cell;
+  uint64_t mask;
+  const unsigned long long* keys;
+  const int* head;
+  const int* next;
+};
+__host__ __device__ inline size_t grid_bytes_for(int64_t n) {
+  uint64_t cap = table_capacity(n);
+  return sizeof(GridHeader) + cap * 8 + cap * 4 + (size_t)(n > 0 ? n : 1) * 4 + 64;
+}
+__device__ __forceinline__ GridView grid_view(const void* g) {
+  const GridHeader* h = (const GridHeader*)g;
+  GridView v;
+  v.cell = h->cell;
+  v.mask = h->cap - 1;
+  v.keys = (const unsigned long long*)((const char*)g + sizeof(GridHeader));
+  v.head = (const int*)((const char*)v.keys + h->cap * 8);
+  v.next = v.head + h->cap;
+  return v;
+}
+constexpr long long CELL_BIAS = 1 << 20;
+__device__ __forceinline__ long long cell_of(double x, double cell) {
+  long long c = (long long)floor(x / cell);
+  return c < -CELL_BIAS + 2 ? -CELL_BIAS + 2 : (c > CELL_BIAS - 2 ? CELL_BIAS - 2 : c);
+}
+__device__ __forceinline__ uint64_t cell_key(long long ix, long long iy, long long iz) {
+  return ((uint64_t)(ix + CELL_BIAS) << 42) | ((uint64_t)(iy + CELL_BIAS) << 21) | (uint64_t)(iz + CELL_BIAS);
+}
+
+__global__ void grid_init_kernel(void* grid, double cell, int64_t n, uint64_t cap) {
+  GridHeader* h = (GridHeader*)grid;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { h->cell = cell; h->n = n; h->cap = cap; h->pad = 0; }
+  unsigned long long* keys = (unsigned long long*)((char*)grid + sizeof(GridHeader));
+  int* head = (int*)((char*)keys + cap * 8);
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    keys[i] = LB_EMPTY_KEY;
+    head[i] = -1;
+  }
+}
+__global__ void grid_insert_kernel(const double* __restrict__ xyz, int64_t n, double cell, void* grid, uint64_t cap) {
+  unsigned long long* keys = (unsigned long long*)((char*)grid + sizeof(GridHeader));
+  int* head = (int*)((char*)keys + cap * 8);
+  int* next = head + cap;
+  const uint64_t mask = cap - 1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = cell_key(cell_of(xyz[3 * i], cell), cell_of(xyz[3 * i + 1], cell), cell_of(xyz[3 * i + 2], cell));
+    uint64_t slot = mix64(key) & mask;
+    while (true) {
+      unsigned long long prev = atomicCAS(&keys[slot], LB_EMPTY_KEY, (unsigned long long)key);
+      if (prev == LB_EMPTY_KEY || prev == key) break;
+      slot = (slot + 1) & mask;
+    }
+    next[i] = atomicExch(&head[slot], (int)i);
+  }
+}
+
+// numpy float32 pairwise sum over n <= 32 lane-resident values (lane j holds a[j]); result valid on lane 0.
+__device__ __forceinline__ float np_pairwise_sum32(float a, int n, int lane) {
+  const unsigned full = 0xffffffffu;
+  if (n < 8) {
+    float res = 0.f;
+    for (int j = 0; j < n; ++j) res = __fadd_rn(res, __shfl_sync(full, a, j));
+    return res;
+  }
+  float r = a;                                    // lanes 0..7 hold r[j]
+  const int body = n - (n % 8);
+  for (int i = 8; i < body; i += 8) {
+    float t = __shfl_sync(full, a, (lane & 7) + i);
+    r = __fadd_rn(r, t);
+  }
+  float s1 = __fadd_rn(r, __shfl_down_sync(full, r, 1));      // valid on even lanes: r[j] + r[j+1]
+  float s2 = __fadd_rn(s1, __shfl_down_sync(full, s1, 2));    // valid on lanes 0,4
+  float res = __fadd_rn(s2, __shfl_down_sync(full, s2, 4));   // valid on lane 0
+  for (int i = body; i < n; ++i) res = __fadd_rn(res, __shfl_sync(full, a, i));
+  return res;
+}
+
+constexpr int MAX_NBR = 32;
+struct FrameRef {
+  const void* grid;
+  const double* xyz;
+  const float* prob;
+  int64_t n;
+};
+struct ScoreParams {
+  FrameRef nbr[MAX_NBR];
+  int n_nbr;
+};
+
+__global__ void __launch_bounds__(256)
+interframe_kernel(const double* __restrict__ q_xyz, const float* __restrict__ q_prob, int64_t nq, int n_cls,
+                  const __grid_constant__ ScoreParams P, double thresh, double* __restrict__ interd_out,
+                  float* __restrict__ intere_out, int* __restrict__ count_out, int* __restrict__ nn_out) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float eps = 0.00001f;
+  const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
+  for (int64_t p = warp; p < nq; p += nwarps) {
+    const double qx = __ldg(&q_xyz[3 * p]), qy = __ldg(&q_xyz[3 * p + 1]), qz = __ldg(&q_xyz[3 * p + 2]);
+    const float q = lane < n_cls ? __ldg(&q_prob[p * n_cls + lane]) : 0.f;
+    float sum = q;
+    double interd = 0.0;
+    int cnt = 1;
+    for (int f = 0; f < P.n_nbr; ++f) {
+      const GridView g = grid_view(P.nbr[f].grid);
+      const double* __restrict__ nxyz = P.nbr[f].xyz;
+      double best = INFINITY;
+      int bi = 0x7fffffff;
+      if (lane < 27) {
+        uint64_t key = cell_key(cell_of(qx, g.cell) + dx, cell_of(qy, g.cell) + dy, cell_of(qz, g.cell) + dz);
+        uint64_t slot = mix64(key) & g.mask;
+        int j = -1;
+        while (true) {
+          unsigned long long k = __ldg(&g.keys[slot]);
+          if (k == key) { j = __ldg(&g.head[slot]); break; }
+          if (k == LB_EMPTY_KEY) break;
+          slot = (slot + 1) & g.mask;
+        }
+        for (; j >= 0; j = __ldg(&g.next[j])) {
+          // sklearn euclidean rdist: d = 0; d += t*t per axis, no FMA contraction
+          double tx = __dsub_rn(qx, __ldg(&nxyz[3 * (int64_t)j]));
+          double ty = __dsub_rn(qy, __ldg(&nxyz[3 * (int64_t)j + 1]));
+          double tz = __dsub_rn(qz, __ldg(&nxyz[3 * (int64_t)j + 2]));
+          double d2 = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+          if (d2 < best || (d2 == best && j < bi)) { best = d2; bi = j; }
+        }
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        double ob = __shfl_xor_sync(full, best, d);
+        int oi = __shfl_xor_sync(full, bi, d);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      const bool match = (bi != 0x7fffffff) && (__dsqrt_rn(best) <= thresh);
+      if (nn_out && lane == 0) nn_out[(int64_t)f * nq + p] = match ? bi : -1;
+      if (match) {
+        const float pn = lane < n_cls ? __ldg(&P.nbr[f].prob[(int64_t)bi * n_cls + lane]) : 0.f;
+        sum = __fadd_rn(sum, pn);
+        float kl = 0.f;
+        if (lane < n_cls) {
+          const double x = (double)__fadd_rn(q, eps), y = (double)__fadd_rn(pn, eps);
+          kl = (float)__dadd_rn(__dsub_rn(__dmul_rn(x, log(__ddiv_rn(x, y))), x), y);
+        }
+        const float ks = np_pairwise_sum32(kl, n_cls, lane);
+        interd += (double)ks;      // only lane 0's value is meaningful
+        cnt += 1;
+      }
+    }
+    // LiDAL.py:75-76  sum_prob /= map_count (f32 / f64 -> f32);  entropy(pk) renormalises, natural log
+    const float pm = lane < n_cls ? (float)__ddiv_rn((double)sum, (double)cnt) : 0.f;
+    float s = np_pairwise_sum32(pm, n_cls, lane);
+    s = __shfl_sync(full, s, 0);
+    const float pk = __fdiv_rn(pm, s);
+    float en = 0.f;
+    if (lane < n_cls) {
+      const double pd = (double)pk;
+      en = pd > 0.0 ? (float)__dmul_rn(-pd, log(pd)) : (pd == 0.0 ? 0.f : -INFINITY);
+    }
+    const float H = np_pairwise_sum32(en, n_cls, lane);
+    if (lane == 0) {
+      // LiDAL.py:79-81
+      const int m = cnt - 1;
+      interd_out[p] = m > 0 ? __ddiv_rn(interd, (double)m) : interd;
+      intere_out[p] = H;
+      if (count_out) count_out[p] = m;
+    }
+  }
+}
+
+// One block per region: fixed-order double reductions => deterministic results.
+__global__ void __launch_bounds__(256)
+region_reduce_kernel(const double* __restrict__ interd, const float* __restrict__ intere, const double* __restrict__ xyz,
+                     const int* __restrict__ ptr, const int* __restrict__ pts, float* __restrict__ sv_d,
+                     float* __restrict__ sv_e, int64_t* __restrict__ sv_n, float* __restrict__ sv_c) {
+  __shared__ double sh[5][256];
+  const int r = blockIdx.x;
+  const int b = ptr[r], e = ptr[r + 1];
+  double a[5] = {0, 0, 0, 0, 0};
+  for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+    int p = __ldg(&pts[i]);
+    a[0] += interd[p];
+    a[1] += (double)intere[p];
+    a[2] += xyz[3 * (int64_t)p];
+    a[3] += xyz[3 * (int64_t)p + 1];
+    a[4] += xyz[3 * (int64_t)p + 2];
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) sh[v][threadIdx.x] = a[v];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+#pragma unroll
+      for (int v = 0; v < 5; ++v) sh[v][threadIdx.x] += sh[v][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = (double)(e - b);
+    sv_d[r] = (float)(sh[0][0] / n);
+    sv_e[r] = (float)(sh[1][0] / n);
+    if (sv_n) sv_n[r] = e - b;
+    if (sv_c) {
+      sv_c[3 * r] = (float)(sh[2][0] / n);
+      sv_c[3 * r + 1] = (float)(sh[3][0] / n);
+      sv_c[3 * r + 2] = (float)(sh[4][0] / n);
+    }
+  }
+}
+
+// float -> order-preserving uint32
+__global__ void argsort_prepare(const float* __restrict__ keys, int64_t n, uint64_t* __restrict__ k64,
+                                uint32_t* __restrict__ vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t u = __float_as_uint(keys[i]);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    k64[i] = u;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+__global__ void f32_to_f64_xyz(const float* __restrict__ c, int64_t n3, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)c[i];
+}
+
+// LiDAL.py:252  dist = np.sqrt(np.square(a - b).sum()) in float32; in range iff dist < radius.
+__global__ void region_pairs_kernel(const float* __restrict__ c, int64_t n, float radius, const void* grid,
+                                    int* __restrict__ row_ptr, int* __restrict__ nbr_idx, int fill) {
+  const GridView g = grid_view(grid);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float ax = c[3 * i], ay = c[3 * i + 1], az = c[3 * i + 2];
+    const long long cx = cell_of((double)ax, g.cell), cy = cell_of((double)ay, g.cell), cz = cell_of((double)az, g.cell);
+    int cnt = 0;
+    const int base = fill ? row_ptr[i] : 0;
+    for (int t = 0; t < 27; ++t) {
+      uint64_t key = cell_key(cx + t / 9 - 1, cy + (t / 3) % 3 - 1, cz + t % 3 - 1);
+      uint64_t slot = mix64(key) & g.mask;
+      int j = -1;
+      while (true) {
+        unsigned long long k = __ldg(&g.keys[slot]);
+        if (k == key) { j = __ldg(&g.head[slot]); break; }
+        if (k == LB_EMPTY_KEY) break;
+        slot = (slot + 1) & g.mask;
+      }
+      for (; j >= 0; j = __ldg(&g.next[j])) {
+        if (j == i) continue;
+        float ex = __fsub_rn(ax, c[3 * (int64_t)j]), ey = __fsub_rn(ay, c[3 * (int64_t)j + 1]),
+              ez = __fsub_rn(az, c[3 * (int64_t)j + 2]);
+        float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez)));
+        if (d < radius) {
+          if (fill) nbr_idx[base + cnt] = j;
+          ++cnt;
+        }
+      }
+    }
+    if (!fill) row_ptr[i] = cnt;
+  }
+}
+
+}  // namespace lb
+using namespace lb;
+
+static inline int grid1d(int64_t n, int block) {
+  int64_t b = (n + block - 1) / block, cap = (int64_t)sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" size_t lb_frame_grid_bytes(int64_t n) { return grid_bytes_for(n); }
+extern "C" int lb_frame_grid_build(const double* xyz, int64_t n, double cell, void* grid, size_t bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && grid && cell > 0, "bad arguments");
+  LB_CHECK_ARG(((uintptr_t)grid & 7) == 0, "grid must be 8-byte aligned");
+  if (bytes < grid_bytes_for(n)) { set_error("lb_frame_grid_build: grid buffer too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  uint64_t cap = table_capacity(n);
+  grid_init_kernel<<<grid1d((int64_t)cap, 256), 256, 0, st>>>(grid, cell, n, cap);
+  if (n > 0) {
+    LB_CHECK_ARG(xyz, "null xyz");
+    grid_insert_kernel<<<grid1d(n, 256), 256, 0, st>>>(xyz, n, cell, grid, cap);
+  }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" int lb_interframe_score(const double* q_xyz, const float* q_prob, int64_t nq, int n_cls,
+                                   const lb_frame_ref* nbrs, int n_nbr, double dis_thresh, double cell,
+                                   double* interd, float* intere, int32_t* count, int32_t* nn_out, void* stream) {
+  LB_CHECK_ARG(nq >= 0 && n_cls > 0 && n_cls <= 32, "n_cls must be in [1,32]");
+  LB_CHECK_ARG(n_nbr >= 0 && n_nbr <= MAX_NBR, "at most 32 neighbour frames");
+  LB_CHECK_ARG(cell >= dis_thresh * 1.001, "grid cell must exceed dis_thresh (27-cell probe exactness)");
+  if (nq == 0) return LB_OK;
+  LB_CHECK_ARG(q_xyz && q_prob && interd && intere && (nbrs || n_nbr == 0), "null pointer");
+  ScoreParams P;
+  P.n_nbr = n_nbr;
+  for (int i = 0; i < n_nbr; ++i) {
+    LB_CHECK_ARG(nbrs[i].grid && nbrs[i].xyz && nbrs[i].prob, "null neighbour frame");
+    P.nbr[i].grid = nbrs[i].grid; P.nbr[i].xyz = nbrs[i].xyz; P.nbr[i].prob = nbrs[i].prob; P.nbr[i].n = nbrs[i].n;
+  }
+  int64_t blocks = (nq + 7) / 8, cap = (int64_t)sm_count() * 8;
+  interframe_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(
+      q_xyz, q_prob, nq, n_cls, P, dis_thresh, interd, intere, count, nn_out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" int lb_region_reduce(const double* interd, const float* intere, const double* xyz, const int32_t* region_ptr,
+                                const int32_t* region_pts, int n_regions, float* sv_d, float* sv_e, int64_t* sv_n,
+                                float* sv_c, void* stream) {
+  LB_CHECK_ARG(n_regions >= 0, "n_regions < 0");
+  if (n_regions == 0) return LB_OK;
+  LB_CHECK_ARG(interd && intere && xyz && region_ptr && region_pts && sv_d && sv_e, "null pointer");
+  region_reduce_kernel<<<n_regions, 256, 0, as_stream(stream)>>>(interd, intere, xyz, region_ptr, region_pts, sv_d, sv_e,
+                                                                 sv_n, sv_c);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" size_t lb_argsort_ws_bytes(int64_t n) { return lb_sort_pairs_ws_bytes(n) + (size_t)(n > 0 ? n : 1) * 12 + 512; }
+extern "C" int lb_argsort_f32(const float* keys, int64_t n, int32_t* order, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && ws, "bad arguments");
+  if (ws_bytes < lb_argsort_ws_bytes(n)) { set_error("lb_argsort_f32: workspace too small"); return LB_ECAP; }
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(keys && order, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  uint64_t* k64 = (uint64_t*)ws;
+  size_t off = ((size_t)n * 8 + 255) & ~(size_t)255;
+  void* sws = (char*)ws + off;
+  argsort_prepare<<<grid1d(n, 256), 256, 0, st>>>(keys, n, k64, (uint32_t*)order);
+  int rc = lb_sort_pairs(k64, (uint32_t*)order, n, 32, sws, ws_bytes - off, stream);
+  if (rc != LB_OK) return rc;
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" size_t lb_region_pairs_ws_bytes(int64_t n) {
+  return (((size_t)(n > 0 ? n : 1) * 24 + 255) & ~(size_t)255) + grid_bytes_for(n) + 256;
+}
+extern "C" int lb_region_pairs(const float* centers, int64_t n, float radius, int32_t* row_counts_or_ptr,
+                               int32_t* nbr_idx, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && radius > 0 && ws, "bad arguments");
+  if (ws_bytes < lb_region_pairs_ws_bytes(n)) { set_error("lb_region_pairs: workspace too small"); return LB_ECAP; }
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(centers && row_counts_or_ptr, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  double* xyz = (double*)ws;
+  void* grid = (char*)ws + (((size_t)n * 24 + 255) & ~(size_t)255);
+  f32_to_f64_xyz<<<grid1d(n * 3, 256), 256, 0, st>>>(centers, n * 3, xyz);
+  int rc = lb_frame_grid_build(xyz, n, (double)radius * 1.01, grid, grid_bytes_for(n), stream);
+  if (rc != LB_OK) return rc;
+  region_pairs_kernel<<<grid1d(n, 128), 128, 0, st>>>(centers, n, radius, grid, row_counts_or_ptr, nbr_idx,
+                                                      nbr_idx ? 1 : 0);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

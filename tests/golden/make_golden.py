@@ -110,18 +110,23 @@ def gen_selection():
     cases = {}
     for name, tpn in (("tight", 700_000), ("loose", 100_000_000)):
         sv_flags, d, e, pn, c = selection_inputs()
+        if name == "loose":
+            # np.argsort's order among exact ties (D == 0) is an accident of its quicksort; the loose case walks every
+            # candidate, so give it distinct keys.  The tight case keeps the zeros (SL pass skips them, LiDAL.py:298).
+            z = np.where(d == 0)[0]
+            d = d.copy(); d[z] = (1e-6 * (1 + np.arange(len(z)))).astype(np.float32)
         ns = dict(np=np, sv_flags=sv_flags.copy(), sv_interds=d, sv_interes=e, sv_pnums=pn, sv_centers=c,
                   train_point_num=tpn)
         with redirect_stdout(io.StringIO()):
             exec(compile(block, "LiDAL.py[225:325]", "exec"), ns)
         mine = orc.select_regions(sv_flags.copy(), d, e, pn, c, tpn)
         assert np.array_equal(ns["sv_flags"], mine), name
-        cases[name] = (tpn, ns["sv_flags"])
+        cases[name] = (tpn, ns["sv_flags"], d)
         print(f"selection[{name}]: oracle == reference block; flags1={int((mine == 1).sum())} flags2={int((mine == 2).sum())}")
     sv_flags, d, e, pn, c = selection_inputs()
     np.savez_compressed(f"{OUT}/selection.npz", sv_flags=sv_flags, sv_interds=d, sv_interes=e, sv_pnums=pn,
                         sv_centers=c, tight_tpn=cases["tight"][0], tight_out=cases["tight"][1],
-                        loose_tpn=cases["loose"][0], loose_out=cases["loose"][1])
+                        loose_tpn=cases["loose"][0], loose_out=cases["loose"][1], loose_interds=cases["loose"][2])
 
 
 def fnv_python(c4):

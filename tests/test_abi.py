@@ -1,0 +1,55 @@
+"""CPU: the C-ABI library loads and exports every symbol include/lidal_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from lidal_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lidal_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lidal_b200.build import build_library
+    build_library()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/lidal_b200.h but not exported"
+
+
+def test_python_binding_covers_header():
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    assert _lib.lib().lb_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.ConvArgs) == 160 or ctypes.sizeof(_lib.ConvArgs) % 8 == 0
+    assert ctypes.sizeof(_lib.FrameRef) == 32
+
+
+def test_no_cpu_fallback():
+    import lidal_b200.compat as ts
+    with pytest.raises(_lib.LidalError):
+        ts.nn.functional.sphash(torch.zeros((4, 4), dtype=torch.int))
+    with pytest.raises(_lib.LidalError):
+        ts.nn.functional.spcount(torch.zeros(4, dtype=torch.int), 4)
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    assert L.lb_hash(None, -1, None, None) == -1
+    assert b"n < 0" in L.lb_last_error()
+    assert L.lb_hashtable_bytes(1000) == 2048 * 12
+    a = _lib.ConvArgs()
+    a.n_out = 5
+    assert L.lb_conv_fwd(ctypes.byref(a), None) == -1

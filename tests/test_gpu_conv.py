@@ -1,0 +1,133 @@
+"""GPU: sparse convolution through lb_conv_fwd against the oracle's gather-mm-scatter loop, and whole-network logits.
+
+Tolerance (BASELINE.json north_star): conv and logit outputs within 1e-2 relative error (16-bit operands, fp32
+accumulation) of the fp32 reference; measured as max |a-b| / max |b| per tensor and as relative L2 error."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-2
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)), float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import lidal_b200.compat as ts
+    return ts
+
+
+def _sparse_input(oracle_ts, small_scan, cin, seed=0):
+    coords = torch.from_numpy(small_scan[0])
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(coords.shape[0], cin, generator=g)
+    return coords, feats
+
+
+@pytest.mark.parametrize("cin,cout,ks,stride,force_simt", [
+    (4, 32, 3, 1, False), (32, 32, 3, 1, False), (32, 64, 3, 1, True), (64, 64, 2, 2, False), (96, 96, 3, 1, False),
+    (128, 96, 3, 1, False), (192, 128, 3, 1, False), (64, 128, 1, 1, False), (256, 256, 3, 1, False), (384, 256, 3, 1, False),
+    (17, 19, 3, 1, False)])
+def test_conv_forward_vs_oracle(ts, oracle_ts, small_scan, cin, cout, ks, stride, force_simt):
+    coords, feats = _sparse_input(oracle_ts, small_scan, cin)
+    conv_o = oracle_ts.nn.Conv3d(cin, cout, kernel_size=ks, stride=stride)
+    conv_g = ts.nn.Conv3d(cin, cout, kernel_size=ks, stride=stride).cuda()
+    conv_g.load_state_dict(conv_o.state_dict())
+    with torch.no_grad():
+        want = conv_o(oracle_ts.SparseTensor(feats, coords))
+        if force_simt:
+            F = ts.nn.functional
+            km = F.build_kernel_map(coords.cuda(), (1, 1, 1), (ks,) * 3, (stride,) * 3, (1, 1, 1))
+            w = F.pack_weight(conv_g.kernel, torch.bfloat16)
+            got_f = F.conv_forward(feats.cuda().bfloat16(), w, km.nbr, km.n_out, force_simt=True)
+            got_c = km.out_coords
+        else:
+            got = conv_g(ts.SparseTensor(feats.cuda(), coords.cuda()))
+            got_f, got_c = got.F, got.C
+            assert got.s == want.s
+    assert torch.equal(got_c.cpu(), want.C)
+    mx, l2 = rel_err(got_f.cpu(), want.F)
+    assert mx < REL_TOL and l2 < REL_TOL, (mx, l2)
+
+
+def test_transposed_conv_vs_oracle(ts, oracle_ts, small_scan):
+    coords, feats = _sparse_input(oracle_ts, small_scan, 64)
+    down_o = oracle_ts.nn.Conv3d(64, 64, kernel_size=2, stride=2)
+    up_o = oracle_ts.nn.Conv3d(64, 96, kernel_size=2, stride=2, transposed=True)
+    down_g = ts.nn.Conv3d(64, 64, kernel_size=2, stride=2).cuda()
+    up_g = ts.nn.Conv3d(64, 96, kernel_size=2, stride=2, transposed=True).cuda()
+    down_g.load_state_dict(down_o.state_dict()); up_g.load_state_dict(up_o.state_dict())
+    with torch.no_grad():
+        xo = oracle_ts.SparseTensor(feats, coords); xo.cmaps[xo.stride] = xo.coords
+        xg = ts.SparseTensor(feats.cuda(), coords.cuda()); xg.cmaps[xg.stride] = xg.coords
+        want = up_o(down_o(xo))
+        got = up_g(down_g(xg))
+    assert got.s == (1, 1, 1) and torch.equal(got.C.cpu(), coords)
+    mx, l2 = rel_err(got.F.cpu(), want.F)
+    assert mx < REL_TOL and l2 < REL_TOL, (mx, l2)
+
+
+def test_fused_epilogue_and_strided_io(ts, oracle_ts, small_scan):
+    """scale/shift/residual/ReLU epilogue, 16-bit output, column-slice input and output (torchsparse.cat without copy)."""
+    F = ts.nn.functional
+    coords, feats = _sparse_input(oracle_ts, small_scan, 64)
+    n = coords.shape[0]
+    km = F.build_kernel_map(coords.cuda(), (1, 1, 1), (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    g = torch.Generator().manual_seed(1)
+    kernel = torch.randn(27, 64, 96, generator=g) * 0.05
+    scale, shift = torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g)
+    res = torch.randn(n, 96, generator=g)
+    wide_in = torch.zeros(n, 64 + 32, dtype=torch.bfloat16, device="cuda")
+    wide_in[:, 32:] = feats.cuda().bfloat16()
+    wide_out = torch.zeros(n, 96 + 32, dtype=torch.bfloat16, device="cuda")
+    F.conv_forward(wide_in[:, 32:], F.pack_weight(kernel.cuda(), torch.bfloat16), km.nbr, n, scale=scale.cuda(),
+                   shift=shift.cuda(), residual=res.cuda().bfloat16(), relu=True, out=wide_out[:, :96])
+    nb, ns, sz, _, _ = oracle_ts.nn.functional.build_kernel_map(coords, (1, 1, 1), (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    x16, w16, r16 = feats.bfloat16().float(), kernel.bfloat16().float(), res.bfloat16().float()
+    acc = torch.zeros(n, 96)
+    cur = 0
+    for k, m in enumerate(ns.tolist()):
+        mm = nb[cur:cur + m]; cur += m
+        acc.index_add_(0, mm[:, 1], x16[mm[:, 0]] @ w16[k])
+    want = torch.relu(acc * scale + shift + r16)
+    mx, l2 = rel_err(wide_out[:, :96].float().cpu(), want)
+    assert mx < REL_TOL and l2 < 5e-3, (mx, l2)
+    assert float(wide_out[:, 96:].abs().max()) == 0.0            # neighbouring columns untouched
+
+
+@pytest.mark.parametrize("name,ncls", [("minkunet", 19), ("spvcnn", 16)])
+def test_network_logits_vs_reference_golden(ts, golden, small_scan, name, ncls):
+    """Whole network on the CUDA path vs the reference's network/*.py on the fp32 oracle (nets.npz)."""
+    from lidal_b200.network import MinkUNet, SPVCNN, seeded_state_dict
+    g = golden["nets"]
+    coords, feats, _ = small_scan
+    model = (MinkUNet if name == "minkunet" else SPVCNN)(ncls, ts)
+    model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        logits, feat = model(ts.SparseTensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda()))
+    assert logits.shape == (coords.shape[0], ncls)
+    want = torch.from_numpy(g[f"{name}_logits_head"])
+    mx, l2 = rel_err(logits[:512].float().cpu(), want)
+    print(f"{name}: logits max-rel {mx:.3e} l2-rel {l2:.3e}")
+    assert l2 < REL_TOL and mx < 3 * REL_TOL, (mx, l2)
+    mxf, l2f = rel_err(feat[:64].float().cpu(), torch.from_numpy(g[f"{name}_feat_head"]))
+    assert l2f < REL_TOL, (mxf, l2f)
+
+
+def test_conv_backward_vs_oracle(ts, oracle_ts, small_scan):
+    coords, feats = _sparse_input(oracle_ts, small_scan, 32)
+    conv_o = oracle_ts.nn.Conv3d(32, 64, kernel_size=3)
+    conv_g = ts.nn.Conv3d(32, 64, kernel_size=3).cuda()
+    conv_g.load_state_dict(conv_o.state_dict())
+    fo = feats.clone().requires_grad_(True)
+    fg = feats.clone().cuda().requires_grad_(True)
+    go = torch.randn(coords.shape[0], 64, generator=torch.Generator().manual_seed(3))
+    conv_o(oracle_ts.SparseTensor(fo, coords)).F.backward(go)
+    conv_g(ts.SparseTensor(fg, coords.cuda())).F.backward(go.cuda())
+    assert rel_err(fg.grad.cpu(), fo.grad)[1] < REL_TOL
+    assert rel_err(conv_g.kernel.grad.cpu(), conv_o.kernel.grad)[1] < REL_TOL

@@ -1,0 +1,117 @@
+"""GPU: hashing, hash query, downsample and kernel maps through the C ABI -- bit-exact against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import lidal_b200.compat as ts
+    return ts
+
+
+def rand_coords(n, seed, batch=3, span=200):
+    rng = np.random.default_rng(seed)
+    c = np.concatenate([rng.integers(0, span, (n, 3)), rng.integers(0, batch, (n, 1))], 1).astype(np.int32)
+    return np.unique(c, axis=0)
+
+
+def test_sphash_golden(ts, golden):
+    g = golden["hash"]
+    got = ts.nn.functional.sphash(torch.from_numpy(g["coords"]).cuda())
+    assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), g["hashes"])
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 5000])
+def test_sphash_and_kernel_hash_vs_oracle(ts, oracle_ts, n):
+    c = torch.from_numpy(rand_coords(n, n)) if n else torch.zeros((0, 4), dtype=torch.int)
+    F, Fo = ts.nn.functional, oracle_ts.nn.functional
+    assert torch.equal(F.sphash(c.cuda()).cpu(), Fo.sphash(c))
+    for ks, st in ((3, 1), (2, 2), (3, 4)):
+        off = oracle_ts.nn.utils.get_kernel_offsets(ks, st)
+        assert torch.equal(ts.nn.utils.get_kernel_offsets(ks, st, device="cuda").cpu(), off)
+        assert torch.equal(F.sphash(c.cuda(), off.cuda()).cpu(), Fo.sphash(c, off))
+
+
+def test_sphashquery_vs_oracle(ts, oracle_ts):
+    F, Fo = ts.nn.functional, oracle_ts.nn.functional
+    c = torch.from_numpy(rand_coords(20000, 1))
+    ref = Fo.sphash(c)
+    off = oracle_ts.nn.utils.get_kernel_offsets(3, 1)
+    q = Fo.sphash(c[:7000], off)                                       # [27, 7000]: hits and misses
+    want = Fo.sphashquery(q, ref)
+    got = F.sphashquery(q.cuda(), ref.cuda())
+    assert got.shape == q.shape and got.dtype == torch.int64
+    assert torch.equal(got.cpu(), want)
+    assert (want == -1).any() and (want >= 0).any()
+    assert F.sphashquery(q[:0].cuda(), ref.cuda()).numel() == 0
+
+
+def test_spcount(ts, oracle_ts):
+    idx = torch.randint(-1, 50, (10000,), dtype=torch.int)
+    assert torch.equal(ts.nn.functional.spcount(idx.cuda(), 50).cpu(), oracle_ts.nn.functional.spcount(idx, 50))
+
+
+@pytest.mark.parametrize("ts_stride", [1, 2, 8])
+def test_spdownsample_sorted_unique(ts, oracle_ts, ts_stride):
+    c = rand_coords(30000, 7, batch=4, span=300)
+    c[:, :3] = c[:, :3] // ts_stride * ts_stride
+    c = torch.from_numpy(np.unique(c, axis=0))
+    want = oracle_ts.nn.functional.spdownsample(c, 2, 2, ts_stride)
+    got = ts.nn.functional.spdownsample(c.cuda(), 2, 2, ts_stride)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_spdownsample_rejects_out_of_range(ts):
+    from lidal_b200._lib import LidalError
+    c = torch.tensor([[1, 2, 3, 0], [70000, 1, 1, 0]], dtype=torch.int).cuda()
+    with pytest.raises(LidalError):
+        ts.nn.functional.spdownsample(c, 2, 2, 1)
+
+
+def test_kernel_maps_bit_exact(ts, oracle_ts, small_scan, golden):
+    """All 9 maps of a MinkUNet forward: nbmaps / nbsizes / out coords identical to the oracle and the golden checksums."""
+    import hashlib
+    F, Fo = ts.nn.functional, oracle_ts.nn.functional
+    coords = torch.from_numpy(small_scan[0])
+    cur_o, cur_g = coords, coords.cuda()
+    g = golden["nets"]
+    for level in range(5):
+        s = 2 ** level
+        st = (s, s, s)
+        nb_o, ns_o, sz_o, _, res_o = Fo.build_kernel_map(cur_o, st, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        km = F.build_kernel_map(cur_g, st, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        assert torch.equal(km.nbr.cpu().long(), res_o)
+        assert torch.equal(km.nbmaps.cpu().long(), nb_o) and torch.equal(km.nbsizes.cpu().long(), ns_o)
+        assert km[2] == sz_o
+        tag = f"kmap_s{s}_k3_st1"
+        assert hashlib.sha1(km.nbmaps.cpu().numpy().astype(np.int32).tobytes()).hexdigest() == str(g[tag + "_sha"])
+        if level == 4:
+            break
+        nb_o, ns_o, sz_o, oc_o, res_o = Fo.build_kernel_map(cur_o, st, (2, 2, 2), (2, 2, 2), (1, 1, 1))
+        km = F.build_kernel_map(cur_g, st, (2, 2, 2), (2, 2, 2), (1, 1, 1))
+        assert torch.equal(km.out_coords.cpu(), oc_o)
+        assert torch.equal(km.nbr.cpu().long(), res_o)
+        assert torch.equal(km.nbmaps.cpu().long(), nb_o) and torch.equal(km.nbsizes.cpu().long(), ns_o)
+        # transposed table is the per-offset inverse
+        nt = km.nbr_t.cpu()
+        k_idx, o_idx = torch.nonzero(res_o >= 0, as_tuple=True)
+        assert torch.equal(nt[k_idx, res_o[k_idx, o_idx]].long(), o_idx)
+        assert int((nt >= 0).sum()) == len(o_idx)
+        cur_o, cur_g = oc_o, km.out_coords
+
+
+def test_sort_pairs_stable_and_sorted():
+    import ctypes as C
+    from lidal_b200 import _lib as L
+    n = 300_000
+    keys = torch.randint(0, 2 ** 20, (n,), dtype=torch.int64).cuda() * 4096      # many duplicates, 32 bits used
+    vals = torch.arange(n, dtype=torch.int32).cuda()
+    k2, v2 = keys.clone(), vals.clone()
+    nbytes = L.lib().lb_sort_pairs_ws_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().lb_sort_pairs(L.ptr(k2), L.ptr(v2), n, 32, L.ptr(ws), nbytes, L.stream()))
+    want_k, want_i = torch.sort(keys.cpu(), stable=True)
+    assert torch.equal(k2.cpu(), want_k) and torch.equal(v2.cpu().long(), want_i)

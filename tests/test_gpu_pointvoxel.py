@@ -1,0 +1,77 @@
+"""GPU: SPVCNN point<->voxel kernels vs the oracle (fp32, tolerance 1e-5 relative; indices bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import lidal_b200.compat as ts
+    return ts
+
+
+def test_voxelize_devoxelize_roundtrip_vs_oracle(ts, oracle_ts, small_scan):
+    from lidal_b200.network.point_voxel import PointVoxel
+    coords, feats, _ = small_scan
+    g = torch.Generator().manual_seed(0)
+    f32 = torch.randn(coords.shape[0], 32, generator=g)
+    jitter = torch.rand(coords.shape[0], 3, generator=g) * 0.98
+    outs = {}
+    for name, be, dev in (("o", oracle_ts, "cpu"), ("g", ts, "cuda")):
+        pv = PointVoxel(be)
+        pc = torch.cat([torch.from_numpy(coords[:, :3]).float() + jitter, torch.from_numpy(coords[:, 3:]).float()], 1)
+        z = be.PointTensor(f32.to(dev), pc.to(dev))
+        x0 = pv.initial_voxelize(z, 0.05, 0.05)
+        z0 = pv.voxel_to_point(x0, z)
+        x1 = pv.point_to_voxel(x0, z0)
+        # a strided level: coarse voxels at stride 4
+        cs = torch.unique(torch.cat([x0.C[:, :3] // 4 * 4, x0.C[:, 3:]], 1), dim=0)
+        xs = be.SparseTensor(torch.randn(cs.shape[0], 16, generator=torch.Generator().manual_seed(5)).to(dev), cs.int(), 4)
+        z4 = pv.voxel_to_point(xs, z0)
+        outs[name] = dict(C=x0.C.cpu(), F=x0.F.cpu(), z0=z0.F.cpu(), x1=x1.F.cpu(), z4=z4.F.cpu(),
+                          iq=z0.idx_query[(1, 1, 1)].cpu(), w=z0.weights[(1, 1, 1)].cpu(),
+                          iq4=z4.idx_query[(4, 4, 4)].cpu(), w4=z4.weights[(4, 4, 4)].cpu())
+    o, g_ = outs["o"], outs["g"]
+    assert torch.equal(o["C"], g_["C"]) and torch.equal(o["iq"], g_["iq"]) and torch.equal(o["iq4"], g_["iq4"])
+    for k in ("F", "z0", "x1", "z4", "w", "w4"):
+        torch.testing.assert_close(g_[k], o[k], rtol=1e-5, atol=1e-6, msg=k)
+
+
+def test_point_voxel_backward_vs_oracle(ts, oracle_ts):
+    g = torch.Generator().manual_seed(2)
+    n, m, c = 5000, 700, 24
+    idx = torch.randint(-1, m, (n,), generator=g)
+    feats = torch.randn(n, c, generator=g)
+    outs = []
+    for be, dev in ((oracle_ts, "cpu"), (ts, "cuda")):
+        F = be.nn.functional
+        counts = F.spcount(idx.int().to(dev), m)
+        f = feats.clone().to(dev).requires_grad_(True)
+        v = F.spvoxelize(f, idx.to(dev), counts)
+        i8 = torch.randint(-1, m, (n, 8), generator=torch.Generator().manual_seed(4)).to(dev)
+        w8 = torch.rand(n, 8, generator=torch.Generator().manual_seed(6)).to(dev)
+        p = F.spdevoxelize(v, i8, w8)
+        p.square().sum().backward()
+        outs.append((v.detach().cpu(), p.detach().cpu(), f.grad.cpu()))
+    for a, b in zip(outs[1], outs[0]):
+        torch.testing.assert_close(a, b, rtol=2e-4, atol=1e-4)
+
+
+def test_tta_tail_vs_oracle():
+    import lidal_scoring as orc
+    from lidal_b200 import score
+    rng = np.random.default_rng(0)
+    n_pts, n_vox_per, reps, ncls = 20000, 15000, 8, 19
+    logits = (rng.normal(size=(reps * n_vox_per, ncls)) * 3).astype(np.float32)
+    inv = np.concatenate([rng.integers(0, n_vox_per, n_pts) + v * n_vox_per for v in range(reps)]).astype(np.int64)
+    want_p, want_y = orc.tta_tail(logits, inv, reps)
+    got_p, got_y = score.tta_tail(torch.from_numpy(logits).cuda(), torch.from_numpy(inv).cuda(), reps)
+    got_p = got_p.cpu().numpy()
+    np.testing.assert_allclose(got_p, want_p, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(got_p.sum(1), 1.0, atol=1e-5)
+    agree = (got_y.cpu().numpy() == want_y)
+    # argmax may only differ where the top-2 probabilities are within float rounding of each other
+    top2 = np.sort(want_p, 1)[:, -2:]
+    assert (agree | (top2[:, 1] - top2[:, 0] < 1e-6)).all() and agree.mean() > 0.9999
