@@ -1,6 +1,469 @@
-// placeholder until the tcgen05 kernel lands
+// Sparse convolution as an output-stationary implicit GEMM on the 5th-generation tensor cores (sm_100a).
+//
+//   out[o, :] = epilogue( sum_{k in offsets} in[nbr[k][o], :] @ W[k] )
+//
+// One persistent CTA per SM walks 128-row output tiles.  Warp roles (288 threads):
+//   warps 0-3  epilogue : tcgen05.ld accumulator rows from TMEM -> scale/shift/residual/ReLU -> global store
+//   warps 4-7  producers: gather the A operand -- 128 neighbour rows x BLOCK_K channels -- straight into the
+//                         swizzled K-major shared-memory layout with 16-byte cp.async (zero-fill for missing
+//                         neighbours); thread 128 also issues the TMA load of the weight tile W[k][:, c0:c0+BK]
+//   warp  8    MMA      : one elected thread issues tcgen05.mma (M=128, N=c_out, K=16) per 16 channels,
+//                         accumulating over all active offsets and channel blocks in TMEM (fp32)
+// Pipelines: a STAGES-deep smem ring (full/empty mbarriers) between producers and MMA, and a 2-deep TMEM
+// accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile t overlaps the
+// gathers and MMAs of tile t+1.  Offsets for which no row of the tile has a neighbour are skipped entirely.
+// No atomics: every output row is written exactly once, by one thread.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace lb {
-int conv_tc_supported(int, int, int, int) { return 0; }
-int conv_tc_launch(const lb_conv_args&, cudaStream_t) { set_error("tcgen05 conv not built"); return LB_EINVAL; }
+
+constexpr int TILE_M = 128;
+constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_PROD_THREADS = 128;
+constexpr int NUM_THREADS = NUM_EPI_THREADS + NUM_PROD_THREADS + 32;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_KVOL = 27;
+constexpr int PROD_LAG = 2;           // cp.async groups kept in flight per producer thread before signalling
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem];  one thread issues on behalf of the CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// mbarrier arrive once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (bits 4-5 = 1), a/b format (0 = F16, 1 = BF16) at bits 7-9 /
+// 10-12, K-major A and B (bits 15, 16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcParams {
+  const char* in;          // 16-bit activations
+  int64_t n_in, ld_in;     // ld in elements
+  char* out;
+  int64_t n_out, ld_out;
+  const int* n_out_dev;
+  const int* nbr;
+  int64_t nbr_ld;
+  const int* out_rows;
+  int k_vol, c_in, c_out;
+  const float* scale;
+  const float* shift;
+  const char* residual;
+  int64_t ld_res;
+  int out_dtype;           // LB_DT_*
+  int relu;
+  int is_bf16;
+  int stages;
+  int tmem_cols;
+};
+
+template <typename T> __device__ __forceinline__ float cvt_in(uint16_t raw);
+template <> __device__ __forceinline__ float cvt_in<__nv_bfloat16>(uint16_t raw) { return __uint_as_float((uint32_t)raw << 16); }
+template <> __device__ __forceinline__ float cvt_in<__half>(uint16_t raw) { return __half2float(__ushort_as_half(raw)); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
+  if (is_bf16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// BK = channels per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
+template <int BK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
+  constexpr int ROW_BYTES = BK * 2;
+  constexpr int CHUNKS = ROW_BYTES / 16;                 // 16-byte chunks per row: 8 or 4
+  constexpr int A_BYTES = TILE_M * ROW_BYTES;            // 16 KB or 8 KB
+  constexpr uint32_t LAYOUT = (BK == 64) ? 2u : 4u;      // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t SBO = 8 * ROW_BYTES;                // 8-row group pitch
+  constexpr int ROWS_PER_PASS = NUM_PROD_THREADS / CHUNKS;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.c_out * ROW_BYTES;
+  const int stage_bytes = A_BYTES + ((b_bytes + 1023) & ~1023);
+  uint8_t* ring = smem;
+  uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
+  int* s_idx = (int*)tail;                                         // [MAX_KVOL][TILE_M]
+  float* s_scale = (float*)(tail + MAX_KVOL * TILE_M * 4);         // [256]
+  float* s_shift = s_scale + 256;                                  // [256]
+  uint64_t* full_bar = (uint64_t*)(s_shift + 256);                 // [MAX_STAGES]
+  uint64_t* empty_bar = full_bar + MAX_STAGES;                     // [MAX_STAGES]
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;                    // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
+  uint32_t* s_flags = (uint32_t*)(tempty_bar + 2);                 // [MAX_STAGES] bit0 = first k-block, bit1 = last
+  uint32_t* s_tmem = s_flags + MAX_STAGES;                         // [1]
+  uint32_t* s_mask = s_tmem + 1;                                   // [1] active-offset mask of the producers' tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out;
+  const int64_t num_tiles = (n_out + TILE_M - 1) / TILE_M;
+  const int kc_blocks = p.c_in / BK;
+
+  // ---------------- one-time setup
+  for (int i = threadIdx.x; i < 256; i += NUM_THREADS) {
+    s_scale[i] = (p.scale && i < p.c_out) ? p.scale[i] : 1.f;
+    s_shift[i] = (p.shift && i < p.c_out) ? p.shift[i] : 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], NUM_PROD_THREADS + 1);   // 128 gather threads + 1 expect_tx arrive for the TMA tile
+      mbar_init(&empty_bar[s], 1);                     // released by tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], NUM_EPI_THREADS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp >= 4 && warp < 8) {
+    // =============================================================== PRODUCERS
+    const int t = threadIdx.x - NUM_EPI_THREADS;          // 0..127
+    const int chunk = t % CHUNKS, row0 = t / CHUNKS;
+    if (t == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&w_map) : "memory");
+    uint32_t it = 0;                                      // global k-block counter (ring position)
+    int pending[PROD_LAG];                                // stages whose cp.async group has not been signalled yet
+    int n_pending = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t base = tile * TILE_M;
+      // all producers finished issuing the previous tile's gathers before s_idx is overwritten
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      if (t == 0) *s_mask = 0;
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      uint32_t my_mask = 0;
+      for (int k = 0; k < p.k_vol; ++k) {
+        const int64_t o = base + t;
+        int nb = -1;
+        if (o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
+        if (nb >= p.n_in) nb = -1;
+        s_idx[k * TILE_M + t] = nb;
+        if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
+      }
+      if (lane == 0 && my_mask) atomicOr(s_mask, my_mask);
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      uint32_t mask = *s_mask;
+      if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
+      const int last_k = 31 - __clz(mask);
+      const int first_k = __ffs(mask) - 1;
+      for (int k = first_k; k <= last_k; ++k) {
+        if (!((mask >> k) & 1)) continue;
+        for (int cb = 0; cb < kc_blocks; ++cb, ++it) {
+          const int stage = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty_bar[stage], ph ^ 1);           // slot free (first lap passes immediately)
+          uint8_t* a_s = ring + (size_t)stage * stage_bytes;
+          if (t == 0) {
+            s_flags[stage] = ((k == first_k && cb == 0) ? 1u : 0u) | ((k == last_k && cb == kc_blocks - 1) ? 2u : 0u);
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+            tma_load_2d(smem_u32(a_s + A_BYTES), &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
+          }
+          const uint32_t a_u32 = smem_u32(a_s);
+#pragma unroll
+          for (int i = 0; i < TILE_M / ROWS_PER_PASS; ++i) {
+            const int r = row0 + i * ROWS_PER_PASS;
+            const int nb = s_idx[k * TILE_M + r];
+            const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
+            const uint32_t dst = a_u32 + r * ROW_BYTES + sw * 16;
+            const char* src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + cb * BK + chunk * 8) * 2;
+            cp_async16(dst, src, nb >= 0 ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (n_pending == PROD_LAG) {                    // oldest group is complete after this wait
+            cp_async_wait<PROD_LAG>();
+            fence_proxy_async();
+            mbar_arrive(&full_bar[pending[0]]);
+#pragma unroll
+            for (int j = 0; j + 1 < PROD_LAG; ++j) pending[j] = pending[j + 1];
+            pending[PROD_LAG - 1] = stage;
+          } else {
+            pending[n_pending++] = stage;
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int j = 0; j < n_pending; ++j) mbar_arrive(&full_bar[pending[j]]);
+  } else if (warp == 8) {
+    // =============================================================== MMA ISSUER
+    const uint32_t idesc = make_idesc(TILE_M, p.c_out, p.is_bf16 ? 1 : 0);
+    uint32_t it = 0;
+    int64_t tcount = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = (int)(tcount & 1);
+      const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
+      mbar_wait(&tempty_bar[acc], acc_ph ^ 1);            // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.c_out);
+      while (true) {
+        const int stage = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&full_bar[stage], ph);
+        tc_fence_after();
+        const uint32_t flags = s_flags[stage];
+        if (lane == 0) {
+          const uint32_t a_u32 = smem_u32(ring + (size_t)stage * stage_bytes);
+          const uint64_t a_desc = make_smem_desc(a_u32, SBO, LAYOUT);
+          const uint64_t b_desc = make_smem_desc(a_u32 + A_BYTES, SBO, LAYOUT);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)            // +32 bytes along K inside the swizzle atom = +2 in the address field
+            umma_f16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, ((flags & 1u) && kk == 0) ? 0u : 1u);
+          umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+          if (flags & 2u) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        ++it;
+        if (flags & 2u) break;
+      }
+    }
+  } else {
+    // =============================================================== EPILOGUE (warps 0-3: TMEM lane quadrant = warp)
+    int64_t tcount = 0;
+    const int out_es = (p.out_dtype == LB_DT_F32) ? 4 : 2;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = (int)(tcount & 1);
+      const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const int64_t o = tile * TILE_M + warp * 32 + lane;
+      const bool live = o < n_out;
+      const int64_t orow = live ? (p.out_rows ? (int64_t)__ldg(&p.out_rows[o]) : o) : 0;
+      char* out_row = p.out + orow * p.ld_out * out_es;
+      const char* res_row = p.residual ? p.residual + orow * p.ld_res * 2 : nullptr;
+      for (int c0 = 0; c0 < p.c_out; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * p.c_out + c0), v);
+        if (live) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+          if (res_row) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rr = __ldg((const uint4*)(res_row + (c0 + q * 8) * 2));
+              const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (p.is_bf16) {
+                  f[q * 8 + 2 * j] += cvt_in<__nv_bfloat16>((uint16_t)(w[j] & 0xffff));
+                  f[q * 8 + 2 * j + 1] += cvt_in<__nv_bfloat16>((uint16_t)(w[j] >> 16));
+                } else {
+                  f[q * 8 + 2 * j] += cvt_in<__half>((uint16_t)(w[j] & 0xffff));
+                  f[q * 8 + 2 * j + 1] += cvt_in<__half>((uint16_t)(w[j] >> 16));
+                }
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_dtype == LB_DT_F32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *(float4*)(out_row + (c0 + q * 4) * 4) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              w.x = pack2(f[q * 8], f[q * 8 + 1], p.is_bf16);
+              w.y = pack2(f[q * 8 + 2], f[q * 8 + 3], p.is_bf16);
+              w.z = pack2(f[q * 8 + 4], f[q * 8 + 5], p.is_bf16);
+              w.w = pack2(f[q * 8 + 6], f[q * 8 + 7], p.is_bf16);
+              *(uint4*)(out_row + (c0 + q * 8) * 2) = w;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  // ---------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static inline int block_k_for(int c_in) { return (c_in % 64 == 0) ? 64 : ((c_in % 32 == 0) ? 32 : 0); }
+
+int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
+  if (act_dtype != LB_DT_BF16 && act_dtype != LB_DT_F16) return 0;
+  if (k_vol < 1 || k_vol > MAX_KVOL) return 0;
+  if (block_k_for(c_in) == 0) return 0;
+  if (c_out % 32 != 0 || c_out < 32 || c_out > 256) return 0;
+  return 1;
+}
+
+static size_t tail_bytes() {
+  return (size_t)MAX_KVOL * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64;
+}
+
+int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
+  const int bk = block_k_for(a.c_in);
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("lb_conv_fwd: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return LB_ECUDA; }
+  if (a.out_dtype != LB_DT_F32 && a.out_dtype != a.act_dtype) {
+    set_error("lb_conv_fwd: out_dtype must be F32 or equal act_dtype");
+    return LB_EINVAL;
+  }
+  const int out_es = a.out_dtype == LB_DT_F32 ? 4 : 2;
+  if (((uintptr_t)a.out & 15) || (a.ld_out * out_es) % 16 || (a.residual && (((uintptr_t)a.residual & 15) || (a.ld_res * 2) % 16))) {
+    set_error("lb_conv_fwd: tensor-core path needs 16-byte aligned out / residual rows");
+    return LB_EINVAL;
+  }
+  // weight viewed as a 2-D tensor [k_vol * c_out rows, c_in cols] (c_in contiguous), box = [c_out rows, bk cols]
+  CUtensorMap map;
+  cuuint64_t gdim[2] = {(cuuint64_t)a.c_in, (cuuint64_t)a.k_vol * a.c_out};
+  cuuint64_t gstride[1] = {(cuuint64_t)a.c_in * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)a.c_out};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(&map, a.act_dtype == LB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                      const_cast<void*>(a.weight), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("lb_conv_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r); return LB_ECUDA; }
+
+  TcParams p;
+  p.in = (const char*)a.in; p.n_in = a.n_in; p.ld_in = a.ld_in;
+  p.out = (char*)a.out; p.n_out = a.n_out; p.ld_out = a.ld_out;
+  p.n_out_dev = a.n_out_dev; p.nbr = a.nbr; p.nbr_ld = a.nbr_ld; p.out_rows = a.out_rows;
+  p.k_vol = a.k_vol; p.c_in = a.c_in; p.c_out = a.c_out;
+  p.scale = a.scale; p.shift = a.shift; p.residual = (const char*)a.residual; p.ld_res = a.ld_res;
+  p.out_dtype = a.out_dtype; p.relu = (a.flags & LB_CONV_RELU) ? 1 : 0; p.is_bf16 = a.act_dtype == LB_DT_BF16;
+  int cols = 32;
+  while (cols < 2 * a.c_out) cols <<= 1;
+  p.tmem_cols = cols;
+  const int row_bytes = bk * 2;
+  const size_t stage_bytes = (size_t)TILE_M * row_bytes + (((size_t)a.c_out * row_bytes + 1023) & ~(size_t)1023);
+  const size_t budget = 227 * 1024 - 1024 - tail_bytes();
+  int stages = (int)(budget / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < PROD_LAG + 1) { set_error("lb_conv_fwd: shared memory too small for the pipeline"); return LB_ECAP; }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + tail_bytes() + 1024;
+  int64_t tiles = (a.n_out + TILE_M - 1) / TILE_M;
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  if (grid < 1) grid = 1;
+  if (bk == 64) {
+    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<64><<<grid, NUM_THREADS, smem, st>>>(map, p);
+  } else {
+    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<32><<<grid, NUM_THREADS, smem, st>>>(map, p);
+  }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+}  // namespace lb

@@ -68,14 +68,21 @@ __global__ void devoxelize_fwd_kernel(const float* __restrict__ feats, const int
       my_w = __ldg(&w[i * 8 + lane]);
       if (my_idx >= m) my_idx = -1;
     }
+    int rk[8];
+    float wk8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {              // broadcast once, outside the (divergent) channel loop
+      rk[k] = __shfl_sync(0xffffffffu, my_idx, k);
+      wk8[k] = __shfl_sync(0xffffffffu, my_w, k);
+    }
     for (int j = lane * VEC; j < c; j += 32 * VEC) {
       float acc[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        int r = __shfl_sync(0xffffffffu, my_idx, k);
-        float wk = __shfl_sync(0xffffffffu, my_w, k);
+        const int r = rk[k];
+        const float wk = wk8[k];
         if (r >= 0) {
           if (VEC == 4) {
             float4 f = __ldg((const float4*)&feats[(int64_t)r * c + j]);

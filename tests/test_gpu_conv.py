@@ -131,3 +131,31 @@ def test_conv_backward_vs_oracle(ts, oracle_ts, small_scan):
     conv_g(ts.SparseTensor(fg, coords.cuda())).F.backward(go.cuda())
     assert rel_err(fg.grad.cpu(), fo.grad)[1] < REL_TOL
     assert rel_err(conv_g.kernel.grad.cpu(), conv_o.kernel.grad)[1] < REL_TOL
+
+
+@pytest.mark.parametrize("cin,cout,k3", [(32, 32, True), (64, 96, True), (96, 128, True), (128, 256, False), (384, 256, True)])
+def test_tensor_core_path_matches_simt(ts, small_scan, cin, cout, k3):
+    """The tcgen05 implicit GEMM and the CUDA-core kernel see the same 16-bit operands: results agree to fp32
+    summation-order noise, and the dispatcher really selects the tensor-core kernel for these shapes."""
+    from lidal_b200 import _lib as L
+    F = ts.nn.functional
+    coords = torch.from_numpy(small_scan[0]).cuda()
+    n = coords.shape[0]
+    kv = 27 if k3 else 1
+    assert L.lib().lb_conv_uses_tensor_cores(kv, cin, cout, L.LB_DT_BF16) == 1
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(n, cin, generator=g).cuda().bfloat16()
+    w = F.pack_weight((torch.randn(kv, cin, cout, generator=g) * (1.0 / (cin * 3) ** 0.5)).cuda(), torch.bfloat16)
+    nbr = F.build_kernel_map(coords, (1, 1, 1), (3, 3, 3), (1, 1, 1), (1, 1, 1)).nbr if k3 else None
+    scale, shift = (torch.rand(cout, generator=g) + 0.5).cuda(), torch.randn(cout, generator=g).cuda()
+    res = torch.randn(n, cout, generator=g).cuda().bfloat16()
+    for dt in (torch.float32, torch.bfloat16):
+        a = F.conv_forward(x, w, nbr, n, scale=scale, shift=shift, residual=res, relu=True, out_dtype=dt)
+        b = F.conv_forward(x, w, nbr, n, scale=scale, shift=shift, residual=res, relu=True, out_dtype=dt, force_simt=True)
+        tol = 1e-4 if dt == torch.float32 else 1e-2
+        torch.testing.assert_close(a.float(), b.float(), rtol=tol, atol=tol)
+    # fp16 operands use the same kernel with the other instruction-descriptor format
+    xh, wh = x.half(), w.half()
+    a = F.conv_forward(xh, wh, nbr, n)
+    b = F.conv_forward(xh, wh, nbr, n, force_simt=True)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
