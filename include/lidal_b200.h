@@ -35,6 +35,8 @@ extern "C" {
 
 int lb_abi_version(void);
 const char* lb_last_error(void); /* [host] thread-local text of the last failure */
+/* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
+uint64_t lb_launch_count(void);
 int lb_device_info(int* sm_count, int* cc_major, int* cc_minor); /* [host] outs */
 
 /* ------------------------------------------------------------------ hashing / kernel maps

@@ -36,6 +36,7 @@ class FrameRef(C.Structure):
 SIGNATURES = {
     "lb_abi_version": (i32, []),
     "lb_last_error": (C.c_char_p, []),
+    "lb_launch_count": (C.c_uint64, []),
     "lb_device_info": (i32, [C.POINTER(i32)] * 3),
     "lb_hash": (i32, [vp, i64, vp, vp]),
     "lb_kernel_hash": (i32, [vp, i64, vp, i32, vp, vp]),

@@ -18,6 +18,7 @@ __all__ = ["sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "ca
            "conv3d", "build_kernel_map"]
 
 ACT_DTYPE = torch.bfloat16          # 16-bit operand type of the tensor-core convolution (fp32 accumulate)
+CONV_TRACE = None                   # set by lidal_b200.profiling to time every conv launch with CUDA events
 
 
 def set_conv_dtype(dtype):
@@ -258,7 +259,13 @@ def conv_forward(feats16, packed_w, nbr, n_out, *, scale=None, shift=None, resid
     a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
     a.act_dtype, a.out_dtype = L.DT_OF[feats16.dtype], L.DT_OF[out.dtype]
     a.flags = (L.LB_CONV_RELU if relu else 0) | (L.LB_CONV_FORCE_SIMT if force_simt else 0)
+    if CONV_TRACE is None:
+        L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
+        return out
+    ev = CONV_TRACE.begin()
     L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
+    tc = (not force_simt) and L.lib().lb_conv_uses_tensor_cores(k, cin, cout, a.act_dtype) and feats16.stride(0) % 8 == 0
+    CONV_TRACE.end(ev, nbr, n_out, k, cin, cout, tc)
     return out
 
 

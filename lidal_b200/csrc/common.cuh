@@ -31,6 +31,9 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
     }                                                                                   \
   } while (0)
 
+// every kernel launch site is followed by LB_LAUNCHED(n): n kernels were just enqueued (feeds lb_launch_count)
+void add_launches(int n);
+#define LB_LAUNCHED(n) lb::add_launches(n)
 #define LB_LAUNCH_CHECK() LB_CUDA(cudaGetLastError())
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -122,7 +122,7 @@ static int launch_simt(const lb_conv_args& a, cudaStream_t st) {
   conv_simt_kernel<T, O><<<grid, ST_THREADS, smem, st>>>(
       (const T*)a.in, a.ld_in, a.n_in, (O*)a.out, a.ld_out, a.n_out, a.n_out_dev, a.nbr, a.nbr_ld, a.out_rows,
       (const T*)a.weight, a.k_vol, a.c_in, a.c_out, a.scale, a.shift, (const T*)a.residual, a.ld_res,
-      (a.flags & LB_CONV_RELU) ? 1 : 0);
+      (a.flags & LB_CONV_RELU) ? 1 : 0); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -142,8 +142,8 @@ extern "C" int lb_conv_pack_weight(const float* kernel, int k, int cin, int cout
   LB_CHECK_ARG(k > 0 && cin > 0 && cout > 0, "bad shape");
   int64_t total = (int64_t)k * cin * cout, blocks = (total + 255) / 256, cap = (int64_t)sm_count() * 16;
   int g = (int)(blocks > cap ? cap : blocks);
-  if (dt == LB_DT_BF16) pack_weight_kernel<<<g, 256, 0, as_stream(stream)>>>(kernel, k, cin, cout, (__nv_bfloat16*)packed);
-  else if (dt == LB_DT_F16) pack_weight_kernel<<<g, 256, 0, as_stream(stream)>>>(kernel, k, cin, cout, (__half*)packed);
+  if (dt == LB_DT_BF16) { pack_weight_kernel<<<g, 256, 0, as_stream(stream)>>>(kernel, k, cin, cout, (__nv_bfloat16*)packed); LB_LAUNCHED(1); }
+  else if (dt == LB_DT_F16) { pack_weight_kernel<<<g, 256, 0, as_stream(stream)>>>(kernel, k, cin, cout, (__half*)packed); LB_LAUNCHED(1); }
   else { set_error("lb_conv_pack_weight: act_dtype must be BF16 or F16"); return LB_EINVAL; }
   LB_LAUNCH_CHECK();
   return LB_OK;

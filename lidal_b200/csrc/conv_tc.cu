@@ -457,10 +457,10 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   if (grid < 1) grid = 1;
   if (bk == 64) {
     LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<64><<<grid, NUM_THREADS, smem, st>>>(map, p);
+    conv_tc_kernel<64><<<grid, NUM_THREADS, smem, st>>>(map, p); LB_LAUNCHED(1);
   } else {
     LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<32><<<grid, NUM_THREADS, smem, st>>>(map, p);
+    conv_tc_kernel<32><<<grid, NUM_THREADS, smem, st>>>(map, p); LB_LAUNCHED(1);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;

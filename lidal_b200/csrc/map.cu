@@ -13,6 +13,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void add_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -146,9 +149,9 @@ int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* t
   }
   int tiles = ceil_div(n, SCAN_TILE);
   uint32_t* sums = (uint32_t*)ws;
-  scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(in, n, sums);
-  scan_sums_single<<<1, 1024, 0, st>>>(sums, tiles, total);
-  scan_tile_apply<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, sums);
+  scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(in, n, sums); LB_LAUNCHED(1);
+  scan_sums_single<<<1, 1024, 0, st>>>(sums, tiles, total); LB_LAUNCHED(1);
+  scan_tile_apply<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, sums); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -249,10 +252,10 @@ extern "C" int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_
   uint64_t *ka = keys, *kb = k2;
   uint32_t *va = vals, *vb = v2;
   for (int ps = 0; ps < passes; ++ps) {
-    rs_hist<<<tiles, RS_THREADS, 0, st>>>(ka, n, ps * 8, hist, tiles);
+    rs_hist<<<tiles, RS_THREADS, 0, st>>>(ka, n, ps * 8, hist, tiles); LB_LAUNCHED(1);
     int rc = exclusive_scan_u32(hist, hist, (int64_t)256 * tiles, nullptr, sws, st);
     if (rc != LB_OK) return rc;
-    rs_scatter<<<tiles, RS_THREADS, 0, st>>>(ka, vals ? va : nullptr, kb, vb, n, ps * 8, hist, tiles);
+    rs_scatter<<<tiles, RS_THREADS, 0, st>>>(ka, vals ? va : nullptr, kb, vb, n, ps * 8, hist, tiles); LB_LAUNCHED(1);
     uint64_t* tk = ka; ka = kb; kb = tk;
     uint32_t* tv = va; va = vb; vb = tv;
   }
@@ -266,6 +269,7 @@ extern "C" int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_
 
 // ------------------------------------------------------------------------------------------ C ABI: hash + table
 extern "C" int lb_abi_version(void) { return LB_ABI_VERSION; }
+extern "C" uint64_t lb_launch_count(void) { return lb::launches(); }
 extern "C" const char* lb_last_error(void) { return lb::g_err; }
 extern "C" int lb_device_info(int* sms, int* major, int* minor) {
   int dev = 0;
@@ -282,7 +286,7 @@ extern "C" int lb_hash(const int32_t* coords, int64_t n, int64_t* out, void* str
   if (n == 0) return LB_OK;
   LB_CHECK_ARG(coords && out, "null pointer");
   LB_CHECK_ARG(((uintptr_t)coords & 15) == 0, "coords must be 16-byte aligned");
-  hash_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>((const int4*)coords, n, out);
+  hash_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>((const int4*)coords, n, out); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -293,7 +297,7 @@ extern "C" int lb_kernel_hash(const int32_t* coords, int64_t n, const int32_t* o
   LB_CHECK_ARG(coords && offsets && out, "null pointer");
   LB_CHECK_ARG(((uintptr_t)coords & 15) == 0, "coords must be 16-byte aligned");
   kernel_hash_kernel<<<grid_for(n, 256), 256, 3 * k * sizeof(int), as_stream(stream)>>>((const int4*)coords, n, offsets,
-                                                                                       k, out);
+                                                                                       k, out); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -310,7 +314,7 @@ extern "C" int lb_hashtable_build(const int64_t* keys, int64_t n, void* table, s
   LB_CUDA(cudaMemsetAsync((char*)table + cap * 8, 0x7F, cap * 4, st));
   if (n == 0) return LB_OK;
   LB_CHECK_ARG(keys, "null keys");
-  table_build_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, n, table_view(table, bytes));
+  table_build_kernel<<<grid_for(n, 256), 256, 0, st>>>(keys, n, table_view(table, bytes)); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -319,7 +323,7 @@ extern "C" int lb_hashtable_query(const void* table, size_t bytes, const int64_t
   LB_CHECK_ARG(table && nq >= 0, "null table or nq < 0");
   if (nq == 0) return LB_OK;
   LB_CHECK_ARG(q && out, "null pointer");
-  table_query_kernel<<<grid_for(nq, 256), 256, 0, as_stream(stream)>>>(table_view(table, bytes), q, nq, out);
+  table_query_kernel<<<grid_for(nq, 256), 256, 0, as_stream(stream)>>>(table_view(table, bytes), q, nq, out); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -377,13 +381,13 @@ extern "C" int lb_downsample(const int32_t* coords, int64_t n, const int32_t ss[
   int* err = (int*)p;
   LB_CUDA(cudaMemsetAsync(err, 0, 4, st));
   int g = grid_for(n, 256);
-  ds_pack<<<g, 256, 0, st>>>((const int4*)coords, n, ss[0], ss[1], ss[2], keys, err);
+  ds_pack<<<g, 256, 0, st>>>((const int4*)coords, n, ss[0], ss[1], ss[2], keys, err); LB_LAUNCHED(1);
   int rc = lb_sort_pairs(keys, nullptr, n, 48 + batch_bits, sort_ws, lb_sort_pairs_ws_bytes(n), stream);
   if (rc != LB_OK) return rc;
-  ds_flags<<<g, 256, 0, st>>>(keys, n, flags);
+  ds_flags<<<g, 256, 0, st>>>(keys, n, flags); LB_LAUNCHED(1);
   rc = exclusive_scan_u32(flags, pos, n, (uint32_t*)n_out, scan_ws, st);
   if (rc != LB_OK) return rc;
-  ds_emit<<<g, 256, 0, st>>>(keys, flags, pos, n, (int4*)out_coords, err, n_out);
+  ds_emit<<<g, 256, 0, st>>>(keys, flags, pos, n, (int4*)out_coords, err, n_out); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -435,7 +439,7 @@ extern "C" int lb_kmap_query(const void* table, size_t bytes, const int32_t* out
   if (cap == 0) return LB_OK;
   LB_CHECK_ARG(table && out_coords && offsets && nbr, "null pointer");
   kmap_query_kernel<<<grid_for(cap * k, 256), 256, 3 * k * sizeof(int), as_stream(stream)>>>(
-      table_view(table, bytes), (const int4*)out_coords, cap, n_dev, offsets, k, nbr);
+      table_view(table, bytes), (const int4*)out_coords, cap, n_dev, offsets, k, nbr); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -460,10 +464,10 @@ extern "C" int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t
   uint32_t* pos = (uint32_t*)p; p += align256((size_t)t * 4);
   void* sws = p;
   int g = grid_for(t, 256);
-  kmap_flags<<<g, 256, 0, st>>>(nbr, t, flags);
+  kmap_flags<<<g, 256, 0, st>>>(nbr, t, flags); LB_LAUNCHED(1);
   int rc = exclusive_scan_u32(flags, pos, t, (uint32_t*)total, sws, st);
   if (rc != LB_OK) return rc;
-  kmap_emit<<<g, 256, 0, st>>>(nbr, pos, n_out, k, (int2*)nbmaps, nbsizes, (const uint32_t*)total);
+  kmap_emit<<<g, 256, 0, st>>>(nbr, pos, n_out, k, (int2*)nbmaps, nbsizes, (const uint32_t*)total); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -487,7 +491,7 @@ extern "C" int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_o
   if (n_in > 0) { LB_CHECK_ARG(nbr_t, "null nbr_t"); LB_CUDA(cudaMemsetAsync(nbr_t, 0xFF, (size_t)n_in * k * 4, st)); }
   if (n_out == 0 || n_in == 0) return LB_OK;
   LB_CHECK_ARG(nbr, "null nbr");
-  kmap_transpose_kernel<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, nbr_t, n_in);
+  kmap_transpose_kernel<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, nbr_t, n_in); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -86,9 +86,10 @@ __global__ void devoxelize_fwd_kernel(const float* __restrict__ feats, const int
         if (r >= 0) {
           if (VEC == 4) {
             float4 f = __ldg((const float4*)&feats[(int64_t)r * c + j]);
-            acc[0] += wk * f.x; acc[1] += wk * f.y; acc[2] += wk * f.z; acc[3] += wk * f.w;
+            acc[0] = __fadd_rn(acc[0], __fmul_rn(wk, f.x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(wk, f.y));
+            acc[2] = __fadd_rn(acc[2], __fmul_rn(wk, f.z)); acc[3] = __fadd_rn(acc[3], __fmul_rn(wk, f.w));
           } else {
-            acc[0] += wk * __ldg(&feats[(int64_t)r * c + j]);
+            acc[0] = __fadd_rn(acc[0], __fmul_rn(wk, __ldg(&feats[(int64_t)r * c + j])));
           }
         }
       }
@@ -206,7 +207,7 @@ extern "C" int lb_count(const int32_t* idx, int64_t n, int32_t* counts, int64_t 
   if (n == 0 || m == 0) return LB_OK;
   LB_CHECK_ARG(idx, "null idx");
   int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
-  count_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(idx, n, counts, m);
+  count_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(idx, n, counts, m); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -217,7 +218,7 @@ extern "C" int lb_voxelize_fwd(const float* feats, const int32_t* idx, const int
   if (m > 0) { LB_CHECK_ARG(out, "null out"); LB_CUDA(cudaMemsetAsync(out, 0, (size_t)m * c * 4, st)); }
   if (n == 0 || m == 0) return LB_OK;
   LB_CHECK_ARG(feats && idx && counts, "null pointer");
-  voxelize_fwd_kernel<<<rows_grid(n, 8), 256, 0, st>>>(feats, idx, counts, n, m, c, out);
+  voxelize_fwd_kernel<<<rows_grid(n, 8), 256, 0, st>>>(feats, idx, counts, n, m, c, out); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -226,7 +227,7 @@ extern "C" int lb_voxelize_bwd(const float* gout, const int32_t* idx, const int3
   LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0, "bad sizes");
   if (n == 0) return LB_OK;
   LB_CHECK_ARG(gout && idx && counts && gf, "null pointer");
-  voxelize_bwd_kernel<<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(gout, idx, counts, n, m, c, gf);
+  voxelize_bwd_kernel<<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(gout, idx, counts, n, m, c, gf); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -236,8 +237,8 @@ extern "C" int lb_devoxelize_fwd(const float* feats, const int32_t* idx, const f
   if (n == 0) return LB_OK;
   LB_CHECK_ARG(feats && idx && w && out, "null pointer");
   bool vec = (c % 4 == 0) && (((uintptr_t)feats | (uintptr_t)out) & 15) == 0;
-  if (vec) devoxelize_fwd_kernel<4><<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(feats, idx, w, n, m, c, out);
-  else devoxelize_fwd_kernel<1><<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(feats, idx, w, n, m, c, out);
+  if (vec) { devoxelize_fwd_kernel<4><<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(feats, idx, w, n, m, c, out); LB_LAUNCHED(1); }
+  else { devoxelize_fwd_kernel<1><<<rows_grid(n, 8), 256, 0, as_stream(stream)>>>(feats, idx, w, n, m, c, out); LB_LAUNCHED(1); }
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -248,7 +249,7 @@ extern "C" int lb_devoxelize_bwd(const float* gout, const int32_t* idx, const fl
   if (m > 0) { LB_CHECK_ARG(gf, "null grad"); LB_CUDA(cudaMemsetAsync(gf, 0, (size_t)m * c * 4, st)); }
   if (n == 0 || m == 0) return LB_OK;
   LB_CHECK_ARG(gout && idx && w, "null pointer");
-  devoxelize_bwd_kernel<<<rows_grid(n, 8), 256, 0, st>>>(gout, idx, w, n, m, c, gf);
+  devoxelize_bwd_kernel<<<rows_grid(n, 8), 256, 0, st>>>(gout, idx, w, n, m, c, gf); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -258,7 +259,7 @@ extern "C" int lb_ti_weights(const float* coords, int64_t ld, const int64_t* idx
   if (n == 0) return LB_OK;
   LB_CHECK_ARG(coords && idx && out, "null pointer");
   int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
-  ti_weights_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(coords, ld, idx, n, scale, out);
+  ti_weights_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(coords, ld, idx, n, scale, out); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -268,9 +269,9 @@ static int cast_dispatch(const S* src, int64_t ld_s, void* dst, int dd, int64_t 
                          cudaStream_t st) {
   int64_t blocks = (rows * cols + 255) / 256, cap = (int64_t)sm_count() * 32;
   int g = (int)(blocks > cap ? cap : blocks);
-  if (dd == LB_DT_F32) cast_kernel<S, float><<<g, 256, 0, st>>>(src, ld_s, (float*)dst, ld_d, rows, cols);
-  else if (dd == LB_DT_BF16) cast_kernel<S, __nv_bfloat16><<<g, 256, 0, st>>>(src, ld_s, (__nv_bfloat16*)dst, ld_d, rows, cols);
-  else if (dd == LB_DT_F16) cast_kernel<S, __half><<<g, 256, 0, st>>>(src, ld_s, (__half*)dst, ld_d, rows, cols);
+  if (dd == LB_DT_F32) { cast_kernel<S, float><<<g, 256, 0, st>>>(src, ld_s, (float*)dst, ld_d, rows, cols); LB_LAUNCHED(1); }
+  else if (dd == LB_DT_BF16) { cast_kernel<S, __nv_bfloat16><<<g, 256, 0, st>>>(src, ld_s, (__nv_bfloat16*)dst, ld_d, rows, cols); LB_LAUNCHED(1); }
+  else if (dd == LB_DT_F16) { cast_kernel<S, __half><<<g, 256, 0, st>>>(src, ld_s, (__half*)dst, ld_d, rows, cols); LB_LAUNCHED(1); }
   else { set_error("lb_cast: bad dst dtype"); return LB_EINVAL; }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -294,7 +295,7 @@ extern "C" int lb_tta_softmax_mean_argmax(const float* logits, int64_t n_vox, in
   LB_CHECK_ARG(reps > 0 && n_pts >= 0 && n_vox >= 0, "bad sizes");
   if (n_pts == 0) return LB_OK;
   LB_CHECK_ARG(logits && inverse && prob && pred, "null pointer");
-  tta_kernel<<<rows_grid(n_pts, 8), 256, 0, as_stream(stream)>>>(logits, n_vox, n_cls, inverse, reps, n_pts, prob, pred);
+  tta_kernel<<<rows_grid(n_pts, 8), 256, 0, as_stream(stream)>>>(logits, n_vox, n_cls, inverse, reps, n_pts, prob, pred); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -235,6 +235,7 @@ __global__ void argsort_prepare(const float* __restrict__ keys, int64_t n, uint6
                                 uint32_t* __restrict__ vals) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t u = __float_as_uint(keys[i]);
+    if (u == 0x80000000u) u = 0;                   // -0.0 == +0.0 for numpy's comparison sort
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
     k64[i] = u;
     vals[i] = (uint32_t)i;
@@ -295,10 +296,10 @@ extern "C" int lb_frame_grid_build(const double* xyz, int64_t n, double cell, vo
   if (bytes < grid_bytes_for(n)) { set_error("lb_frame_grid_build: grid buffer too small"); return LB_ECAP; }
   cudaStream_t st = as_stream(stream);
   uint64_t cap = table_capacity(n);
-  grid_init_kernel<<<grid1d((int64_t)cap, 256), 256, 0, st>>>(grid, cell, n, cap);
+  grid_init_kernel<<<grid1d((int64_t)cap, 256), 256, 0, st>>>(grid, cell, n, cap); LB_LAUNCHED(1);
   if (n > 0) {
     LB_CHECK_ARG(xyz, "null xyz");
-    grid_insert_kernel<<<grid1d(n, 256), 256, 0, st>>>(xyz, n, cell, grid, cap);
+    grid_insert_kernel<<<grid1d(n, 256), 256, 0, st>>>(xyz, n, cell, grid, cap); LB_LAUNCHED(1);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -320,7 +321,7 @@ extern "C" int lb_interframe_score(const double* q_xyz, const float* q_prob, int
   }
   int64_t blocks = (nq + 7) / 8, cap = (int64_t)sm_count() * 8;
   interframe_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(
-      q_xyz, q_prob, nq, n_cls, P, dis_thresh, interd, intere, count, nn_out);
+      q_xyz, q_prob, nq, n_cls, P, dis_thresh, interd, intere, count, nn_out); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -332,7 +333,7 @@ extern "C" int lb_region_reduce(const double* interd, const float* intere, const
   if (n_regions == 0) return LB_OK;
   LB_CHECK_ARG(interd && intere && xyz && region_ptr && region_pts && sv_d && sv_e, "null pointer");
   region_reduce_kernel<<<n_regions, 256, 0, as_stream(stream)>>>(interd, intere, xyz, region_ptr, region_pts, sv_d, sv_e,
-                                                                 sv_n, sv_c);
+                                                                 sv_n, sv_c); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -347,7 +348,7 @@ extern "C" int lb_argsort_f32(const float* keys, int64_t n, int32_t* order, void
   uint64_t* k64 = (uint64_t*)ws;
   size_t off = ((size_t)n * 8 + 255) & ~(size_t)255;
   void* sws = (char*)ws + off;
-  argsort_prepare<<<grid1d(n, 256), 256, 0, st>>>(keys, n, k64, (uint32_t*)order);
+  argsort_prepare<<<grid1d(n, 256), 256, 0, st>>>(keys, n, k64, (uint32_t*)order); LB_LAUNCHED(1);
   int rc = lb_sort_pairs(k64, (uint32_t*)order, n, 32, sws, ws_bytes - off, stream);
   if (rc != LB_OK) return rc;
   LB_LAUNCH_CHECK();
@@ -366,11 +367,11 @@ extern "C" int lb_region_pairs(const float* centers, int64_t n, float radius, in
   cudaStream_t st = as_stream(stream);
   double* xyz = (double*)ws;
   void* grid = (char*)ws + (((size_t)n * 24 + 255) & ~(size_t)255);
-  f32_to_f64_xyz<<<grid1d(n * 3, 256), 256, 0, st>>>(centers, n * 3, xyz);
+  f32_to_f64_xyz<<<grid1d(n * 3, 256), 256, 0, st>>>(centers, n * 3, xyz); LB_LAUNCHED(1);
   int rc = lb_frame_grid_build(xyz, n, (double)radius * 1.01, grid, grid_bytes_for(n), stream);
   if (rc != LB_OK) return rc;
   region_pairs_kernel<<<grid1d(n, 128), 128, 0, st>>>(centers, n, radius, grid, row_counts_or_ptr, nbr_idx,
-                                                      nbr_idx ? 1 : 0);
+                                                      nbr_idx ? 1 : 0); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -1,0 +1,151 @@
+"""Live roofline accounting for bench.py (CUDA events on the launching stream; nothing here runs under a profiler)."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}   # B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return dict(FALLBACK, source="fallback (B200_PROFILING.md)")
+
+
+class ConvTrace:
+    """Installed as functional.CONV_TRACE: records one (start, end) event pair per lb_conv_fwd launch."""
+
+    def __init__(self):
+        self.records = []
+
+    def begin(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def end(self, ev0, nbr, n_out, k_vol, c_in, c_out, tc):
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        self.records.append((ev0, ev1, nbr, int(n_out), k_vol, c_in, c_out, bool(tc)))
+
+    def summarise(self):
+        torch.cuda.synchronize()
+        rows = []
+        pair_cache = {}
+        for ev0, ev1, nbr, n_out, k, cin, cout, tc in self.records:
+            if nbr is None:
+                pairs = n_out
+            else:
+                key = (nbr.data_ptr(), tuple(nbr.shape), n_out)
+                if key not in pair_cache:
+                    pair_cache[key] = int((nbr[:, :n_out] >= 0).sum().item())
+                pairs = pair_cache[key]
+            rows.append(dict(ms=ev0.elapsed_time(ev1), pairs=pairs, n_out=n_out, k=k, cin=cin, cout=cout, tc=tc,
+                             flops=2.0 * pairs * cin * cout, dense_flops=2.0 * n_out * k * cin * cout))
+        return rows
+
+
+def conv_roofline(run, resident, steps=3):
+    """Events around every sparse-conv launch for ``steps`` steps.  achieved = algorithmic FLOPs (2 * map pairs * Cin *
+    Cout, summed over the tcgen05 launches) / their summed device time."""
+    from .compat.nn import functional as F
+    peaks = measured_peaks()
+    run(*resident[0])
+    torch.cuda.synchronize()
+    trace = ConvTrace()
+    F.CONV_TRACE = trace
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        e0.record()
+        for i in range(steps):
+            run(*resident[i % len(resident)])
+        e1.record()
+    finally:
+        F.CONV_TRACE = None
+    rows = trace.summarise()
+    step_ms = e0.elapsed_time(e1) / steps
+    tc = [r for r in rows if r["tc"]]
+    simt = [r for r in rows if not r["tc"]]
+    tc_ms, tc_fl = sum(r["ms"] for r in tc), sum(r["flops"] for r in tc)
+    peak = float(peaks.get("bf16_tflops_sustained", FALLBACK["bf16_tflops_sustained"]))
+    achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    best = max(tc, key=lambda r: r["flops"] / max(r["ms"], 1e-6)) if tc else None
+    return {
+        "bound": "tensor", "kernel": "lb::conv_tc_kernel (tcgen05 implicit-GEMM sparse conv)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "launches_per_step": len(tc) / steps, "avg_launch_ms": tc_ms / max(len(tc), 1),
+        "algorithmic_gflop_per_step": tc_fl / steps / 1e9,
+        "dense_gflop_per_step": sum(r["dense_flops"] for r in tc) / steps / 1e9,
+        "kernel_ms_per_step": tc_ms / steps, "share_of_step": (tc_ms / steps) / step_ms,
+        "simt_conv_ms_per_step": sum(r["ms"] for r in simt) / steps, "instrumented_step_ms": step_ms,
+        "best_layer": None if best is None else {k: best[k] for k in ("cin", "cout", "k", "n_out", "pairs", "ms")}
+        | {"tflops": best["flops"] / (best["ms"] * 1e-3) / 1e12},
+        "how": "CUDA events on the launching stream around each conv launch; algorithmic FLOPs = 2*pairs*Cin*Cout from the live kernel maps",
+    }
+
+
+def scoring_extras(ms_per_step: float, dev, n_frames: int = 25, n_cls: int = 19):
+    """Second half of the metric: LiDAL scored frames/s = frames completing prob_inference (one 8-view step) + TTA tail
+    + inter-frame scoring + region reduce.  Scoring kernels report achieved HBM GB/s against the measured copy peak."""
+    from . import score, synth
+    peaks = measured_peaks()
+    seq = synth.make_sequence(n_frames, "SK", seed=77)
+    sc = score.SequenceScorer(dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    probs = [synth.synthetic_probs(seq.xyz[i], n_cls, 300 + i) for i in range(n_frames)]
+    g0, g1 = ev(), ev()
+    g0.record()
+    for i in range(n_frames):
+        sc.add_frame(seq.xyz[i], probs[i], seq.sv_id[i], seq.sv2point[i])
+    g1.record()
+    fid = n_frames // 2
+    sc.score_frame_device(fid)
+    torch.cuda.synchronize()
+    reps = 10
+    s0, s1 = ev(), ev()
+    s0.record()
+    for _ in range(reps):
+        out = sc.score_frame_device(fid)
+    s1.record()
+    torch.cuda.synchronize()
+    score_ms = s0.elapsed_time(s1) / reps
+    _, _, cnt = sc.score_points(fid)
+    matched = int(cnt.sum().item())
+    npts = sc.frames[fid].n
+    nn_pts = sum(sc.frames[n].n for n in score.neighbour_ids(fid, n_frames))
+    alg_bytes = npts * n_cls * 4 + npts * 24 + nn_pts * 24 + matched * n_cls * 4 + npts * 12
+    # TTA tail on a batch-8 shaped logits tensor
+    nv = 8 * 92000
+    logits = torch.randn(nv, n_cls, device=dev)
+    inv = torch.cat([torch.randint(0, 92000, (npts,), device=dev) + v * 92000 for v in range(8)])
+    score.tta_tail(logits, inv, 8)
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(reps):
+        score.tta_tail(logits, inv, 8)
+    t1.record()
+    torch.cuda.synchronize()
+    tail_ms = t0.elapsed_time(t1) / reps
+    tail_bytes = 8 * npts * (n_cls * 4 + 8) + npts * (n_cls * 4 + 8)
+    grid_ms = g0.elapsed_time(g1) / n_frames      # includes the H2D upload of xyz + prob of each frame
+    hbm = float(peaks.get("hbm_gbs", FALLBACK["hbm_gbs"]))
+    frame_ms = ms_per_step + tail_ms + score_ms
+    return {
+        "lidal_scored_frames_per_sec": 1e3 / frame_ms, "frame_ms": frame_ms,
+        "prob_inference_ms": ms_per_step, "tta_tail_ms": tail_ms, "interframe_score_ms": score_ms,
+        "frame_upload_and_grid_build_ms": grid_ms, "points_per_frame": npts, "matched_pairs": matched,
+        "score_roofline": {"bound": "hbm", "achieved": alg_bytes / (score_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": alg_bytes / (score_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg_bytes},
+        "tta_roofline": {"bound": "hbm", "achieved": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": tail_bytes},
+        "note": "frame = one 8-view TTA step of the benchmarked network + tail + scoring against a resident 24-frame window",
+    }
