@@ -80,6 +80,12 @@ int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t* nbmaps, i
 int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* nbr_t, int64_t n_in,
                       void* stream);
 
+/* torch.unique(keys) with inverse (network/utils.py:18-19 fused): uniq int64 [<=n] ascending, n_unique device
+ * int32[1], inverse int32 [n] (optional) = position of keys[i] in uniq.  key_bits: significant low bits of the keys. */
+size_t lb_unique_ws_bytes(int64_t n);
+int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64_t* uniq, int32_t* n_unique, int32_t* inverse,
+                  void* ws, size_t ws_bytes, void* stream);
+
 /* Stable LSD radix sort of (uint64 key, uint32 value) pairs on bits [0, end_bit). */
 size_t lb_sort_pairs_ws_bytes(int64_t n);
 int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* ws, size_t ws_bytes, void* stream);
@@ -101,6 +107,7 @@ int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* 
 
 #define LB_CONV_RELU 1      /* apply ReLU last                                   */
 #define LB_CONV_FORCE_SIMT 2 /* use the CUDA-core kernel even where tcgen05 applies */
+#define LB_CONV_RELU_FIRST 4 /* with LB_CONV_RELU: relu(v*scale+shift) + residual (SPVCNN point branch)  */
 
 typedef struct lb_conv_args {
   const void* in;          /* [n_in, ld_in] act_dtype                                        */
@@ -149,6 +156,21 @@ int lb_devoxelize_bwd(const float* grad_out, const int32_t* idx, const float* w,
 /* F.calc_ti_weights: coords f32 [n, ld_c>=3], idx int64 [8,n] (corner-major), out f32 [8,n]. */
 int lb_ti_weights(const float* coords, int64_t ld_c, const int64_t* idx, int64_t n, float scale, float* out,
                   void* stream);
+
+/* Fused forms used by the inference engine (same arithmetic as the separate calls above):
+ * lb_point_cell_query   network/utils.py:42-48 : idx[i] = voxel holding floor(p/stride)*stride, -1 if none.
+ * lb_point_corner_query network/utils.py:69-79 : the 8 surrounding voxels (x slowest, z fastest) and their
+ *                       F.calc_ti_weights, idx int32 [n,8], w f32 [n,8].   pts f32 [n, ld>=4] = (x,y,z,...,batch LAST).
+ * table: lb_hashtable_build over lb_hash(voxel coords).
+ * *_ex: 16-bit or fp32 features with a row stride (elements); voxelize accumulates in fp32. */
+int lb_point_cell_query(const float* pts, int64_t ld, int64_t n, int stride, const void* table, size_t table_bytes,
+                        int32_t* idx, void* stream);
+int lb_point_corner_query(const float* pts, int64_t ld, int64_t n, int stride, const void* table, size_t table_bytes,
+                          int32_t* idx, float* w, void* stream);
+int lb_voxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_feats, const int32_t* idx, const int32_t* counts,
+                       int64_t n, int64_t m, int c, float* out, void* stream);
+int lb_devoxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_feats, const int32_t* idx, const float* w,
+                         int64_t n, int64_t m, int c, void* out, int out_dtype, int64_t ld_out, void* stream);
 
 /* ------------------------------------------------------------------ prob_inference tail
  * score/prob_inference.py:100-113: gather logits by inverse index, softmax, mean over views, argmax.

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liblidal_b200.so")
 
 LB_DT_BF16, LB_DT_F16, LB_DT_F32 = 0, 1, 2
-LB_CONV_RELU, LB_CONV_FORCE_SIMT = 1, 2
+LB_CONV_RELU, LB_CONV_FORCE_SIMT, LB_CONV_RELU_FIRST = 1, 2, 4
 DT_OF = {torch.bfloat16: LB_DT_BF16, torch.float16: LB_DT_F16, torch.float32: LB_DT_F32}
 
 vp, i64, i32, sz, dbl, flt = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double, C.c_float
@@ -49,6 +49,8 @@ SIGNATURES = {
     "lb_kmap_compact_ws_bytes": (sz, [i64, i32]),
     "lb_kmap_compact": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
     "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
+    "lb_unique_ws_bytes": (sz, [i64]),
+    "lb_unique_i64": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
     "lb_sort_pairs_ws_bytes": (sz, [i64]),
     "lb_sort_pairs": (i32, [vp, vp, i64, i32, vp, sz, vp]),
     "lb_conv_pack_weight": (i32, [vp, i32, i32, i32, i32, vp, vp]),
@@ -61,6 +63,10 @@ SIGNATURES = {
     "lb_devoxelize_fwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
     "lb_devoxelize_bwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
     "lb_ti_weights": (i32, [vp, i64, vp, i64, flt, vp, vp]),
+    "lb_point_cell_query": (i32, [vp, i64, i64, i32, vp, sz, vp, vp]),
+    "lb_point_corner_query": (i32, [vp, i64, i64, i32, vp, sz, vp, vp, vp]),
+    "lb_voxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, vp]),
+    "lb_devoxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, i32, i64, vp]),
     "lb_tta_softmax_mean_argmax": (i32, [vp, i64, i32, vp, i32, i64, vp, vp, vp]),
     "lb_frame_grid_bytes": (sz, [i64]),
     "lb_frame_grid_build": (i32, [vp, i64, dbl, vp, sz, vp]),

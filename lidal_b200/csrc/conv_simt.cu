@@ -104,8 +104,9 @@ conv_simt_kernel(const T* __restrict__ in, int64_t ld_in, int64_t n_in, O* __res
             float v = acc[i];
             if (scale) v *= __ldg(&scale[j]);
             if (shift) v += __ldg(&shift[j]);
+            if (relu == 2) v = fmaxf(v, 0.f);
             if (res) v += to_f<T>(res[orow * ld_res + j]);
-            if (relu) v = fmaxf(v, 0.f);
+            if (relu == 1) v = fmaxf(v, 0.f);
             out[orow * ld_out + j] = from_f<O>(v);
           }
         }
@@ -122,7 +123,7 @@ static int launch_simt(const lb_conv_args& a, cudaStream_t st) {
   conv_simt_kernel<T, O><<<grid, ST_THREADS, smem, st>>>(
       (const T*)a.in, a.ld_in, a.n_in, (O*)a.out, a.ld_out, a.n_out, a.n_out_dev, a.nbr, a.nbr_ld, a.out_rows,
       (const T*)a.weight, a.k_vol, a.c_in, a.c_out, a.scale, a.shift, (const T*)a.residual, a.ld_res,
-      (a.flags & LB_CONV_RELU) ? 1 : 0); LB_LAUNCHED(1);
+      (a.flags & LB_CONV_RELU) ? ((a.flags & LB_CONV_RELU_FIRST) ? 2 : 1) : 0); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -327,6 +327,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+          if (p.relu == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
           if (res_row) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -344,7 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
               }
             }
           }
-          if (p.relu) {
+          if (p.relu == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
@@ -440,7 +444,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.n_out_dev = a.n_out_dev; p.nbr = a.nbr; p.nbr_ld = a.nbr_ld; p.out_rows = a.out_rows;
   p.k_vol = a.k_vol; p.c_in = a.c_in; p.c_out = a.c_out;
   p.scale = a.scale; p.shift = a.shift; p.residual = (const char*)a.residual; p.ld_res = a.ld_res;
-  p.out_dtype = a.out_dtype; p.relu = (a.flags & LB_CONV_RELU) ? 1 : 0; p.is_bf16 = a.act_dtype == LB_DT_BF16;
+  p.out_dtype = a.out_dtype; p.relu = (a.flags & LB_CONV_RELU) ? ((a.flags & LB_CONV_RELU_FIRST) ? 2 : 1) : 0; p.is_bf16 = a.act_dtype == LB_DT_BF16;
   int cols = 32;
   while (cols < 2 * a.c_out) cols <<= 1;
   p.tmem_cols = cols;

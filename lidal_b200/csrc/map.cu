@@ -495,3 +495,50 @@ extern "C" int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_o
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+
+// ------------------------------------------------------------------------------------------ unique with inverse
+namespace lb {
+__global__ void uq_iota(uint32_t* v, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
+}
+__global__ void uq_emit(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                        const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
+                        int64_t* __restrict__ uniq, int* __restrict__ inverse) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t id = pos[i] + flags[i] - 1;          // exclusive scan of flags -> id of the run this element belongs to
+    if (flags[i]) uniq[id] = (int64_t)keys[i];
+    if (inverse) inverse[vals[i]] = (int)id;
+  }
+}
+}  // namespace lb
+extern "C" size_t lb_unique_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return align256((size_t)n * 8) + 3 * align256((size_t)n * 4) + align256(scan_ws_bytes(n)) +
+         align256(lb_sort_pairs_ws_bytes(n)) + 256;
+}
+extern "C" int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64_t* uniq, int32_t* n_unique,
+                             int32_t* inverse, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && n_unique && ws && key_bits > 0 && key_bits <= 64, "bad arguments");
+  if (ws_bytes < lb_unique_ws_bytes(n)) { set_error("lb_unique_i64: workspace too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) { LB_CUDA(cudaMemsetAsync(n_unique, 0, 4, st)); return LB_OK; }
+  LB_CHECK_ARG(keys && uniq, "null pointer");
+  char* p = (char*)ws;
+  uint64_t* k = (uint64_t*)p; p += align256((size_t)n * 8);
+  uint32_t* v = (uint32_t*)p; p += align256((size_t)n * 4);
+  uint32_t* flags = (uint32_t*)p; p += align256((size_t)n * 4);
+  uint32_t* pos = (uint32_t*)p; p += align256((size_t)n * 4);
+  void* scan_ws = p; p += align256(scan_ws_bytes(n));
+  void* sort_ws = p;
+  LB_CUDA(cudaMemcpyAsync(k, keys, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  int g = grid_for(n, 256);
+  uq_iota<<<g, 256, 0, st>>>(v, n); LB_LAUNCHED(1);
+  int rc = lb_sort_pairs(k, v, n, key_bits, sort_ws, lb_sort_pairs_ws_bytes(n), stream);
+  if (rc != LB_OK) return rc;
+  ds_flags<<<g, 256, 0, st>>>(k, n, flags); LB_LAUNCHED(1);
+  rc = exclusive_scan_u32(flags, pos, n, (uint32_t*)n_unique, scan_ws, st);
+  if (rc != LB_OK) return rc;
+  uq_emit<<<g, 256, 0, st>>>(k, v, flags, pos, n, uniq, inverse); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

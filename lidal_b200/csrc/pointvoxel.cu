@@ -299,3 +299,176 @@ extern "C" int lb_tta_softmax_mean_argmax(const float* logits, int64_t n_vox, in
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+
+// ---------------------------------------------------------------------------------------- fused point queries (engine)
+namespace lb {
+// network/utils.py:42-48: cell = floor(p / s) * s (int), hash, lookup among the voxel hashes.
+__global__ void point_cell_query_kernel(const float* __restrict__ pts, int64_t ld, int64_t n, int s, TableView t,
+                                        int* __restrict__ idx) {
+  const float fs = (float)s;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int cx = (int)floorf(__fdiv_rn(pts[i * ld], fs)) * s, cy = (int)floorf(__fdiv_rn(pts[i * ld + 1], fs)) * s,
+        cz = (int)floorf(__fdiv_rn(pts[i * ld + 2], fs)) * s;
+    idx[i] = table_find(t, (uint64_t)fnv60(cx, cy, cz, (int)pts[i * ld + ld - 1]));
+  }
+}
+// network/utils.py:69-79: 8 corners (x slowest, z fastest) + F.calc_ti_weights, one thread per point.
+__global__ void point_corner_query_kernel(const float* __restrict__ pts, int64_t ld, int64_t n, int s, TableView t,
+                                          int* __restrict__ idx /*[n,8]*/, float* __restrict__ w /*[n,8]*/) {
+  const float fs = (float)s;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[3], lo[3], hi[3];
+    int c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      p[a] = pts[i * ld + a];
+      float fl = floorf(__fdiv_rn(p[a], fs));
+      c[a] = (int)fl * s;
+      float pf = (s != 1) ? __fmul_rn(fl, fs) : floorf(p[a]);
+      float pc = __fadd_rn(pf, fs);
+      hi[a] = __fsub_rn(pc, p[a]);
+      lo[a] = __fsub_rn(p[a], pf);
+    }
+    const int b = (int)pts[i * ld + ld - 1];
+    const float s3 = fs * fs * fs;
+    float wk[8], sum = 0.f;
+    int ik[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ox = (k >> 2) & 1, oy = (k >> 1) & 1, oz = k & 1;
+      ik[k] = table_find(t, (uint64_t)fnv60(c[0] + ox * s, c[1] + oy * s, c[2] + oz * s, b));
+      float v = __fmul_rn(__fmul_rn(ox ? lo[0] : hi[0], oy ? lo[1] : hi[1]), oz ? lo[2] : hi[2]);
+      if (s != 1) v = __fdiv_rn(v, s3);
+      if (ik[k] < 0) v = 0.f;
+      wk[k] = v;
+      sum = __fadd_rn(sum, v);
+    }
+    sum = __fadd_rn(sum, 1e-8f);
+    int4* ip = (int4*)&idx[i * 8];
+    float4* wp = (float4*)&w[i * 8];
+    ip[0] = make_int4(ik[0], ik[1], ik[2], ik[3]);
+    ip[1] = make_int4(ik[4], ik[5], ik[6], ik[7]);
+    wp[0] = make_float4(__fdiv_rn(wk[0], sum), __fdiv_rn(wk[1], sum), __fdiv_rn(wk[2], sum), __fdiv_rn(wk[3], sum));
+    wp[1] = make_float4(__fdiv_rn(wk[4], sum), __fdiv_rn(wk[5], sum), __fdiv_rn(wk[6], sum), __fdiv_rn(wk[7], sum));
+  }
+}
+
+template <typename T> __device__ __forceinline__ float ld_f(const T* p);
+template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_f<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ld_f<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ void st_f(T* p, float v);
+template <> __device__ __forceinline__ void st_f<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_f<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void st_f<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// 8 lanes x 2 channels... generic row-strided variants: lane j walks channels j, j+32, ... (2- or 4-byte elements)
+template <typename TI>
+__global__ void voxelize_ex_kernel(const TI* __restrict__ feats, int64_t ld_f_, const int* __restrict__ idx,
+                                   const int* __restrict__ counts, int64_t n, int64_t m, int c, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int v = __ldg(&idx[i]);
+    if (v < 0 || v >= m) continue;
+    int cnt = __ldg(&counts[v]);
+    if (cnt == 0) continue;
+    float fc = (float)cnt;
+    for (int j = lane; j < c; j += 32) atomicAdd(&out[(int64_t)v * c + j], ld_f<TI>(&feats[i * ld_f_ + j]) / fc);
+  }
+}
+template <typename TI, typename TO>
+__global__ void devoxelize_ex_kernel(const TI* __restrict__ feats, int64_t ld_f_, const int* __restrict__ idx,
+                                     const float* __restrict__ w, int64_t n, int64_t m, int c, TO* __restrict__ out,
+                                     int64_t ld_o) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int my_idx = -1;
+    float my_w = 0.f;
+    if (lane < 8) {
+      my_idx = __ldg(&idx[i * 8 + lane]);
+      my_w = __ldg(&w[i * 8 + lane]);
+      if (my_idx >= m) my_idx = -1;
+    }
+    int rk[8];
+    float wk8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      rk[k] = __shfl_sync(0xffffffffu, my_idx, k);
+      wk8[k] = __shfl_sync(0xffffffffu, my_w, k);
+    }
+    for (int j = lane; j < c; j += 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (rk[k] >= 0) acc = __fadd_rn(acc, __fmul_rn(wk8[k], ld_f<TI>(&feats[(int64_t)rk[k] * ld_f_ + j])));
+      st_f<TO>(&out[i * ld_o + j], acc);
+    }
+  }
+}
+}  // namespace lb
+
+extern "C" int lb_point_cell_query(const float* pts, int64_t ld, int64_t n, int stride, const void* table,
+                                   size_t table_bytes, int32_t* idx, void* stream) {
+  LB_CHECK_ARG(n >= 0 && ld >= 4 && stride > 0, "bad sizes");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(pts && table && idx, "null pointer");
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  point_cell_query_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(
+      pts, ld, n, stride, table_view(table, table_bytes), idx); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_point_corner_query(const float* pts, int64_t ld, int64_t n, int stride, const void* table,
+                                     size_t table_bytes, int32_t* idx, float* w, void* stream) {
+  LB_CHECK_ARG(n >= 0 && ld >= 4 && stride > 0, "bad sizes");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(pts && table && idx && w, "null pointer");
+  LB_CHECK_ARG((((uintptr_t)idx | (uintptr_t)w) & 15) == 0, "idx / w must be 16-byte aligned");
+  int64_t blocks = (n + 127) / 128, cap = (int64_t)sm_count() * 16;
+  point_corner_query_kernel<<<(int)(blocks > cap ? cap : blocks), 128, 0, as_stream(stream)>>>(
+      pts, ld, n, stride, table_view(table, table_bytes), idx, w); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_voxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_f, const int32_t* idx,
+                                  const int32_t* counts, int64_t n, int64_t m, int c, float* out, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0 && ld_f >= c, "bad sizes");
+  cudaStream_t st = as_stream(stream);
+  if (m > 0) { LB_CHECK_ARG(out, "null out"); LB_CUDA(cudaMemsetAsync(out, 0, (size_t)m * c * 4, st)); }
+  if (n == 0 || m == 0) return LB_OK;
+  LB_CHECK_ARG(feats && idx && counts, "null pointer");
+  int g = rows_grid(n, 8);
+  if (feats_dtype == LB_DT_F32) { voxelize_ex_kernel<float><<<g, 256, 0, st>>>((const float*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+  else if (feats_dtype == LB_DT_BF16) { voxelize_ex_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+  else if (feats_dtype == LB_DT_F16) { voxelize_ex_kernel<__half><<<g, 256, 0, st>>>((const __half*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+  else { set_error("lb_voxelize_fwd_ex: bad dtype"); return LB_EINVAL; }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+template <typename TI>
+static int devox_out(const TI* feats, int64_t ld_f, const int32_t* idx, const float* w, int64_t n, int64_t m, int c,
+                     void* out, int od, int64_t ld_o, cudaStream_t st) {
+  int g = rows_grid(n, 8);
+  if (od == LB_DT_F32) { devoxelize_ex_kernel<TI, float><<<g, 256, 0, st>>>(feats, ld_f, idx, w, n, m, c, (float*)out, ld_o); LB_LAUNCHED(1); }
+  else if (od == LB_DT_BF16) { devoxelize_ex_kernel<TI, __nv_bfloat16><<<g, 256, 0, st>>>(feats, ld_f, idx, w, n, m, c, (__nv_bfloat16*)out, ld_o); LB_LAUNCHED(1); }
+  else if (od == LB_DT_F16) { devoxelize_ex_kernel<TI, __half><<<g, 256, 0, st>>>(feats, ld_f, idx, w, n, m, c, (__half*)out, ld_o); LB_LAUNCHED(1); }
+  else { set_error("lb_devoxelize_fwd_ex: bad out dtype"); return LB_EINVAL; }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_devoxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_f, const int32_t* idx, const float* w,
+                                    int64_t n, int64_t m, int c, void* out, int out_dtype, int64_t ld_o, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0 && ld_f >= c && ld_o >= c, "bad sizes");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(feats && idx && w && out, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (feats_dtype == LB_DT_F32) return devox_out((const float*)feats, ld_f, idx, w, n, m, c, out, out_dtype, ld_o, st);
+  if (feats_dtype == LB_DT_BF16) return devox_out((const __nv_bfloat16*)feats, ld_f, idx, w, n, m, c, out, out_dtype, ld_o, st);
+  if (feats_dtype == LB_DT_F16) return devox_out((const __half*)feats, ld_f, idx, w, n, m, c, out, out_dtype, ld_o, st);
+  set_error("lb_devoxelize_fwd_ex: bad feats dtype");
+  return LB_EINVAL;
+}

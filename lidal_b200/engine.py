@@ -1,0 +1,298 @@
+"""Fused inference plan for LiDAL's two networks (eval mode), built from any module with the reference's layout
+(network/minkunet.py:14-122, network/spvcnn.py:9-155 -- or the mirrors in lidal_b200.network).
+
+What changes relative to running the modules one by one through ``lidal_b200.compat``:
+  * eval-mode BatchNorm, ReLU and the residual add are folded into the convolution epilogue (one kernel per conv,
+    one HBM round trip per activation instead of four);
+  * activations stay 16-bit (bf16 default) between convolutions, fp32 accumulate in TMEM;
+  * ``torchsparse.cat`` is free: producers write straight into column slices of the concatenated buffer;
+  * packed weights and folded scale/shift are prepared once at construction;
+  * SPVCNN's point branch uses fused query kernels (floor/hash/lookup/trilinear weights in one pass) and 16-bit
+    gathers; ``Linear+BN1d+ReLU`` point MLPs run on the same tcgen05 kernel as 1x1 convolutions with the
+    devoxelised features as the epilogue's residual.
+Arithmetic is otherwise the reference's: same kernel maps, same voxel order, same offset order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .compat.nn import functional as F
+from .compat.nn.utils import get_kernel_offsets
+
+
+def _fold_bn(bn, extra_bias=None):
+    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
+    shift = (bn.bias - bn.running_mean * scale).float()
+    if extra_bias is not None:
+        shift = shift + extra_bias.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class _Conv:
+    """One fused launch: packed 16-bit weight [K, Cout, Cin] + per-channel scale/shift + flags."""
+
+    def __init__(self, kernel, bn=None, relu=False, dtype=torch.bfloat16, bias=None, pad_out_to=None):
+        w = kernel.detach()
+        if w.dim() == 2:
+            w = w.unsqueeze(0)
+        self.k, self.cin, self.cout = w.shape
+        self.cout_real = self.cout
+        dev = w.device
+        if bn is not None:
+            self.scale, self.shift = (t.detach().to(dev) for t in _fold_bn(bn, bias))
+        else:
+            self.scale = None
+            self.shift = bias.detach().float().contiguous() if bias is not None else None
+        if pad_out_to and self.cout % pad_out_to:
+            pad = pad_out_to - self.cout % pad_out_to
+            w = torch.cat([w, torch.zeros(self.k, self.cin, pad, device=dev, dtype=w.dtype)], 2)
+            if self.shift is not None:
+                self.shift = torch.cat([self.shift, torch.zeros(pad, device=dev)])
+            if self.scale is not None:
+                self.scale = torch.cat([self.scale, torch.ones(pad, device=dev)])
+            self.cout += pad
+        self.w = F.pack_weight(w.float(), dtype)
+        self.relu = relu
+
+    def __call__(self, x, nbr, n_out, out=None, residual=None, out_dtype=None, relu_first=False):
+        out_dtype = out_dtype or x.dtype
+        if out is None:
+            out = torch.empty((n_out, self.cout), dtype=out_dtype, device=x.device)
+        a = L.ConvArgs()
+        a.inp, a.n_in, a.ld_in = x.data_ptr(), x.shape[0], x.stride(0)
+        a.out, a.n_out, a.ld_out = out.data_ptr(), n_out, out.stride(0)
+        a.n_out_dev = None
+        a.nbr, a.nbr_ld = (nbr.data_ptr(), nbr.stride(0)) if nbr is not None else (None, 0)
+        a.out_rows = None
+        a.weight, a.k_vol, a.c_in, a.c_out = self.w.data_ptr(), self.k, self.cin, self.cout
+        a.scale = self.scale.data_ptr() if self.scale is not None else None
+        a.shift = self.shift.data_ptr() if self.shift is not None else None
+        a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
+        a.act_dtype, a.out_dtype = L.DT_OF[x.dtype], L.DT_OF[out.dtype]
+        a.flags = (L.LB_CONV_RELU if self.relu else 0) | (L.LB_CONV_RELU_FIRST if relu_first else 0)
+        trace = F.CONV_TRACE
+        ev = trace.begin() if trace is not None else None
+        L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
+        if trace is not None:
+            tc = L.lib().lb_conv_uses_tensor_cores(self.k, self.cin, self.cout, a.act_dtype) and x.stride(0) % 8 == 0
+            trace.end(ev, nbr, n_out, self.k, self.cin, self.cout, tc)
+        return out
+
+
+class _Res:
+    def __init__(self, block, dtype):
+        net = block.net
+        self.c1 = _Conv(net[0].kernel, net[1], relu=True, dtype=dtype)
+        self.c2 = _Conv(net[3].kernel, net[4], relu=True, dtype=dtype)        # ReLU after the residual add
+        ds = block.downsample
+        self.skip = None if isinstance(ds, torch.nn.Identity) else _Conv(ds[0].kernel, ds[1], relu=False, dtype=dtype)
+
+    def __call__(self, x, nbr, n, out=None):
+        t = self.c1(x, nbr, n)
+        s = x if self.skip is None else self.skip(x, None, n)
+        return self.c2(t, nbr, n, out=out, residual=s)
+
+
+_OFFSETS = {}
+
+
+def _offsets(ks, stride, dev):
+    key = (ks, stride, str(dev))
+    if key not in _OFFSETS:
+        _OFFSETS[key] = get_kernel_offsets(ks, stride, 1, device=dev)
+    return _OFFSETS[key]
+
+
+class Maps:
+    """Coordinates and neighbour tables of the 5 resolution levels (9 kernel maps) for one batch."""
+
+    def __init__(self, coords):
+        self.coords, self.n, self.nbr3, self.nbr_dn, self.nbr_up, self.tables = [coords], [coords.shape[0]], [], [], [], []
+        dev = coords.device
+        for lvl in range(5):
+            s = 2 ** lvl
+            c = self.coords[lvl]
+            table = F._build_table(F.sphash(c))
+            self.tables.append(table)
+            off3 = _offsets(3, s, dev)
+            nbr3 = torch.empty((27, c.shape[0]), dtype=torch.int, device=dev)
+            L.check(L.lib().lb_kmap_query(L.ptr(table[0]), table[1], L.ptr(c), c.shape[0], None, L.ptr(off3), 27,
+                                          L.ptr(nbr3), L.stream()))
+            self.nbr3.append(nbr3)
+            if lvl == 4:
+                break
+            cn = F.spdownsample(c, 2, 2, s)
+            off2 = _offsets(2, s, dev)
+            dn = torch.empty((8, cn.shape[0]), dtype=torch.int, device=dev)
+            L.check(L.lib().lb_kmap_query(L.ptr(table[0]), table[1], L.ptr(cn), cn.shape[0], None, L.ptr(off2), 8,
+                                          L.ptr(dn), L.stream()))
+            up = torch.empty((8, c.shape[0]), dtype=torch.int, device=dev)
+            L.check(L.lib().lb_kmap_transpose(L.ptr(dn), dn.stride(0), cn.shape[0], 8, L.ptr(up), c.shape[0], L.stream()))
+            self.coords.append(cn)
+            self.n.append(cn.shape[0])
+            self.nbr_dn.append(dn)
+            self.nbr_up.append(up)
+
+
+class InferenceEngine:
+    def __init__(self, model, dtype=torch.bfloat16):
+        assert not model.training, "InferenceEngine folds BatchNorm: call model.eval() first"
+        self.dtype = dtype
+        self.is_spvcnn = hasattr(model, "point_transforms")
+        st = model.stem
+        self.stem0 = _Conv(st[0].kernel, st[1], relu=True, dtype=dtype)
+        self.stem1 = _Conv(st[3].kernel, st[4], relu=True, dtype=dtype)
+        self.down, self.enc = [], []
+        for i in range(1, 5):
+            stage = getattr(model, f"stage{i}")
+            self.down.append(_Conv(stage[0].net[0].kernel, stage[0].net[1], relu=True, dtype=dtype))
+            self.enc.append((_Res(stage[1], dtype), _Res(stage[2], dtype)))
+        self.up, self.dec = [], []
+        for i in range(1, 5):
+            up = getattr(model, f"up{i}")
+            self.up.append(_Conv(up[0].net[0].kernel, up[0].net[1], relu=True, dtype=dtype))
+            self.dec.append((_Res(up[1][0], dtype), _Res(up[1][1], dtype)))
+        lin = model.classifier[0]
+        self.n_cls = lin.out_features
+        self.classifier = _Conv(lin.weight.detach().t().contiguous(), None, relu=False, dtype=dtype, bias=lin.bias,
+                                pad_out_to=32)
+        if self.is_spvcnn:
+            self.mlp = [_Conv(seq[0].weight.detach().t().contiguous(), seq[1], relu=True, dtype=dtype, bias=seq[0].bias)
+                        for seq in model.point_transforms]
+            self.pres, self.vres = model.pres, model.vres
+        self.device = lin.weight.device
+
+    # ---- trunk pieces
+    def _cast(self, x, dtype):
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        L.check(L.lib().lb_cast(L.ptr(x), L.DT_OF[x.dtype], x.stride(0), L.ptr(out), L.DT_OF[dtype], out.stride(0),
+                                x.shape[0], x.shape[1], L.stream()))
+        return out
+
+    def _stem(self, feats16, m, cat4):
+        a = self.stem0(feats16, m.nbr3[0], m.n[0])
+        return self.stem1(a, m.nbr3[0], m.n[0], out=cat4[:, self.up[3].cout:])
+
+    def _encode(self, x, m, lvl, out=None):
+        """stage `lvl` (1..4): strided conv from level lvl-1, two residual blocks."""
+        d = self.down[lvl - 1](x, m.nbr_dn[lvl - 1], m.n[lvl])
+        r = self.enc[lvl - 1][0](d, m.nbr3[lvl], m.n[lvl])
+        return self.enc[lvl - 1][1](r, m.nbr3[lvl], m.n[lvl], out=out)
+
+    def _decode(self, y, m, i, cat):
+        """up`i` (1..4): transposed conv to level 4-i into the left columns of `cat`, two residual blocks."""
+        lvl = 4 - i
+        self.up[i - 1](y, m.nbr_up[lvl], m.n[lvl], out=cat[:, : self.up[i - 1].cout])
+        r = self.dec[i - 1][0](cat, m.nbr3[lvl], m.n[lvl])
+        return self.dec[i - 1][1](r, m.nbr3[lvl], m.n[lvl])
+
+    def _cat_buffers(self, m):
+        dev, dt = self.device, self.dtype
+        # cat_i = [up_i output | encoder skip] at level 4-i
+        widths = [self.up[i].cout + self.dec[i][0].c1.cin - self.up[i].cout for i in range(4)]
+        return [torch.empty((m.n[3 - i], widths[i]), dtype=dt, device=dev) for i in range(4)]
+
+    @torch.no_grad()
+    def __call__(self, coords, feats):
+        L.require_cuda(coords, feats)
+        return self._spvcnn(coords, feats) if self.is_spvcnn else self._minkunet(coords, feats)
+
+    def _minkunet(self, coords, feats):
+        m = Maps(coords.contiguous())
+        cats = self._cat_buffers(m)
+        x = self._stem(self._cast(feats.contiguous(), self.dtype), m, cats[3])
+        for lvl in range(1, 5):
+            skip_out = cats[3 - lvl][:, self.up[3 - lvl].cout:] if lvl < 4 else None
+            x = self._encode(x, m, lvl, out=skip_out)
+        y = x
+        for i in range(1, 5):
+            y = self._decode(y, m, i, cats[i - 1])
+        logits = self.classifier(y, None, m.n[0], out_dtype=torch.float32)
+        return logits[:, : self.n_cls]
+
+    # ---- SPVCNN point branch
+    def _table_of(self, m, lvl):
+        return m.tables[lvl]
+
+    def _corner_query(self, pts, m, lvl):
+        n = pts.shape[0]
+        idx = torch.empty((n, 8), dtype=torch.int, device=pts.device)
+        w = torch.empty((n, 8), dtype=torch.float32, device=pts.device)
+        t = m.tables[lvl]
+        L.check(L.lib().lb_point_corner_query(L.ptr(pts), pts.stride(0), n, 2 ** lvl, L.ptr(t[0]), t[1], L.ptr(idx),
+                                              L.ptr(w), L.stream()))
+        return idx, w
+
+    def _cell_query(self, pts, m, lvl):
+        n = pts.shape[0]
+        idx = torch.empty(n, dtype=torch.int, device=pts.device)
+        t = m.tables[lvl]
+        L.check(L.lib().lb_point_cell_query(L.ptr(pts), pts.stride(0), n, 2 ** lvl, L.ptr(t[0]), t[1], L.ptr(idx), L.stream()))
+        counts = torch.empty(m.n[lvl], dtype=torch.int, device=pts.device)
+        L.check(L.lib().lb_count(L.ptr(idx), n, L.ptr(counts), m.n[lvl], L.stream()))
+        return idx, counts
+
+    def _devox(self, x, idx, w, out_dtype=None):
+        n, c = idx.shape[0], x.shape[1]
+        out = torch.empty((n, c), dtype=out_dtype or self.dtype, device=x.device)
+        L.check(L.lib().lb_devoxelize_fwd_ex(L.ptr(x), L.DT_OF[x.dtype], x.stride(0), L.ptr(idx), L.ptr(w), n, x.shape[0], c,
+                                             L.ptr(out), L.DT_OF[out.dtype], out.stride(0), L.stream()))
+        return out
+
+    def _vox(self, f, idx, counts, m_rows):
+        acc = torch.empty((m_rows, f.shape[1]), dtype=torch.float32, device=f.device)
+        L.check(L.lib().lb_voxelize_fwd_ex(L.ptr(f), L.DT_OF[f.dtype], f.stride(0), L.ptr(idx), L.ptr(counts), f.shape[0],
+                                           m_rows, f.shape[1], L.ptr(acc), L.stream()))
+        return acc
+
+    def _initial_voxelize(self, coords, feats):
+        """network/utils.py:13-33: voxels = unique hashes of the floored point coordinates, ascending hash order."""
+        dev = coords.device
+        zc = coords.float()
+        zc = torch.cat([(zc[:, :3] * self.pres) / self.vres, zc[:, 3:]], 1).contiguous()       # new_float_coord
+        cell = torch.floor(zc)
+        h = F.sphash(cell.int())
+        n = h.shape[0]
+        uniq = torch.empty(n, dtype=torch.int64, device=dev)
+        n_u = torch.zeros(1, dtype=torch.int, device=dev)
+        inv = torch.empty(n, dtype=torch.int, device=dev)
+        nbytes = L.lib().lb_unique_ws_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        L.check(L.lib().lb_unique_i64(L.ptr(h), n, 60, L.ptr(uniq), L.ptr(n_u), L.ptr(inv), L.ptr(ws), nbytes, L.stream()))
+        nv = int(n_u.item())
+        counts = torch.empty(nv, dtype=torch.int, device=dev)
+        L.check(L.lib().lb_count(L.ptr(inv), n, L.ptr(counts), nv, L.stream()))
+        vcoords = torch.round(self._vox(cell, inv, counts, nv)).int()
+        vfeats = self._vox(feats.contiguous(), inv, counts, nv)
+        return zc, vcoords, vfeats
+
+    def _spvcnn(self, coords, feats):
+        zc, vcoords, vfeats = self._initial_voxelize(coords.contiguous(), feats)
+        m = Maps(vcoords)
+        cats = self._cat_buffers(m)
+        x0 = self._stem(self._cast(vfeats, self.dtype), m, cats[3])
+        iq0, w0 = self._corner_query(zc, m, 0)
+        z0 = self._devox(x0, iq0, w0)                                            # [Np, 32]
+        ci0, cn0 = self._cell_query(zc, m, 0)
+        x = self._cast(self._vox(z0, ci0, cn0, m.n[0]), self.dtype)
+        for lvl in range(1, 5):
+            skip_out = cats[3 - lvl][:, self.up[3 - lvl].cout:] if lvl < 4 else None
+            x = self._encode(x, m, lvl, out=skip_out)
+        iq4, w4 = self._corner_query(zc, m, 4)
+        z1 = self.mlp[0](z0, None, z0.shape[0], residual=self._devox(x, iq4, w4), relu_first=True)   # [Np, 256]
+        ci4, cn4 = self._cell_query(zc, m, 4)
+        y = self._cast(self._vox(z1, ci4, cn4, m.n[4]), self.dtype)              # dropout: identity in eval
+        y = self._decode(y, m, 1, cats[0])
+        y = self._decode(y, m, 2, cats[1])
+        iq2, w2 = self._corner_query(zc, m, 2)
+        z2 = self.mlp[1](z1, None, z1.shape[0], residual=self._devox(y, iq2, w2), relu_first=True)   # [Np, 128]
+        ci2, cn2 = self._cell_query(zc, m, 2)
+        y = self._cast(self._vox(z2, ci2, cn2, m.n[2]), self.dtype)
+        y = self._decode(y, m, 3, cats[2])
+        y = self._decode(y, m, 4, cats[3])
+        z3 = self.mlp[2](z2, None, z2.shape[0], residual=self._devox(y, iq0, w0), relu_first=True)   # [Np, 96]
+        logits = self.classifier(z3, None, z3.shape[0], out_dtype=torch.float32)
+        return logits[:, : self.n_cls]

@@ -1,0 +1,95 @@
+"""GPU: the fused inference engine against the reference-network goldens and against the module-by-module compat path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-2
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("name,ncls", [("minkunet", 19), ("spvcnn", 16)])
+def test_engine_logits_vs_reference_golden(golden, small_scan, name, ncls):
+    import lidal_b200.compat as ts
+    from lidal_b200.engine import InferenceEngine
+    from lidal_b200.network import MinkUNet, SPVCNN, seeded_state_dict
+    g = golden["nets"]
+    coords, feats, _ = small_scan
+    model = (MinkUNet if name == "minkunet" else SPVCNN)(ncls, ts)
+    model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
+    model = model.cuda().eval()
+    eng = InferenceEngine(model)
+    c, f = torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda()
+    logits = eng(c, f)
+    assert logits.shape == (coords.shape[0], ncls) and logits.dtype == torch.float32
+    err = rel_l2(logits[:512].cpu(), torch.from_numpy(g[f"{name}_logits_head"]))
+    print(f"{name} engine vs fp32 reference: rel-L2 {err:.3e}")
+    assert err < REL_TOL
+    with torch.no_grad():
+        compat_logits = model(ts.SparseTensor(f, c))[0]
+    assert rel_l2(logits.cpu(), compat_logits.cpu()) < REL_TOL
+    # argmax agreement with the fp32 reference on confidently-classified rows
+    ref = torch.from_numpy(g[f"{name}_logits_head"])
+    top2 = ref.topk(2, 1).values
+    confident = (top2[:, 0] - top2[:, 1]) > 0.05 * ref.abs().max()
+    assert (logits[:512].cpu().argmax(1) == ref.argmax(1))[confident].all()
+
+
+def test_engine_fp16_operands(golden, small_scan):
+    import lidal_b200.compat as ts
+    from lidal_b200.engine import InferenceEngine
+    from lidal_b200.network import MinkUNet, seeded_state_dict
+    coords, feats, _ = small_scan
+    model = MinkUNet(19, ts)
+    model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
+    eng = InferenceEngine(model.cuda().eval(), dtype=torch.float16)
+    logits = eng(torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda())
+    err = rel_l2(logits[:512].cpu(), torch.from_numpy(golden["nets"]["minkunet_logits_head"]))
+    print(f"minkunet engine fp16 operands: rel-L2 {err:.3e}")
+    assert err < REL_TOL
+
+
+def test_unique_and_point_queries_vs_oracle(oracle_ts, small_scan):
+    import lidal_b200.compat as ts
+    from lidal_b200 import _lib as L
+    from lidal_b200.engine import InferenceEngine, Maps
+    F, Fo = ts.nn.functional, oracle_ts.nn.functional
+    coords = torch.from_numpy(small_scan[0])
+    h = Fo.sphash(coords)
+    keys = torch.cat([h, h[::3]])                                     # duplicates
+    n = keys.numel()
+    uniq = torch.empty(n, dtype=torch.int64, device="cuda")
+    n_u = torch.zeros(1, dtype=torch.int, device="cuda")
+    inv = torch.empty(n, dtype=torch.int, device="cuda")
+    nbytes = L.lib().lb_unique_ws_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    kd = keys.cuda()
+    L.check(L.lib().lb_unique_i64(L.ptr(kd), n, 60, L.ptr(uniq), L.ptr(n_u), L.ptr(inv), L.ptr(ws), nbytes, L.stream()))
+    want_u, want_inv = torch.unique(keys, return_inverse=True)
+    assert int(n_u.item()) == want_u.numel()
+    assert torch.equal(uniq[: want_u.numel()].cpu(), want_u) and torch.equal(inv.cpu().long(), want_inv)
+    # fused corner query == sphash(offsets) + sphashquery + calc_ti_weights
+    g = torch.Generator().manual_seed(0)
+    pts = torch.cat([coords[:, :3].float() + torch.rand(coords.shape[0], 3, generator=g) * 0.97, coords[:, 3:].float()], 1)
+    for lvl in (0, 2):
+        s = 2 ** lvl
+        vox = torch.unique(torch.cat([coords[:, :3] // s * s, coords[:, 3:]], 1), dim=0).int()
+        m = Maps.__new__(Maps)
+        m.tables = {lvl: F._build_table(F.sphash(vox.cuda()))}
+        m.n = {lvl: vox.shape[0]}
+        eng = InferenceEngine.__new__(InferenceEngine)
+        idx, w = InferenceEngine._corner_query(eng, pts.cuda(), m, lvl)
+        off = oracle_ts.nn.utils.get_kernel_offsets(2, s, 1)
+        cell = torch.cat([torch.floor(pts[:, :3] / s).int() * s, pts[:, 3:].int()], 1)
+        want_idx = Fo.sphashquery(Fo.sphash(cell, off), Fo.sphash(vox))
+        want_w = Fo.calc_ti_weights(pts, want_idx, scale=s)
+        assert torch.equal(idx.cpu().long(), want_idx.t())
+        torch.testing.assert_close(w.cpu(), want_w.t().contiguous(), rtol=1e-5, atol=1e-7)
+        ci, cn = InferenceEngine._cell_query(eng, pts.cuda(), m, lvl)
+        want_ci = Fo.sphashquery(Fo.sphash(cell), Fo.sphash(vox))
+        assert torch.equal(ci.cpu().long(), want_ci)
+        assert torch.equal(cn.cpu(), Fo.spcount(want_ci.int(), vox.shape[0]))

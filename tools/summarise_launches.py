@@ -1,0 +1,26 @@
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel (share of device time)."""
+import collections
+import csv
+import re
+import sys
+
+
+def main(path, top=30):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    tot, n = 0.0, 0
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        v = v / 1e3 if row["Metric Unit"] == "ns" else (v * 1e3 if row["Metric Unit"] == "ms" else v)
+        name = re.sub(r"<.*", "", row["Kernel Name"])[:70]
+        agg[name][0] += 1
+        agg[name][1] += v
+        tot += v
+        n += 1
+    print(f"# {path}: {n} launches, {tot / 1e3:.2f} ms of device time (cold-cache, serialised: compare shares)")
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        print(f"{t:10.1f} us {100 * t / tot:5.1f}%  x{c:5d}  {k}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30)
