@@ -75,6 +75,13 @@ size_t lb_kmap_compact_ws_bytes(int64_t n_out, int k);
 int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t* nbmaps, int32_t* nbsizes, int32_t* total,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* Row permutation that groups output rows with equal neighbour masks (bit k = offset k present) so that the
+ * 128-row tiles of lb_conv_fwd can skip whole offsets: perm int32 [n_out] (ascending mask, stable) and the permuted
+ * table nbr_sorted[k][j] = nbr[k][perm[j]].  Use as  args.nbr = nbr_sorted, args.out_rows = perm. */
+size_t lb_kmap_sort_ws_bytes(int64_t n_out);
+int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm, int32_t* nbr_sorted,
+                         void* ws, size_t ws_bytes, void* stream);
+
 /* Per-offset inverse of a neighbour table (transposed convolution / dgrad roles):
  * nbr int32 [k, nbr_ld] with values in [0, n_in) or -1  ->  nbr_t int32 [k, n_in], nbr_t[k][nbr[k][o]] = o. */
 int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* nbr_t, int64_t n_in,
@@ -107,6 +114,9 @@ int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* 
 
 #define LB_CONV_RELU 1      /* apply ReLU last                                   */
 #define LB_CONV_FORCE_SIMT 2 /* use the CUDA-core kernel even where tcgen05 applies */
+#define LB_CONV_PACK8 8      /* tiny-channel layers (the c_in = 4 stem): `in` rows hold 8 channels (zero padded,
+                                c_in == 8) and `weight` is [c_out][k_vol*8 -> padded to 64] with col = offset*8 + ch;
+                                8 offsets share one 64-wide K block of the tensor-core kernel               */
 #define LB_CONV_RELU_FIRST 4 /* with LB_CONV_RELU: relu(v*scale+shift) + residual (SPVCNN point branch)  */
 
 typedef struct lb_conv_args {

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liblidal_b200.so")
 
 LB_DT_BF16, LB_DT_F16, LB_DT_F32 = 0, 1, 2
-LB_CONV_RELU, LB_CONV_FORCE_SIMT, LB_CONV_RELU_FIRST = 1, 2, 4
+LB_CONV_RELU, LB_CONV_FORCE_SIMT, LB_CONV_RELU_FIRST, LB_CONV_PACK8 = 1, 2, 4, 8
 DT_OF = {torch.bfloat16: LB_DT_BF16, torch.float16: LB_DT_F16, torch.float32: LB_DT_F32}
 
 vp, i64, i32, sz, dbl, flt = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double, C.c_float
@@ -48,6 +48,8 @@ SIGNATURES = {
     "lb_kmap_query": (i32, [vp, sz, vp, i64, vp, vp, i32, vp, vp]),
     "lb_kmap_compact_ws_bytes": (sz, [i64, i32]),
     "lb_kmap_compact": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
+    "lb_kmap_sort_ws_bytes": (sz, [i64]),
+    "lb_kmap_sort_by_mask": (i32, [vp, i64, i64, i32, vp, vp, vp, sz, vp]),
     "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
     "lb_unique_ws_bytes": (sz, [i64]),
     "lb_unique_i64": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),

@@ -9,6 +9,7 @@ namespace lb {
 
 int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype);
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st);
+int conv_tc_pack8_supported(int k_vol, int c_in, int c_out, int act_dtype);
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -166,6 +167,12 @@ extern "C" int lb_conv_fwd(const lb_conv_args* a, void* stream) {
   LB_CHECK_ARG(a->act_dtype == LB_DT_BF16 || a->act_dtype == LB_DT_F16, "act_dtype must be BF16 or F16");
   LB_CHECK_ARG(!a->residual || a->ld_res >= a->c_out, "ld_res < c_out");
   cudaStream_t st = as_stream(stream);
+  if (a->flags & LB_CONV_PACK8) {
+    LB_CHECK_ARG(conv_tc_pack8_supported(a->k_vol, a->c_in, a->c_out, a->act_dtype) && (a->ld_in % 8 == 0) &&
+                     (((uintptr_t)a->in) & 15) == 0 && a->nbr,
+                 "LB_CONV_PACK8 needs c_in == 8, 16-byte rows, c_out % 32 == 0 and a neighbour table");
+    return conv_tc_launch(*a, st);
+  }
   if (!(a->flags & LB_CONV_FORCE_SIMT) && conv_tc_supported(a->k_vol, a->c_in, a->c_out, a->act_dtype) &&
       (a->ld_in % 8 == 0) && (((uintptr_t)a->in) & 15) == 0)
     return conv_tc_launch(*a, st);

@@ -9,6 +9,8 @@
 //                         neighbours); thread 128 also issues the TMA load of the weight tile W[k][:, c0:c0+BK]
 //   warp  8    MMA      : one elected thread issues tcgen05.mma (M=128, N=c_out, K=16) per 16 channels,
 //                         accumulating over all active offsets and channel blocks in TMEM (fp32)
+// Producers never block on their own copies: each thread posts `cp.async.mbarrier.arrive.noinc` on the stage's full
+// barrier, which the hardware fires when that thread's copies have landed, so the whole ring depth is in flight.
 // Pipelines: a STAGES-deep smem ring (full/empty mbarriers) between producers and MMA, and a 2-deep TMEM
 // accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile t overlaps the
 // gathers and MMAs of tile t+1.  Offsets for which no row of the tile has a neighbour are skipped entirely.
@@ -22,9 +24,9 @@ constexpr int TILE_M = 128;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int NUM_PROD_THREADS = 128;
 constexpr int NUM_THREADS = NUM_EPI_THREADS + NUM_PROD_THREADS + 32;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 constexpr int MAX_KVOL = 27;
-constexpr int PROD_LAG = 2;           // cp.async groups kept in flight per producer thread before signalling
+constexpr int MAX_LAG = 10;           // cp.async groups a producer thread keeps in flight before signalling the oldest
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,8 +61,27 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// the mbarrier receives one arrival from this thread once all of its prior cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    case 7: cp_async_wait<7>(); break;
+    case 8: cp_async_wait<8>(); break;
+    case 9: cp_async_wait<9>(); break;
+    default: cp_async_wait<10>(); break;
+  }
+}
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -136,6 +157,8 @@ struct TcParams {
   int is_bf16;
   int stages;
   int tmem_cols;
+  int lag;                 // producer run-ahead in stages (< stages)
+  int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
 };
 
 template <typename T> __device__ __forceinline__ float cvt_in(uint16_t raw);
@@ -211,9 +234,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     const int t = threadIdx.x - NUM_EPI_THREADS;          // 0..127
     const int chunk = t % CHUNKS, row0 = t / CHUNKS;
     if (t == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&w_map) : "memory");
-    uint32_t it = 0;                                      // global k-block counter (ring position)
-    int pending[PROD_LAG];                                // stages whose cp.async group has not been signalled yet
-    int n_pending = 0;
+    uint32_t it = 0;                                      // k-blocks issued so far
+    int stage = 0;                                        // ring position of `it`
+    uint32_t ph = 0;
+    // one k-block: acquire the slot, (thread 0) flags + TMA weight tile, gather 128 rows x BK channels, commit
+    auto issue = [&](int k, int cb, int b_col, int b_row, bool first, bool last) {
+      mbar_wait(&empty_bar[stage], ph ^ 1);               // slot free (first lap passes immediately)
+      uint8_t* a_s = ring + (size_t)stage * stage_bytes;
+      if (t == 0) {
+        s_flags[stage] = (first ? 1u : 0u) | (last ? 2u : 0u);
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+        tma_load_2d(smem_u32(a_s + A_BYTES), &w_map, b_col, b_row, &full_bar[stage]);
+      }
+      const uint32_t a_u32 = smem_u32(a_s);
+#pragma unroll
+      for (int i = 0; i < TILE_M / ROWS_PER_PASS; ++i) {
+        const int r = row0 + i * ROWS_PER_PASS;
+        int nb;
+        const char* src;
+        if (p.pack8) {                                    // chunk <-> offset 8*cb + chunk, 16 bytes = its 8 channels
+          const int kk = cb * 8 + chunk;
+          nb = kk < p.k_vol ? s_idx[kk * TILE_M + r] : -1;
+          src = p.in + (int64_t)(nb >= 0 ? nb : 0) * p.ld_in * 2;
+        } else {
+          nb = s_idx[k * TILE_M + r];
+          src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + cb * BK + chunk * 8) * 2;
+        }
+        const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
+        cp_async16(a_u32 + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
+      }
+      cp_async_arrive_noinc(&full_bar[stage]);            // asynchronous: fires when this thread's copies have landed
+      ++it;
+      if (++stage == p.stages) { stage = 0; ph ^= 1; }
+    };
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int64_t base = tile * TILE_M;
       // all producers finished issuing the previous tile's gathers before s_idx is overwritten
@@ -233,51 +286,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t mask = *s_mask;
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
-      const int last_k = 31 - __clz(mask);
-      const int first_k = __ffs(mask) - 1;
-      for (int k = first_k; k <= last_k; ++k) {
-        if (!((mask >> k) & 1)) continue;
-        for (int cb = 0; cb < kc_blocks; ++cb, ++it) {
-          const int stage = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&empty_bar[stage], ph ^ 1);           // slot free (first lap passes immediately)
-          uint8_t* a_s = ring + (size_t)stage * stage_bytes;
-          if (t == 0) {
-            s_flags[stage] = ((k == first_k && cb == 0) ? 1u : 0u) | ((k == last_k && cb == kc_blocks - 1) ? 2u : 0u);
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
-            tma_load_2d(smem_u32(a_s + A_BYTES), &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
-          }
-          const uint32_t a_u32 = smem_u32(a_s);
-#pragma unroll
-          for (int i = 0; i < TILE_M / ROWS_PER_PASS; ++i) {
-            const int r = row0 + i * ROWS_PER_PASS;
-            const int nb = s_idx[k * TILE_M + r];
-            const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
-            const uint32_t dst = a_u32 + r * ROW_BYTES + sw * 16;
-            const char* src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + cb * BK + chunk * 8) * 2;
-            cp_async16(dst, src, nb >= 0 ? 16u : 0u);
-          }
-          cp_async_commit();
-          if (n_pending == PROD_LAG) {                    // oldest group is complete after this wait
-            cp_async_wait<PROD_LAG>();
-            fence_proxy_async();
-            mbar_arrive(&full_bar[pending[0]]);
-#pragma unroll
-            for (int j = 0; j + 1 < PROD_LAG; ++j) pending[j] = pending[j + 1];
-            pending[PROD_LAG - 1] = stage;
-          } else {
-            pending[n_pending++] = stage;
-          }
+      if (p.pack8) {
+        const int nkb = (p.k_vol * 8 + BK - 1) / BK;
+        for (int kb = 0; kb < nkb; ++kb) issue(0, kb, kb * BK, 0, kb == 0, kb == nkb - 1);
+      } else {
+        const int last_k = 31 - __clz(mask);
+        const int first_k = __ffs(mask) - 1;
+        for (int k = first_k; k <= last_k; ++k) {
+          if (!((mask >> k) & 1)) continue;
+          for (int cb = 0; cb < kc_blocks; ++cb)
+            issue(k, cb, cb * BK, k * p.c_out, k == first_k && cb == 0, k == last_k && cb == kc_blocks - 1);
         }
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = 0; j < n_pending; ++j) mbar_arrive(&full_bar[pending[j]]);
+    cp_async_wait<0>();                                   // nothing of ours may still be in flight at teardown
   } else if (warp == 8) {
     // =============================================================== MMA ISSUER
     const uint32_t idesc = make_idesc(TILE_M, p.c_out, p.is_bf16 ? 1 : 0);
-    uint32_t it = 0;
+    int stage = 0;
+    uint32_t ph = 0;
     int64_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int acc = (int)(tcount & 1);
@@ -286,9 +313,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.c_out);
       while (true) {
-        const int stage = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(&full_bar[stage], ph);
+        fence_proxy_async();                              // gathered rows were written through the generic proxy (cp.async)
         tc_fence_after();
         const uint32_t flags = s_flags[stage];
         if (lane == 0) {
@@ -302,7 +328,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
           if (flags & 2u) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
         __syncwarp();
-        ++it;
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
         if (flags & 2u) break;
       }
     }
@@ -400,6 +426,9 @@ static EncodeTiledFn get_encode() {
 }
 
 static inline int block_k_for(int c_in) { return (c_in % 64 == 0) ? 64 : ((c_in % 32 == 0) ? 32 : 0); }
+int conv_tc_pack8_supported(int k_vol, int c_in, int c_out, int act_dtype) {
+  return (act_dtype == LB_DT_BF16 || act_dtype == LB_DT_F16) && c_in == 8 && k_vol >= 1 && k_vol <= MAX_KVOL && c_out % 32 == 0 && c_out >= 32 && c_out <= 256;
+}
 
 int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
   if (act_dtype != LB_DT_BF16 && act_dtype != LB_DT_F16) return 0;
@@ -414,7 +443,8 @@ static size_t tail_bytes() {
 }
 
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
-  const int bk = block_k_for(a.c_in);
+  const bool pack8 = (a.flags & LB_CONV_PACK8) != 0;
+  const int bk = pack8 ? 64 : block_k_for(a.c_in);
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("lb_conv_fwd: cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return LB_ECUDA; }
   if (a.out_dtype != LB_DT_F32 && a.out_dtype != a.act_dtype) {
@@ -428,8 +458,10 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   }
   // weight viewed as a 2-D tensor [k_vol * c_out rows, c_in cols] (c_in contiguous), box = [c_out rows, bk cols]
   CUtensorMap map;
-  cuuint64_t gdim[2] = {(cuuint64_t)a.c_in, (cuuint64_t)a.k_vol * a.c_out};
-  cuuint64_t gstride[1] = {(cuuint64_t)a.c_in * 2};
+  // PACK8: weight is [c_out rows, kpad cols] with col = offset * 8 + channel, kpad = k_vol * 8 rounded up to 64
+  const int kpad = ((a.k_vol * 8 + 63) / 64) * 64;
+  cuuint64_t gdim[2] = {(cuuint64_t)(pack8 ? kpad : a.c_in), (cuuint64_t)(pack8 ? a.c_out : a.k_vol * a.c_out)};
+  cuuint64_t gstride[1] = {(cuuint64_t)(pack8 ? kpad : a.c_in) * 2};
   cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)a.c_out};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(&map, a.act_dtype == LB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
@@ -453,8 +485,10 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const size_t budget = 227 * 1024 - 1024 - tail_bytes();
   int stages = (int)(budget / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < PROD_LAG + 1) { set_error("lb_conv_fwd: shared memory too small for the pipeline"); return LB_ECAP; }
+  if (stages < 3) { set_error("lb_conv_fwd: shared memory too small for the pipeline"); return LB_ECAP; }
   p.stages = stages;
+  p.lag = stages - 1 < MAX_LAG ? stages - 1 : MAX_LAG;
+  p.pack8 = pack8 ? 1 : 0;
   const size_t smem = (size_t)stages * stage_bytes + tail_bytes() + 1024;
   int64_t tiles = (a.n_out + TILE_M - 1) / TILE_M;
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());

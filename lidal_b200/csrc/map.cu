@@ -542,3 +542,45 @@ extern "C" int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+
+// ------------------------------------------------------------------------------------------ mask-sorted kernel maps
+namespace lb {
+__global__ void ks_keys(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, uint64_t* __restrict__ keys,
+                        uint32_t* __restrict__ vals) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t m = 0;
+    for (int j = 0; j < k; ++j) m |= (uint64_t)(__ldg(&nbr[(int64_t)j * ld + o]) >= 0) << j;
+    keys[o] = m;
+    vals[o] = (uint32_t)o;
+  }
+}
+__global__ void ks_permute(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, const int* __restrict__ perm,
+                           int* __restrict__ out) {
+  const int64_t total = n * k;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int j = (int)(t / n);
+    int64_t i = t - (int64_t)j * n;
+    out[t] = __ldg(&nbr[(int64_t)j * ld + __ldg(&perm[i])]);
+  }
+}
+}  // namespace lb
+extern "C" size_t lb_kmap_sort_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return align256((size_t)n * 8) + align256(lb_sort_pairs_ws_bytes(n)) + 256;
+}
+extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm,
+                                    int32_t* nbr_sorted, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n_out >= 0 && k > 0 && k <= 32 && nbr_ld >= n_out && ws, "bad arguments");
+  if (ws_bytes < lb_kmap_sort_ws_bytes(n_out)) { set_error("lb_kmap_sort_by_mask: workspace too small"); return LB_ECAP; }
+  if (n_out == 0) return LB_OK;
+  LB_CHECK_ARG(nbr && perm && nbr_sorted, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  uint64_t* keys = (uint64_t*)ws;
+  void* sort_ws = (char*)ws + align256((size_t)n_out * 8);
+  ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, keys, (uint32_t*)perm); LB_LAUNCHED(1);
+  int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
+  if (rc != LB_OK) return rc;
+  ks_permute<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, perm, nbr_sorted); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

@@ -34,11 +34,12 @@ def _fold_bn(bn, extra_bias=None):
 class _Conv:
     """One fused launch: packed 16-bit weight [K, Cout, Cin] + per-channel scale/shift + flags."""
 
-    def __init__(self, kernel, bn=None, relu=False, dtype=torch.bfloat16, bias=None, pad_out_to=None):
+    def __init__(self, kernel, bn=None, relu=False, dtype=torch.bfloat16, bias=None, pad_out_to=None, pack8=False):
         w = kernel.detach()
         if w.dim() == 2:
             w = w.unsqueeze(0)
         self.k, self.cin, self.cout = w.shape
+        self.pack8 = pack8
         self.cout_real = self.cout
         dev = w.device
         if bn is not None:
@@ -54,10 +55,20 @@ class _Conv:
             if self.scale is not None:
                 self.scale = torch.cat([self.scale, torch.ones(pad, device=dev)])
             self.cout += pad
-        self.w = F.pack_weight(w.float(), dtype)
+        if pack8:
+            # LB_CONV_PACK8: [Cout][kpad] with column = offset * 8 + channel (channels zero-padded to 8)
+            assert self.cin <= 8
+            kpad = (self.k * 8 + 63) // 64 * 64
+            w8 = torch.zeros(kpad // 8, 8, self.cout, device=dev, dtype=torch.float32)
+            w8[: self.k, : self.cin] = w.float()
+            self.w = w8.permute(2, 0, 1).reshape(1, self.cout, kpad).to(dtype).contiguous()
+            self.cin = 8
+        else:
+            self.w = F.pack_weight(w.float(), dtype)
         self.relu = relu
 
     def __call__(self, x, nbr, n_out, out=None, residual=None, out_dtype=None, relu_first=False):
+        nbr, out_rows = nbr if isinstance(nbr, tuple) else (nbr, None)
         out_dtype = out_dtype or x.dtype
         if out is None:
             out = torch.empty((n_out, self.cout), dtype=out_dtype, device=x.device)
@@ -66,18 +77,19 @@ class _Conv:
         a.out, a.n_out, a.ld_out = out.data_ptr(), n_out, out.stride(0)
         a.n_out_dev = None
         a.nbr, a.nbr_ld = (nbr.data_ptr(), nbr.stride(0)) if nbr is not None else (None, 0)
-        a.out_rows = None
+        a.out_rows = out_rows.data_ptr() if out_rows is not None else None
         a.weight, a.k_vol, a.c_in, a.c_out = self.w.data_ptr(), self.k, self.cin, self.cout
         a.scale = self.scale.data_ptr() if self.scale is not None else None
         a.shift = self.shift.data_ptr() if self.shift is not None else None
         a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
         a.act_dtype, a.out_dtype = L.DT_OF[x.dtype], L.DT_OF[out.dtype]
-        a.flags = (L.LB_CONV_RELU if self.relu else 0) | (L.LB_CONV_RELU_FIRST if relu_first else 0)
+        a.flags = ((L.LB_CONV_RELU if self.relu else 0) | (L.LB_CONV_RELU_FIRST if relu_first else 0)
+                   | (L.LB_CONV_PACK8 if self.pack8 else 0))
         trace = F.CONV_TRACE
         ev = trace.begin() if trace is not None else None
         L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
         if trace is not None:
-            tc = L.lib().lb_conv_uses_tensor_cores(self.k, self.cin, self.cout, a.act_dtype) and x.stride(0) % 8 == 0
+            tc = self.pack8 or (L.lib().lb_conv_uses_tensor_cores(self.k, self.cin, self.cout, a.act_dtype) and x.stride(0) % 8 == 0)
             trace.end(ev, nbr, n_out, self.k, self.cin, self.cout, tc)
         return out
 
@@ -97,6 +109,7 @@ class _Res:
 
 
 _OFFSETS = {}
+SORT_MAPS = True        # group rows by neighbour mask (tile-level offset skipping); False = natural row order
 
 
 def _offsets(ks, stride, dev):
@@ -106,8 +119,20 @@ def _offsets(ks, stride, dev):
     return _OFFSETS[key]
 
 
+def _mask_sorted(nbr):
+    """(nbr_sorted, perm): rows grouped by neighbour mask so 128-row tiles skip absent offsets (lb_kmap_sort_by_mask)."""
+    k, n = nbr.shape
+    perm = torch.empty(n, dtype=torch.int, device=nbr.device)
+    out = torch.empty_like(nbr)
+    nbytes = L.lib().lb_kmap_sort_ws_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=nbr.device)
+    L.check(L.lib().lb_kmap_sort_by_mask(L.ptr(nbr), nbr.stride(0), n, k, L.ptr(perm), L.ptr(out), L.ptr(ws), nbytes, L.stream()))
+    return out, perm
+
+
 class Maps:
-    """Coordinates and neighbour tables of the 5 resolution levels (9 kernel maps) for one batch."""
+    """Coordinates and neighbour tables of the 5 resolution levels (9 kernel maps) for one batch.  Every table is kept
+    as (mask-sorted table, row permutation): the conv kernel walks rows in permuted order and scatters through out_rows."""
 
     def __init__(self, coords):
         self.coords, self.n, self.nbr3, self.nbr_dn, self.nbr_up, self.tables = [coords], [coords.shape[0]], [], [], [], []
@@ -121,7 +146,7 @@ class Maps:
             nbr3 = torch.empty((27, c.shape[0]), dtype=torch.int, device=dev)
             L.check(L.lib().lb_kmap_query(L.ptr(table[0]), table[1], L.ptr(c), c.shape[0], None, L.ptr(off3), 27,
                                           L.ptr(nbr3), L.stream()))
-            self.nbr3.append(nbr3)
+            self.nbr3.append(_mask_sorted(nbr3) if SORT_MAPS else nbr3)
             if lvl == 4:
                 break
             cn = F.spdownsample(c, 2, 2, s)
@@ -133,8 +158,8 @@ class Maps:
             L.check(L.lib().lb_kmap_transpose(L.ptr(dn), dn.stride(0), cn.shape[0], 8, L.ptr(up), c.shape[0], L.stream()))
             self.coords.append(cn)
             self.n.append(cn.shape[0])
-            self.nbr_dn.append(dn)
-            self.nbr_up.append(up)
+            self.nbr_dn.append(_mask_sorted(dn) if SORT_MAPS else dn)
+            self.nbr_up.append(_mask_sorted(up) if SORT_MAPS else up)
 
 
 class InferenceEngine:
@@ -143,7 +168,7 @@ class InferenceEngine:
         self.dtype = dtype
         self.is_spvcnn = hasattr(model, "point_transforms")
         st = model.stem
-        self.stem0 = _Conv(st[0].kernel, st[1], relu=True, dtype=dtype)
+        self.stem0 = _Conv(st[0].kernel, st[1], relu=True, dtype=dtype, pack8=True)
         self.stem1 = _Conv(st[3].kernel, st[4], relu=True, dtype=dtype)
         self.down, self.enc = [], []
         for i in range(1, 5):
@@ -170,6 +195,14 @@ class InferenceEngine:
         out = torch.empty(x.shape, dtype=dtype, device=x.device)
         L.check(L.lib().lb_cast(L.ptr(x), L.DT_OF[x.dtype], x.stride(0), L.ptr(out), L.DT_OF[dtype], out.stride(0),
                                 x.shape[0], x.shape[1], L.stream()))
+        return out
+
+    def _pad8(self, feats):
+        """fp32 [N, <=8] -> 16-bit [N, 8] zero padded (16-byte rows for the PACK8 stem conv)."""
+        feats = feats.contiguous()
+        out = torch.zeros((feats.shape[0], 8), dtype=self.dtype, device=feats.device)
+        L.check(L.lib().lb_cast(L.ptr(feats), L.DT_OF[feats.dtype], feats.stride(0), L.ptr(out), L.DT_OF[self.dtype], 8,
+                                feats.shape[0], feats.shape[1], L.stream()))
         return out
 
     def _stem(self, feats16, m, cat4):
@@ -203,7 +236,7 @@ class InferenceEngine:
     def _minkunet(self, coords, feats):
         m = Maps(coords.contiguous())
         cats = self._cat_buffers(m)
-        x = self._stem(self._cast(feats.contiguous(), self.dtype), m, cats[3])
+        x = self._stem(self._pad8(feats), m, cats[3])
         for lvl in range(1, 5):
             skip_out = cats[3 - lvl][:, self.up[3 - lvl].cout:] if lvl < 4 else None
             x = self._encode(x, m, lvl, out=skip_out)
@@ -273,7 +306,7 @@ class InferenceEngine:
         zc, vcoords, vfeats = self._initial_voxelize(coords.contiguous(), feats)
         m = Maps(vcoords)
         cats = self._cat_buffers(m)
-        x0 = self._stem(self._cast(vfeats, self.dtype), m, cats[3])
+        x0 = self._stem(self._pad8(vfeats), m, cats[3])
         iq0, w0 = self._corner_query(zc, m, 0)
         z0 = self._devox(x0, iq0, w0)                                            # [Np, 32]
         ci0, cn0 = self._cell_query(zc, m, 0)

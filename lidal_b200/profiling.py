@@ -78,6 +78,13 @@ def conv_roofline(run, resident, steps=3):
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK["bf16_tflops_sustained"]))
     achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     best = max(tc, key=lambda r: r["flops"] / max(r["ms"], 1e-6)) if tc else None
+    if os.environ.get("LIDAL_LAYER_TABLE"):
+        import sys
+        per = len(rows) // steps
+        print(f"{'k':>3} {'cin':>4} {'cout':>4} {'n_out':>8} {'pairs':>9} {'dens':>5} {'ms':>7} {'alg TF/s':>8} {'dense TF/s':>10} tc", file=sys.stderr)
+        for r in rows[:per]:
+            print(f"{r['k']:3d} {r['cin']:4d} {r['cout']:4d} {r['n_out']:8d} {r['pairs']:9d} {r['pairs'] / max(r['n_out'] * r['k'], 1):5.2f} "
+                  f"{r['ms']:7.3f} {r['flops'] / r['ms'] / 1e9:8.1f} {r['dense_flops'] / r['ms'] / 1e9:10.1f} {int(r['tc'])}", file=sys.stderr)
     return {
         "bound": "tensor", "kernel": "lb::conv_tc_kernel (tcgen05 implicit-GEMM sparse conv)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,

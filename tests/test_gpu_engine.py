@@ -93,3 +93,37 @@ def test_unique_and_point_queries_vs_oracle(oracle_ts, small_scan):
         want_ci = Fo.sphashquery(Fo.sphash(cell), Fo.sphash(vox))
         assert torch.equal(ci.cpu().long(), want_ci)
         assert torch.equal(cn.cpu(), Fo.spcount(want_ci.int(), vox.shape[0]))
+
+
+def test_mask_sorted_map_and_pack8(small_scan):
+    """lb_kmap_sort_by_mask: perm is a permutation ordered by neighbour mask; conv through (sorted table, out_rows)
+    equals conv through the natural table; the PACK8 stem path equals the CUDA-core kernel."""
+    import lidal_b200.compat as ts
+    from lidal_b200 import engine
+    F = ts.nn.functional
+    coords = torch.from_numpy(small_scan[0]).cuda()
+    n = coords.shape[0]
+    nbr = F.build_kernel_map(coords, (1, 1, 1), (3, 3, 3), (1, 1, 1), (1, 1, 1)).nbr
+    nbr_s, perm = engine._mask_sorted(nbr)
+    assert torch.equal(torch.sort(perm.long()).values.cpu(), torch.arange(n))
+    assert torch.equal(nbr_s, nbr[:, perm.long()])
+    mask = ((nbr >= 0).long() << torch.arange(27, device="cuda").unsqueeze(1)).sum(0)
+    ms = mask[perm.long()]
+    assert bool((ms[1:] >= ms[:-1]).all())
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 64, generator=g).cuda().bfloat16()
+    conv = engine._Conv((torch.randn(27, 64, 96, generator=g) * 0.05).cuda(), None, relu=True)
+    res = torch.randn(n, 96, generator=g).cuda().bfloat16()
+    a = conv(x, nbr, n, residual=res)
+    b = conv(x, (nbr_s, perm), n, residual=res)
+    torch.testing.assert_close(a.float(), b.float(), rtol=1e-2, atol=1e-2)
+    assert float((a.float() - b.float()).abs().mean()) < 1e-3
+    # PACK8 (c_in = 4 stem) vs the SIMT kernel
+    f4 = torch.randn(n, 4, generator=g).cuda()
+    k4 = (torch.randn(27, 4, 32, generator=g) * 0.2).cuda()
+    stem = engine._Conv(k4, None, relu=False, pack8=True)
+    eng = engine.InferenceEngine.__new__(engine.InferenceEngine)
+    eng.dtype = torch.bfloat16
+    got = stem(eng._pad8(f4), (nbr_s, perm), n, out_dtype=torch.float32)
+    want = F.conv_forward(f4.bfloat16(), F.pack_weight(k4, torch.bfloat16), nbr, n, force_simt=True)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)

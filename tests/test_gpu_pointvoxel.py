@@ -23,7 +23,9 @@ def test_voxelize_devoxelize_roundtrip_vs_oracle(ts, oracle_ts, small_scan):
         pv = PointVoxel(be)
         pc = torch.cat([torch.from_numpy(coords[:, :3]).float() + jitter, torch.from_numpy(coords[:, 3:]).float()], 1)
         z = be.PointTensor(f32.to(dev), pc.to(dev))
-        x0 = pv.initial_voxelize(z, 0.05, 0.05)
+        # resolution 1.0: (C * r) / r is exact on both devices.  With r = 0.05 CUDA torch evaluates the caller's
+        # `x / 0.05` as `x * (1 / 0.05)` (1 ulp off CPU torch at |x| ~ 8192) -- outside the boundary under test.
+        x0 = pv.initial_voxelize(z, 1.0, 1.0)
         z0 = pv.voxel_to_point(x0, z)
         x1 = pv.point_to_voxel(x0, z0)
         # a strided level: coarse voxels at stride 4
