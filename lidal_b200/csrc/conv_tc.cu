@@ -200,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
   uint32_t* s_flags = (uint32_t*)(tempty_bar + 2);                 // [MAX_STAGES] bit0 = first k-block, bit1 = last
   uint32_t* s_tmem = s_flags + MAX_STAGES;                         // [1]
-  uint32_t* s_mask = s_tmem + 1;                                   // [1] active-offset mask of the producers' tile
+  uint32_t* s_mask = s_tmem + 1;                                   // [2] active-offset mask of the producers' tile (by parity)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out;
@@ -267,25 +267,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       ++it;
       if (++stage == p.stages) { stage = 0; ph ^= 1; }
     };
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int64_t base = tile * TILE_M;
-      // all producers finished issuing the previous tile's gathers before s_idx is overwritten
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
-      if (t == 0) *s_mask = 0;
+    // Neighbour indices of the NEXT tile are fetched into registers while the current tile's stages are being issued
+    // (27 independent loads in flight), so the tile prologue never waits on global memory.
+    int nb_reg[MAX_KVOL];
+    auto fetch_indices = [&](int64_t tile) {
+      const int64_t o = tile * TILE_M + t;
+#pragma unroll
+      for (int k = 0; k < MAX_KVOL; ++k) {
+        int nb = -1;
+        if (k < p.k_vol && o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
+        nb_reg[k] = nb;
+      }
+    };
+    if ((int64_t)blockIdx.x < num_tiles) fetch_indices(blockIdx.x);
+    if (t < 2) s_mask[t] = 0;
+    uint32_t par = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, par ^= 1) {
+      // (A) every producer has finished reading s_idx / s_mask[par^1] of the previous tile
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t my_mask = 0;
-      for (int k = 0; k < p.k_vol; ++k) {
-        const int64_t o = base + t;
-        int nb = -1;
-        if (o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
-        if (nb >= p.n_in) nb = -1;
-        s_idx[k * TILE_M + t] = nb;
-        if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
+#pragma unroll
+      for (int k = 0; k < MAX_KVOL; ++k) {
+        if (k < p.k_vol) {
+          int nb = nb_reg[k];
+          if (nb >= p.n_in) nb = -1;
+          s_idx[k * TILE_M + t] = nb;
+          if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
+        }
       }
-      if (lane == 0 && my_mask) atomicOr(s_mask, my_mask);
+      if (lane == 0 && my_mask) atomicOr(&s_mask[par], my_mask);
+      if (t == 0) s_mask[par ^ 1] = 0;
+      // (B) indices and mask of this tile are complete
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
-      uint32_t mask = *s_mask;
+      uint32_t mask = s_mask[par];
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
+      if (tile + gridDim.x < num_tiles) fetch_indices(tile + gridDim.x);
       if (p.pack8) {
         const int nkb = (p.k_vol * 8 + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb) issue(0, kb, kb * BK, 0, kb == 0, kb == nkb - 1);
