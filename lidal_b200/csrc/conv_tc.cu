@@ -157,7 +157,7 @@ struct TcParams {
   int is_bf16;
   int stages;
   int tmem_cols;
-  int lag;                 // producer run-ahead in stages (< stages)
+  int nb;                  // (offset, channel-block) blocks carried by one pipeline stage (1..4)
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
 };
 
@@ -188,7 +188,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.c_out * ROW_BYTES;
-  const int stage_bytes = A_BYTES + ((b_bytes + 1023) & ~1023);
+  const int b_pad = (b_bytes + 1023) & ~1023;
+  const int stage_bytes = p.nb * (A_BYTES + b_pad);       // [nb A sub-tiles][nb B sub-tiles]
   uint8_t* ring = smem;
   uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
   int* s_idx = (int*)tail;                                         // [MAX_KVOL][TILE_M]
@@ -234,19 +235,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     const int t = threadIdx.x - NUM_EPI_THREADS;          // 0..127
     const int chunk = t % CHUNKS, row0 = t / CHUNKS;
     if (t == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&w_map) : "memory");
-    uint32_t it = 0;                                      // k-blocks issued so far
-    int stage = 0;                                        // ring position of `it`
+    int stage = 0;                                        // ring position of the open stage
     uint32_t ph = 0;
-    // one k-block: acquire the slot, (thread 0) flags + TMA weight tile, gather 128 rows x BK channels, commit
-    auto issue = [&](int k, int cb, int b_col, int b_row, bool first, bool last) {
-      mbar_wait(&empty_bar[stage], ph ^ 1);               // slot free (first lap passes immediately)
-      uint8_t* a_s = ring + (size_t)stage * stage_bytes;
-      if (t == 0) {
-        s_flags[stage] = (first ? 1u : 0u) | (last ? 2u : 0u);
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
-        tma_load_2d(smem_u32(a_s + A_BYTES), &w_map, b_col, b_row, &full_bar[stage]);
+    // One block = 128 gathered rows x BK channels of one offset (+ its weight tile).  A stage carries up to p.nb
+    // blocks; the slot is acquired at its first block and published (hardware arrive) after its last.
+    int blk = 0, blk_goal = 0;                            // blocks issued / wanted in the open stage
+    auto issue = [&](int k, int cb, int b_col, int b_row, bool first, int remaining) {
+      uint8_t* st_base = ring + (size_t)stage * stage_bytes;
+      if (blk == 0) {
+        blk_goal = remaining < p.nb ? remaining : p.nb;
+        mbar_wait(&empty_bar[stage], ph ^ 1);             // slot free (first lap passes immediately)
+        if (t == 0) {
+          s_flags[stage] = (first ? 1u : 0u) | (remaining <= p.nb ? 2u : 0u) | ((uint32_t)blk_goal << 8);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(b_bytes * blk_goal));
+        }
       }
-      const uint32_t a_u32 = smem_u32(a_s);
+      if (t == 0) tma_load_2d(smem_u32(st_base + p.nb * A_BYTES + blk * b_pad), &w_map, b_col, b_row, &full_bar[stage]);
+      const uint32_t a_u32 = smem_u32(st_base + blk * A_BYTES);
 #pragma unroll
       for (int i = 0; i < TILE_M / ROWS_PER_PASS; ++i) {
         const int r = row0 + i * ROWS_PER_PASS;
@@ -263,9 +268,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
         const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
         cp_async16(a_u32 + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
       }
-      cp_async_arrive_noinc(&full_bar[stage]);            // asynchronous: fires when this thread's copies have landed
-      ++it;
-      if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      if (++blk == blk_goal) {
+        cp_async_arrive_noinc(&full_bar[stage]);          // asynchronous: fires when this thread's copies have landed
+        blk = 0;
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
     };
     // Neighbour indices of the NEXT tile are fetched into registers while the current tile's stages are being issued
     // (27 independent loads in flight), so the tile prologue never waits on global memory.
@@ -304,14 +311,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       if (tile + gridDim.x < num_tiles) fetch_indices(tile + gridDim.x);
       if (p.pack8) {
         const int nkb = (p.k_vol * 8 + BK - 1) / BK;
-        for (int kb = 0; kb < nkb; ++kb) issue(0, kb, kb * BK, 0, kb == 0, kb == nkb - 1);
+        for (int kb = 0; kb < nkb; ++kb) issue(0, kb, kb * BK, 0, kb == 0, nkb - kb);
       } else {
-        const int last_k = 31 - __clz(mask);
-        const int first_k = __ffs(mask) - 1;
-        for (int k = first_k; k <= last_k; ++k) {
+        int remaining = __popc(mask) * kc_blocks;
+        bool first = true;
+        for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
           if (!((mask >> k) & 1)) continue;
-          for (int cb = 0; cb < kc_blocks; ++cb)
-            issue(k, cb, cb * BK, k * p.c_out, k == first_k && cb == 0, k == last_k && cb == kc_blocks - 1);
+          for (int cb = 0; cb < kc_blocks; ++cb, --remaining, first = false)
+            issue(k, cb, cb * BK, k * p.c_out, first, remaining);
         }
       }
     }
@@ -334,12 +341,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
         tc_fence_after();
         const uint32_t flags = s_flags[stage];
         if (lane == 0) {
-          const uint32_t a_u32 = smem_u32(ring + (size_t)stage * stage_bytes);
-          const uint64_t a_desc = make_smem_desc(a_u32, SBO, LAYOUT);
-          const uint64_t b_desc = make_smem_desc(a_u32 + A_BYTES, SBO, LAYOUT);
+          const uint32_t st_u32 = smem_u32(ring + (size_t)stage * stage_bytes);
+          const int nblk = (int)(flags >> 8);
+          for (int j = 0; j < nblk; ++j) {
+            const uint64_t a_desc = make_smem_desc(st_u32 + j * A_BYTES, SBO, LAYOUT);
+            const uint64_t b_desc = make_smem_desc(st_u32 + p.nb * A_BYTES + j * b_pad, SBO, LAYOUT);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk)            // +32 bytes along K inside the swizzle atom = +2 in the address field
-            umma_f16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc, ((flags & 1u) && kk == 0) ? 0u : 1u);
+            for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
+              umma_f16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                       ((flags & 1u) && j == 0 && kk == 0) ? 0u : 1u);
+          }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
           if (flags & 2u) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
@@ -497,13 +508,17 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   while (cols < 2 * a.c_out) cols <<= 1;
   p.tmem_cols = cols;
   const int row_bytes = bk * 2;
-  const size_t stage_bytes = (size_t)TILE_M * row_bytes + (((size_t)a.c_out * row_bytes + 1023) & ~(size_t)1023);
+  const size_t block_bytes = (size_t)TILE_M * row_bytes + (((size_t)a.c_out * row_bytes + 1023) & ~(size_t)1023);
   const size_t budget = 227 * 1024 - 1024 - tail_bytes();
+  // blocks per stage: measured on B200, carrying several blocks per stage (fewer, coarser stages) is not faster than
+  // a deep ring of single-block stages -- the kernel is bound by L2 traffic, not by the per-stage hand-shake.
+  int nb = 1;
+  const size_t stage_bytes = nb * block_bytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 3) { set_error("lb_conv_fwd: shared memory too small for the pipeline"); return LB_ECAP; }
+  if (stages < 2) { set_error("lb_conv_fwd: shared memory too small for the pipeline"); return LB_ECAP; }
   p.stages = stages;
-  p.lag = stages - 1 < MAX_LAG ? stages - 1 : MAX_LAG;
+  p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
   const size_t smem = (size_t)stages * stage_bytes + tail_bytes() + 1024;
   int64_t tiles = (a.n_out + TILE_M - 1) / TILE_M;

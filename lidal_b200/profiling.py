@@ -128,7 +128,7 @@ def scoring_extras(ms_per_step: float, dev, n_frames: int = 25, n_cls: int = 19)
     _, _, cnt = sc.score_points(fid)
     matched = int(cnt.sum().item())
     npts = sc.frames[fid].n
-    nn_pts = sum(sc.frames[n].n for n in score.neighbour_ids(fid, n_frames))
+    nn_pts = sum(sc.frames[n].n for n in score.neighbour_ids(fid, n_frames))  # noqa
     alg_bytes = npts * n_cls * 4 + npts * 24 + nn_pts * 24 + matched * n_cls * 4 + npts * 12
     # TTA tail on a batch-8 shaped logits tensor
     nv = 8 * 92000

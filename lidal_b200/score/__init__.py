@@ -57,13 +57,18 @@ class Frame:
 class SequenceScorer:
     """Frames of one sequence resident in HBM: registered xyz f64 [Np,3], prob f32 [Np,C], one hash grid each."""
 
-    def __init__(self, device="cuda", nei_num=24, dis_thresh=0.1):
+    def __init__(self, device="cuda", nei_num=24, dis_thresh=0.1, n_total=None):
         self.device = torch.device(device)
         self.nei_num, self.dis_thresh = nei_num, dis_thresh
         self.cell = dis_thresh * GRID_CELL_FACTOR
-        self.frames: list[Frame] = []
+        self.frames: dict[int, Frame] = {}          # frame id -> resident frame (a rank may hold only own + halo frames)
+        self.n_total = n_total                      # frames in the whole sequence (default: all are resident)
 
-    def add_frame(self, xyz, prob, sv_id=None, sv2point=None):
+    @property
+    def n_frames(self):
+        return self.n_total if self.n_total is not None else len(self.frames)
+
+    def add_frame(self, xyz, prob, sv_id=None, sv2point=None, fid=None):
         f = Frame()
         f.xyz = torch.as_tensor(np.ascontiguousarray(xyz, dtype=np.float64) if isinstance(xyz, np.ndarray) else xyz
                                 ).to(self.device, torch.float64).contiguous()
@@ -76,7 +81,7 @@ class SequenceScorer:
         f.sv_id = None
         if sv2point is not None:
             self.set_regions(f, sv_id, sv2point)
-        self.frames.append(f)
+        self.frames[len(self.frames) if fid is None else int(fid)] = f
         return f
 
     def set_regions(self, f: Frame, sv_id, sv2point):
@@ -90,7 +95,7 @@ class SequenceScorer:
     def score_points(self, fid: int, want_nn=False):
         """LiDAL.py:59-81 for frame ``fid``: (interd f64 [Np], intere f32 [Np], matches int32 [Np][, nn int32 [24,Np]])."""
         q = self.frames[fid]
-        nids = neighbour_ids(fid, len(self.frames), self.nei_num)
+        nids = neighbour_ids(fid, self.n_frames, self.nei_num)
         refs = (L.FrameRef * len(nids))()
         for j, n in enumerate(nids):
             fr = self.frames[n]

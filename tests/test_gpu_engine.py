@@ -127,3 +127,21 @@ def test_mask_sorted_map_and_pack8(small_scan):
     got = stem(eng._pad8(f4), (nbr_s, perm), n, out_dtype=torch.float32)
     want = F.conv_forward(f4.bfloat16(), F.pack_weight(k4, torch.bfloat16), nbr, n, force_simt=True)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+def test_devoxelize16_matches_fp32_kernel():
+    """The vectorised 16-bit devoxelize (engine) against the fp32 kernel on the same bf16-rounded inputs."""
+    from lidal_b200 import _lib as L
+    import lidal_b200.compat as ts
+    g = torch.Generator().manual_seed(0)
+    n, m = 20000, 3000
+    for c in (32, 96, 256):
+        feats = torch.randn(m, c, generator=g).cuda().bfloat16()
+        idx = torch.randint(-1, m, (n, 8), generator=g).int().cuda()
+        w = torch.rand(n, 8, generator=g).cuda()
+        w[::3, 1:] = 0.0                                        # degenerate rows: only corner 0 contributes
+        out = torch.empty(n, c, dtype=torch.bfloat16, device="cuda")
+        L.check(L.lib().lb_devoxelize_fwd_ex(L.ptr(feats), L.LB_DT_BF16, c, L.ptr(idx), L.ptr(w), n, m, c, L.ptr(out),
+                                             L.LB_DT_BF16, c, L.stream()))
+        want = ts.nn.functional.spdevoxelize(feats.float(), idx, w)
+        assert torch.equal(out, want.bfloat16())
