@@ -193,11 +193,13 @@ int lb_tta_softmax_mean_argmax(const float* logits, int64_t n_vox, int n_cls, co
  * is unchanged: exact nearest neighbour in float64, accepted iff sqrt(d2) <= dis_thresh. */
 size_t lb_frame_grid_bytes(int64_t n_pts);
 /* xyz f64 [n,3] registered coordinates (dataset/prepare_kdtree_sk.py:77-80); `cell` must exceed dis_thresh. */
-int lb_frame_grid_build(const double* xyz, int64_t n, double cell, void* grid, size_t grid_bytes, void* stream);
+size_t lb_frame_grid_ws_bytes(int64_t n_pts);
+int lb_frame_grid_build(const double* xyz, int64_t n, double cell, void* grid, size_t grid_bytes, void* ws,
+                        size_t ws_bytes, void* stream);
 
 typedef struct lb_frame_ref { /* one neighbouring frame, all device pointers */
-  const void* grid;    /* built by lb_frame_grid_build over `xyz`  */
-  const double* xyz;   /* [n,3]                                     */
+  const void* grid;    /* built by lb_frame_grid_build over `xyz` (holds a cell-sorted copy of the coordinates) */
+  const double* xyz;   /* [n,3] original order (kept for callers; the kernel reads the grid's copy)              */
   const float* prob;   /* [n,n_cls] mean softmax (prob_inference)   */
   int64_t n;
 } lb_frame_ref;
@@ -206,11 +208,13 @@ typedef struct lb_frame_ref { /* one neighbouring frame, all device pointers */
  * for each neighbour frame in the given order (nei_ids order): exact 1-NN, match iff dist <= dis_thresh,
  * sum_prob += P_n[nn]; interd += sum_c kl_div(P_q+1e-5, P_n[nn]+1e-5); count += 1; then
  * intere = entropy(sum_prob / count) and interd /= (count-1) where > 0.
- * nbrs: [host] array of n_nbr (<= 32) frames.  Outputs: interd f64 [nq], intere f32 [nq]; optional
- * count int32 [nq] (= matches) and nn_out int32 [n_nbr, nq] (matched row or -1) for parity tests. */
-int lb_interframe_score(const double* q_xyz, const float* q_prob, int64_t nq, int n_cls, const lb_frame_ref* nbrs,
+ * q_grid: the QUERY frame's own grid (its points are walked in cell-sorted order); q_prob in original row order.
+ * nbrs: [host] array of n_nbr (<= 32) frames.  Outputs: interd f64 [nq], intere f32 [nq]; optional count int32 [nq]
+ * (= matches).  nn int32 [nq, n_nbr] is REQUIRED scratch/output: phase 1 (one thread per point) stores the matched
+ * neighbour row (or -1) per neighbour frame, phase 2 (one warp per point, lane = class) consumes it. */
+int lb_interframe_score(const void* q_grid, const float* q_prob, int64_t nq, int n_cls, const lb_frame_ref* nbrs,
                         int n_nbr, double dis_thresh, double cell, double* interd, float* intere, int32_t* count,
-                        int32_t* nn_out, void* stream);
+                        int32_t* nn, void* stream);
 
 /* LiDAL.py:87-98: per-region means over the ragged `sv2point` lists given in CSR form:
  * region_ptr int32 [r+1], region_pts int32 [region_ptr[r]].  Outs: d,e f32 [r]; optional pnums i64 [r],

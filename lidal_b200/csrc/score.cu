@@ -13,31 +13,42 @@
 
 namespace lb {
 
+// Per-frame uniform grid, cell-sorted:
+//   header | slots[cap] {key, start, count} (open addressing on the packed cell key) | xyz_sorted f64 [n,3] | orig i32 [n]
+// Points are radix-sorted by cell key, so the candidates of a cell are one contiguous run and consecutive points are
+// spatial neighbours (probes of consecutive query points hit the same cache lines).
 struct GridHeader {
   double cell;
   int64_t n;
   uint64_t cap;
   uint64_t pad;
 };
+struct GridSlot {
+  unsigned long long key;
+  int start;
+  int count;
+};
 struct GridView {
   double cell;
   uint64_t mask;
-  const unsigned long long* keys;
-  const int* head;
-  const int* next;
+  int64_t n;
+  const GridSlot* slots;
+  const double* xyz;     // cell-sorted coordinates
+  const int* orig;       // cell-sorted position -> original row
 };
 __host__ __device__ inline size_t grid_bytes_for(int64_t n) {
   uint64_t cap = table_capacity(n);
-  return sizeof(GridHeader) + cap * 8 + cap * 4 + (size_t)(n > 0 ? n : 1) * 4 + 64;
+  return sizeof(GridHeader) + cap * sizeof(GridSlot) + (size_t)(n > 0 ? n : 1) * 28 + 64;
 }
-__device__ __forceinline__ GridView grid_view(const void* g) {
+__host__ __device__ __forceinline__ GridView grid_view(const void* g) {
   const GridHeader* h = (const GridHeader*)g;
   GridView v;
   v.cell = h->cell;
   v.mask = h->cap - 1;
-  v.keys = (const unsigned long long*)((const char*)g + sizeof(GridHeader));
-  v.head = (const int*)((const char*)v.keys + h->cap * 8);
-  v.next = v.head + h->cap;
+  v.n = h->n;
+  v.slots = (const GridSlot*)((const char*)g + sizeof(GridHeader));
+  v.xyz = (const double*)(v.slots + h->cap);
+  v.orig = (const int*)(v.xyz + 3 * (h->n > 0 ? h->n : 1));
   return v;
 }
 constexpr long long CELL_BIAS = 1 << 20;
@@ -48,31 +59,63 @@ __device__ __forceinline__ long long cell_of(double x, double cell) {
 __device__ __forceinline__ uint64_t cell_key(long long ix, long long iy, long long iz) {
   return ((uint64_t)(ix + CELL_BIAS) << 42) | ((uint64_t)(iy + CELL_BIAS) << 21) | (uint64_t)(iz + CELL_BIAS);
 }
+// slot index of a packed cell key: 32-bit murmur finaliser over the folded key (cheaper than the 64-bit mix)
+__device__ __forceinline__ uint64_t cell_slot(uint64_t key) {
+  uint32_t h = (uint32_t)key ^ (uint32_t)(key >> 21) ^ (uint32_t)(key >> 42) * 0x9E3779B1u;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return (uint64_t)h;
+}
+// slot lookup: (start, count) of a cell or count = 0
+__device__ __forceinline__ int2 grid_find(const GridView& g, uint64_t key) {
+  uint64_t slot = cell_slot(key) & g.mask;
+  while (true) {
+    const uint4 raw = __ldg((const uint4*)&g.slots[slot]);          // one 16-byte load per probe
+    const unsigned long long k = ((unsigned long long)raw.y << 32) | raw.x;
+    if (k == key) return make_int2((int)raw.z, (int)raw.w);
+    if (k == LB_EMPTY_KEY) return make_int2(0, 0);
+    slot = (slot + 1) & g.mask;
+  }
+}
 
 __global__ void grid_init_kernel(void* grid, double cell, int64_t n, uint64_t cap) {
   GridHeader* h = (GridHeader*)grid;
   if (blockIdx.x == 0 && threadIdx.x == 0) { h->cell = cell; h->n = n; h->cap = cap; h->pad = 0; }
-  unsigned long long* keys = (unsigned long long*)((char*)grid + sizeof(GridHeader));
-  int* head = (int*)((char*)keys + cap * 8);
+  GridSlot* slots = (GridSlot*)((char*)grid + sizeof(GridHeader));
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-    keys[i] = LB_EMPTY_KEY;
-    head[i] = -1;
+    slots[i].key = LB_EMPTY_KEY;
+    slots[i].start = 0;
+    slots[i].count = 0;
   }
 }
-__global__ void grid_insert_kernel(const double* __restrict__ xyz, int64_t n, double cell, void* grid, uint64_t cap) {
-  unsigned long long* keys = (unsigned long long*)((char*)grid + sizeof(GridHeader));
-  int* head = (int*)((char*)keys + cap * 8);
-  int* next = head + cap;
+__global__ void grid_keys_kernel(const double* __restrict__ xyz, int64_t n, double cell, uint64_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = cell_key(cell_of(xyz[3 * i], cell), cell_of(xyz[3 * i + 1], cell), cell_of(xyz[3 * i + 2], cell));
+    vals[i] = (uint32_t)i;
+  }
+}
+// after the sort: copy coordinates in sorted order, register every run [start, end) of equal keys in the slot table
+__global__ void grid_fill_kernel(const double* __restrict__ xyz, const uint64_t* __restrict__ keys,
+                                 const uint32_t* __restrict__ vals, int64_t n, void* grid, uint64_t cap) {
+  GridSlot* slots = (GridSlot*)((char*)grid + sizeof(GridHeader));
+  double* sx = (double*)(slots + cap);
+  int* orig = (int*)(sx + 3 * n);
   const uint64_t mask = cap - 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint64_t key = cell_key(cell_of(xyz[3 * i], cell), cell_of(xyz[3 * i + 1], cell), cell_of(xyz[3 * i + 2], cell));
-    uint64_t slot = mix64(key) & mask;
-    while (true) {
-      unsigned long long prev = atomicCAS(&keys[slot], LB_EMPTY_KEY, (unsigned long long)key);
-      if (prev == LB_EMPTY_KEY || prev == key) break;
-      slot = (slot + 1) & mask;
+    const uint32_t o = vals[i];
+    sx[3 * i] = xyz[3 * (int64_t)o];
+    sx[3 * i + 1] = xyz[3 * (int64_t)o + 1];
+    sx[3 * i + 2] = xyz[3 * (int64_t)o + 2];
+    orig[i] = (int)o;
+    const uint64_t key = keys[i];
+    if (i == 0 || keys[i - 1] != key) {                  // run start: claim the slot (keys are unique per run)
+      int64_t e = i + 1;
+      while (e < n && keys[e] == key) ++e;               // runs are a handful of points
+      uint64_t slot = cell_slot(key) & mask;
+      while (atomicCAS(&slots[slot].key, LB_EMPTY_KEY, (unsigned long long)key) != LB_EMPTY_KEY) slot = (slot + 1) & mask;
+      slots[slot].start = (int)i;
+      slots[slot].count = (int)(e - i);
     }
-    next[i] = atomicExch(&head[slot], (int)i);
   }
 }
 
@@ -109,55 +152,68 @@ struct ScoreParams {
   int n_nbr;
 };
 
+// Phase 1 -- nearest-neighbour search, one THREAD per cell-sorted query point, all neighbour frames in turn.
+// Consecutive threads are spatial neighbours, so their 27-cell probes and candidate reads coalesce in L1/L2.
+// nn[p * n_nbr + f] = original row of the exact float64 nearest neighbour in frame f if sqrt(d2) <= thresh, else -1.
+__global__ void __launch_bounds__(128)
+nn_search_kernel(const void* __restrict__ q_grid, int64_t nq, const __grid_constant__ ScoreParams P, double thresh,
+                 int* __restrict__ nn) {
+  const GridView qg = grid_view(q_grid);
+  const double t2 = thresh * thresh * (1.0 + 1e-6) + 1e-12;   // inflated: pruning must never drop a true match
+  for (int64_t sp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; sp < nq; sp += (int64_t)gridDim.x * blockDim.x) {
+    const double qx = __ldg(&qg.xyz[3 * sp]), qy = __ldg(&qg.xyz[3 * sp + 1]), qz = __ldg(&qg.xyz[3 * sp + 2]);
+    const int64_t p = __ldg(&qg.orig[sp]);
+    for (int f = 0; f < P.n_nbr; ++f) {
+      const GridView g = grid_view(P.nbr[f].grid);
+      const long long cx = cell_of(qx, g.cell), cy = cell_of(qy, g.cell), cz = cell_of(qz, g.cell);
+      // distance from the query to the lower / upper face of its own cell per axis: a neighbouring cell can hold a match
+      // only if its box is within the (slightly inflated) match radius -- exact pruning, typically ~6 of 27 cells remain
+      const double lx = fmax(qx - (double)cx * g.cell, 0.0), hx = fmax((double)(cx + 1) * g.cell - qx, 0.0);
+      const double ly = fmax(qy - (double)cy * g.cell, 0.0), hy = fmax((double)(cy + 1) * g.cell - qy, 0.0);
+      const double lz = fmax(qz - (double)cz * g.cell, 0.0), hz = fmax((double)(cz + 1) * g.cell - qz, 0.0);
+      double best = INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll 1
+      for (int c = 0; c < 27; ++c) {
+        const int ox = c / 9 - 1, oy = (c / 3) % 3 - 1, oz = c % 3 - 1;
+        const double gx = ox == 0 ? 0.0 : (ox < 0 ? lx : hx), gy = oy == 0 ? 0.0 : (oy < 0 ? ly : hy),
+                     gz = oz == 0 ? 0.0 : (oz < 0 ? lz : hz);
+        if (gx * gx + gy * gy + gz * gz > t2) continue;
+        const int2 run = grid_find(g, cell_key(cx + ox, cy + oy, cz + oz));
+        for (int j = run.x; j < run.x + run.y; ++j) {
+          // sklearn euclidean rdist: d = 0; d += t*t per axis, no FMA contraction
+          const double tx = __dsub_rn(qx, __ldg(&g.xyz[3 * (int64_t)j]));
+          const double ty = __dsub_rn(qy, __ldg(&g.xyz[3 * (int64_t)j + 1]));
+          const double tz = __dsub_rn(qz, __ldg(&g.xyz[3 * (int64_t)j + 2]));
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+          const int oj = __ldg(&g.orig[j]);
+          if (d2 < best || (d2 == best && oj < bi)) { best = d2; bi = oj; }
+        }
+      }
+      nn[p * P.n_nbr + f] = (bi != 0x7fffffff && __dsqrt_rn(best) <= thresh) ? bi : -1;
+    }
+  }
+}
+
+// Phase 2 -- one WARP per query point, lane = class: accumulate over the matched neighbours in nei_ids order.
 __global__ void __launch_bounds__(256)
-interframe_kernel(const double* __restrict__ q_xyz, const float* __restrict__ q_prob, int64_t nq, int n_cls,
-                  const __grid_constant__ ScoreParams P, double thresh, double* __restrict__ interd_out,
-                  float* __restrict__ intere_out, int* __restrict__ count_out, int* __restrict__ nn_out) {
+interframe_kernel(const float* __restrict__ q_prob, int64_t nq, int n_cls, const __grid_constant__ ScoreParams P,
+                  const int* __restrict__ nn, double* __restrict__ interd_out, float* __restrict__ intere_out,
+                  int* __restrict__ count_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float eps = 0.00001f;
-  const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
   for (int64_t p = warp; p < nq; p += nwarps) {
-    const double qx = __ldg(&q_xyz[3 * p]), qy = __ldg(&q_xyz[3 * p + 1]), qz = __ldg(&q_xyz[3 * p + 2]);
     const float q = lane < n_cls ? __ldg(&q_prob[p * n_cls + lane]) : 0.f;
+    const int my_nn = lane < P.n_nbr ? __ldg(&nn[p * P.n_nbr + lane]) : -1;
     float sum = q;
     double interd = 0.0;
     int cnt = 1;
     for (int f = 0; f < P.n_nbr; ++f) {
-      const GridView g = grid_view(P.nbr[f].grid);
-      const double* __restrict__ nxyz = P.nbr[f].xyz;
-      double best = INFINITY;
-      int bi = 0x7fffffff;
-      if (lane < 27) {
-        uint64_t key = cell_key(cell_of(qx, g.cell) + dx, cell_of(qy, g.cell) + dy, cell_of(qz, g.cell) + dz);
-        uint64_t slot = mix64(key) & g.mask;
-        int j = -1;
-        while (true) {
-          unsigned long long k = __ldg(&g.keys[slot]);
-          if (k == key) { j = __ldg(&g.head[slot]); break; }
-          if (k == LB_EMPTY_KEY) break;
-          slot = (slot + 1) & g.mask;
-        }
-        for (; j >= 0; j = __ldg(&g.next[j])) {
-          // sklearn euclidean rdist: d = 0; d += t*t per axis, no FMA contraction
-          double tx = __dsub_rn(qx, __ldg(&nxyz[3 * (int64_t)j]));
-          double ty = __dsub_rn(qy, __ldg(&nxyz[3 * (int64_t)j + 1]));
-          double tz = __dsub_rn(qz, __ldg(&nxyz[3 * (int64_t)j + 2]));
-          double d2 = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
-          if (d2 < best || (d2 == best && j < bi)) { best = d2; bi = j; }
-        }
-      }
-#pragma unroll
-      for (int d = 16; d; d >>= 1) {
-        double ob = __shfl_xor_sync(full, best, d);
-        int oi = __shfl_xor_sync(full, bi, d);
-        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      const bool match = (bi != 0x7fffffff) && (__dsqrt_rn(best) <= thresh);
-      if (nn_out && lane == 0) nn_out[(int64_t)f * nq + p] = match ? bi : -1;
-      if (match) {
+      const int bi = __shfl_sync(full, my_nn, f);
+      if (bi >= 0) {
         const float pn = lane < n_cls ? __ldg(&P.nbr[f].prob[(int64_t)bi * n_cls + lane]) : 0.f;
         sum = __fadd_rn(sum, pn);
         float kl = 0.f;
@@ -257,16 +313,9 @@ __global__ void region_pairs_kernel(const float* __restrict__ c, int64_t n, floa
     int cnt = 0;
     const int base = fill ? row_ptr[i] : 0;
     for (int t = 0; t < 27; ++t) {
-      uint64_t key = cell_key(cx + t / 9 - 1, cy + (t / 3) % 3 - 1, cz + t % 3 - 1);
-      uint64_t slot = mix64(key) & g.mask;
-      int j = -1;
-      while (true) {
-        unsigned long long k = __ldg(&g.keys[slot]);
-        if (k == key) { j = __ldg(&g.head[slot]); break; }
-        if (k == LB_EMPTY_KEY) break;
-        slot = (slot + 1) & g.mask;
-      }
-      for (; j >= 0; j = __ldg(&g.next[j])) {
+      const int2 run = grid_find(g, cell_key(cx + t / 9 - 1, cy + (t / 3) % 3 - 1, cz + t % 3 - 1));
+      for (int jj = run.x; jj < run.x + run.y; ++jj) {
+        const int j = __ldg(&g.orig[jj]);
         if (j == i) continue;
         float ex = __fsub_rn(ax, c[3 * (int64_t)j]), ey = __fsub_rn(ay, c[3 * (int64_t)j + 1]),
               ez = __fsub_rn(az, c[3 * (int64_t)j + 2]);
@@ -290,38 +339,54 @@ static inline int grid1d(int64_t n, int block) {
 }
 
 extern "C" size_t lb_frame_grid_bytes(int64_t n) { return grid_bytes_for(n); }
-extern "C" int lb_frame_grid_build(const double* xyz, int64_t n, double cell, void* grid, size_t bytes, void* stream) {
-  LB_CHECK_ARG(n >= 0 && grid && cell > 0, "bad arguments");
-  LB_CHECK_ARG(((uintptr_t)grid & 7) == 0, "grid must be 8-byte aligned");
+extern "C" size_t lb_frame_grid_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return (((size_t)n * 8 + 255) & ~(size_t)255) + (((size_t)n * 4 + 255) & ~(size_t)255) + lb_sort_pairs_ws_bytes(n) + 256;
+}
+extern "C" int lb_frame_grid_build(const double* xyz, int64_t n, double cell, void* grid, size_t bytes, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && grid && cell > 0 && ws, "bad arguments");
+  LB_CHECK_ARG(((uintptr_t)grid & 15) == 0, "grid must be 16-byte aligned");
   if (bytes < grid_bytes_for(n)) { set_error("lb_frame_grid_build: grid buffer too small"); return LB_ECAP; }
+  if (ws_bytes < lb_frame_grid_ws_bytes(n)) { set_error("lb_frame_grid_build: workspace too small"); return LB_ECAP; }
   cudaStream_t st = as_stream(stream);
   uint64_t cap = table_capacity(n);
   grid_init_kernel<<<grid1d((int64_t)cap, 256), 256, 0, st>>>(grid, cell, n, cap); LB_LAUNCHED(1);
   if (n > 0) {
     LB_CHECK_ARG(xyz, "null xyz");
-    grid_insert_kernel<<<grid1d(n, 256), 256, 0, st>>>(xyz, n, cell, grid, cap); LB_LAUNCHED(1);
+    uint64_t* keys = (uint64_t*)ws;
+    uint32_t* vals = (uint32_t*)((char*)ws + (((size_t)n * 8 + 255) & ~(size_t)255));
+    void* sort_ws = (char*)vals + (((size_t)n * 4 + 255) & ~(size_t)255);
+    grid_keys_kernel<<<grid1d(n, 256), 256, 0, st>>>(xyz, n, cell, keys, vals); LB_LAUNCHED(1);
+    int rc = lb_sort_pairs(keys, vals, n, 63, sort_ws, lb_sort_pairs_ws_bytes(n), stream);
+    if (rc != LB_OK) return rc;
+    grid_fill_kernel<<<grid1d(n, 256), 256, 0, st>>>(xyz, keys, vals, n, grid, cap); LB_LAUNCHED(1);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 
-extern "C" int lb_interframe_score(const double* q_xyz, const float* q_prob, int64_t nq, int n_cls,
+extern "C" int lb_interframe_score(const void* q_grid, const float* q_prob, int64_t nq, int n_cls,
                                    const lb_frame_ref* nbrs, int n_nbr, double dis_thresh, double cell,
-                                   double* interd, float* intere, int32_t* count, int32_t* nn_out, void* stream) {
+                                   double* interd, float* intere, int32_t* count, int32_t* nn, void* stream) {
   LB_CHECK_ARG(nq >= 0 && n_cls > 0 && n_cls <= 32, "n_cls must be in [1,32]");
   LB_CHECK_ARG(n_nbr >= 0 && n_nbr <= MAX_NBR, "at most 32 neighbour frames");
   LB_CHECK_ARG(cell >= dis_thresh * 1.001, "grid cell must exceed dis_thresh (27-cell probe exactness)");
   if (nq == 0) return LB_OK;
-  LB_CHECK_ARG(q_xyz && q_prob && interd && intere && (nbrs || n_nbr == 0), "null pointer");
+  LB_CHECK_ARG(q_grid && q_prob && interd && intere && nn && (nbrs || n_nbr == 0), "null pointer");
   ScoreParams P;
   P.n_nbr = n_nbr;
   for (int i = 0; i < n_nbr; ++i) {
-    LB_CHECK_ARG(nbrs[i].grid && nbrs[i].xyz && nbrs[i].prob, "null neighbour frame");
+    LB_CHECK_ARG(nbrs[i].grid && nbrs[i].prob, "null neighbour frame");
     P.nbr[i].grid = nbrs[i].grid; P.nbr[i].xyz = nbrs[i].xyz; P.nbr[i].prob = nbrs[i].prob; P.nbr[i].n = nbrs[i].n;
   }
+  cudaStream_t st = as_stream(stream);
+  if (n_nbr > 0) {
+    int64_t b1 = (nq + 127) / 128, cap1 = (int64_t)sm_count() * 16;
+    nn_search_kernel<<<(int)(b1 > cap1 ? cap1 : b1), 128, 0, st>>>(q_grid, nq, P, dis_thresh, nn); LB_LAUNCHED(1);
+  }
   int64_t blocks = (nq + 7) / 8, cap = (int64_t)sm_count() * 8;
-  interframe_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(
-      q_xyz, q_prob, nq, n_cls, P, dis_thresh, interd, intere, count, nn_out); LB_LAUNCHED(1);
+  interframe_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(q_prob, nq, n_cls, P, nn, interd, intere, count); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -356,7 +421,8 @@ extern "C" int lb_argsort_f32(const float* keys, int64_t n, int32_t* order, void
 }
 
 extern "C" size_t lb_region_pairs_ws_bytes(int64_t n) {
-  return (((size_t)(n > 0 ? n : 1) * 24 + 255) & ~(size_t)255) + grid_bytes_for(n) + 256;
+  return (((size_t)(n > 0 ? n : 1) * 24 + 255) & ~(size_t)255) + ((grid_bytes_for(n) + 255) & ~(size_t)255) +
+         lb_frame_grid_ws_bytes(n) + 256;
 }
 extern "C" int lb_region_pairs(const float* centers, int64_t n, float radius, int32_t* row_counts_or_ptr,
                                int32_t* nbr_idx, void* ws, size_t ws_bytes, void* stream) {
@@ -368,7 +434,8 @@ extern "C" int lb_region_pairs(const float* centers, int64_t n, float radius, in
   double* xyz = (double*)ws;
   void* grid = (char*)ws + (((size_t)n * 24 + 255) & ~(size_t)255);
   f32_to_f64_xyz<<<grid1d(n * 3, 256), 256, 0, st>>>(centers, n * 3, xyz); LB_LAUNCHED(1);
-  int rc = lb_frame_grid_build(xyz, n, (double)radius * 1.01, grid, grid_bytes_for(n), stream);
+  void* gws = (char*)grid + ((grid_bytes_for(n) + 255) & ~(size_t)255);
+  int rc = lb_frame_grid_build(xyz, n, (double)radius * 1.01, grid, grid_bytes_for(n), gws, lb_frame_grid_ws_bytes(n), stream);
   if (rc != LB_OK) return rc;
   region_pairs_kernel<<<grid1d(n, 128), 128, 0, st>>>(centers, n, radius, grid, row_counts_or_ptr, nbr_idx,
                                                       nbr_idx ? 1 : 0); LB_LAUNCHED(1);

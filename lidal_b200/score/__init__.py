@@ -18,7 +18,10 @@ import torch
 
 from .. import _lib as L
 
-GRID_CELL_FACTOR = 1.25        # grid cell = 1.25 x dis_thresh: the 27-cell probe provably covers the match radius
+import os as _os
+GRID_CELL_FACTOR = float(_os.environ.get('LIDAL_CELL_FACTOR', 1.05))         # grid cell just above dis_thresh (measured best on B200: near-sensor LiDAR
+                               # rings are dense, so small cells minimise fp64 candidate evaluations); the 27-cell neighbourhood
+                               # covers the match radius and cells whose box is farther than the radius are pruned exactly
 
 
 def _ws(nbytes, device):
@@ -77,7 +80,10 @@ class SequenceScorer:
         assert f.prob.shape[0] == f.n
         f.grid_bytes = L.lib().lb_frame_grid_bytes(f.n)
         f.grid = _ws(f.grid_bytes, self.device)
-        L.check(L.lib().lb_frame_grid_build(L.ptr(f.xyz), f.n, self.cell, L.ptr(f.grid), f.grid_bytes, L.stream()))
+        ws_bytes = L.lib().lb_frame_grid_ws_bytes(f.n)
+        ws = _ws(ws_bytes, self.device)
+        L.check(L.lib().lb_frame_grid_build(L.ptr(f.xyz), f.n, self.cell, L.ptr(f.grid), f.grid_bytes, L.ptr(ws), ws_bytes,
+                                            L.stream()))
         f.sv_id = None
         if sv2point is not None:
             self.set_regions(f, sv_id, sv2point)
@@ -93,7 +99,7 @@ class SequenceScorer:
         f.sv_id = np.asarray(sv_id)
 
     def score_points(self, fid: int, want_nn=False):
-        """LiDAL.py:59-81 for frame ``fid``: (interd f64 [Np], intere f32 [Np], matches int32 [Np][, nn int32 [24,Np]])."""
+        """LiDAL.py:59-81 for frame ``fid``: (interd f64 [Np], intere f32 [Np], matches int32 [Np][, nn int32 [Np,24]])."""
         q = self.frames[fid]
         nids = neighbour_ids(fid, self.n_frames, self.nei_num)
         refs = (L.FrameRef * len(nids))()
@@ -103,8 +109,8 @@ class SequenceScorer:
         interd = torch.empty(q.n, dtype=torch.float64, device=self.device)
         intere = torch.empty(q.n, dtype=torch.float32, device=self.device)
         count = torch.empty(q.n, dtype=torch.int32, device=self.device)
-        nn = torch.empty((len(nids), q.n), dtype=torch.int32, device=self.device) if want_nn else None
-        L.check(L.lib().lb_interframe_score(L.ptr(q.xyz), L.ptr(q.prob), q.n, q.prob.shape[1], refs, len(nids),
+        nn = torch.empty((q.n, len(nids)), dtype=torch.int32, device=self.device)
+        L.check(L.lib().lb_interframe_score(L.ptr(q.grid), L.ptr(q.prob), q.n, q.prob.shape[1], refs, len(nids),
                                             self.dis_thresh, self.cell, L.ptr(interd), L.ptr(intere), L.ptr(count),
                                             L.ptr(nn), L.stream()))
         return (interd, intere, count, nn) if want_nn else (interd, intere, count)

@@ -49,7 +49,7 @@ def test_per_point_scores_and_matches_exact(scorer_and_inputs, golden):
         for col, n in enumerate(orc.neighbour_ids(int(fid), seq.n_frames)):
             dist, idx = trees[n].query(seq.xyz[int(fid)], k=1)
             want = np.where(dist[:, 0] <= 0.1, idx[:, 0], -1)
-            assert np.array_equal(nn[col].cpu().numpy(), want), (fid, n)
+            assert np.array_equal(nn[:, col].cpu().numpy(), want), (fid, n)
         frac_exact = float((d.cpu().numpy() == g[f"pt_d{j}"]).mean())
         print(f"frame {fid}: {frac_exact:.4f} of per-point divergences bit-identical")
 
