@@ -93,6 +93,20 @@ size_t lb_unique_ws_bytes(int64_t n);
 int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64_t* uniq, int32_t* n_unique, int32_t* inverse,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* Engine-side map construction where the row ORDER of coarse levels is free (results are order independent):
+ * lb_group_by_key: groups equal int64 keys without sorting; groups are numbered by first occurrence (deterministic).
+ *   inverse int32 [n] = group of row i; first_row int32 [<=n] (optional) = first row of each group; n_groups device int32[1].
+ * lb_downsample_maps: kernel 2 / stride 2 level transition in one pass: parent voxels (coords // 2ts * 2ts, grouped by
+ *   first occurrence) plus both maps: nbr_dn int32 [8, ld_dn] (child row of parent g at offset k, the F.conv3d map of
+ *   the strided conv) and nbr_up int32 [8, n] (its per-offset inverse for the transposed conv).  Offset order is
+ *   get_kernel_offsets(2): k = 4*ox + 2*oy + oz.  Same voxel SET as lb_downsample; coordinates must be >= 0. */
+size_t lb_group_by_key_ws_bytes(int64_t n);
+int lb_group_by_key(const int64_t* keys, int64_t n, int32_t* inverse, int32_t* first_row, int32_t* n_groups, void* ws,
+                    size_t ws_bytes, void* stream);
+size_t lb_downsample_maps_ws_bytes(int64_t n);
+int lb_downsample_maps(const int32_t* coords, int64_t n, int tensor_stride, int32_t* out_coords, int32_t* n_out,
+                       int32_t* nbr_dn, int64_t ld_dn, int32_t* nbr_up, void* ws, size_t ws_bytes, void* stream);
+
 /* Stable LSD radix sort of (uint64 key, uint32 value) pairs on bits [0, end_bit). */
 size_t lb_sort_pairs_ws_bytes(int64_t n);
 int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* ws, size_t ws_bytes, void* stream);

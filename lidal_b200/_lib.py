@@ -53,6 +53,10 @@ SIGNATURES = {
     "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
     "lb_unique_ws_bytes": (sz, [i64]),
     "lb_unique_i64": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
+    "lb_group_by_key_ws_bytes": (sz, [i64]),
+    "lb_group_by_key": (i32, [vp, i64, vp, vp, vp, vp, sz, vp]),
+    "lb_downsample_maps_ws_bytes": (sz, [i64]),
+    "lb_downsample_maps": (i32, [vp, i64, i32, vp, vp, vp, i64, vp, vp, sz, vp]),
     "lb_sort_pairs_ws_bytes": (sz, [i64]),
     "lb_sort_pairs": (i32, [vp, vp, i64, i32, vp, sz, vp]),
     "lb_conv_pack_weight": (i32, [vp, i32, i32, i32, i32, vp, vp]),

@@ -584,3 +584,101 @@ extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t 
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+
+// ------------------------------------------------------------------------------------------ hash group-by (engine)
+// Groups equal keys without sorting: the group of a key is owned by its smallest row (atomicMin in the table), groups
+// are numbered in order of their owner row (exclusive scan) -> deterministic, first-occurrence order.
+namespace lb {
+__global__ void gb_flags(TableView t, const int64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ flags,
+                         int* __restrict__ owner) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int o = table_find(t, (uint64_t)__ldg(&keys[i]));
+    owner[i] = o;
+    flags[i] = (o == (int)i) ? 1u : 0u;
+  }
+}
+__global__ void gb_emit(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, const int* __restrict__ owner,
+                        int64_t n, int* __restrict__ inverse, int* __restrict__ first_row) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    inverse[i] = (int)pos[owner[i]];
+    if (flags[i] && first_row) first_row[pos[i]] = (int)i;
+  }
+}
+__global__ void dsm_keys(const int4* __restrict__ coords, int64_t n, int s2, int64_t* __restrict__ keys) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = __ldg(&coords[i]);
+    keys[i] = fnv60(c.x / s2 * s2, c.y / s2 * s2, c.z / s2 * s2, c.w);
+  }
+}
+// parent coordinates + both stride-2 maps from the child -> parent assignment (no hash queries)
+__global__ void dsm_emit(const int4* __restrict__ coords, const int* __restrict__ inverse, const uint32_t* __restrict__ flags,
+                         int64_t n, int ts, int4* __restrict__ out_coords, int* __restrict__ nbr_dn, int64_t ld_dn,
+                         int* __restrict__ nbr_up) {
+  const int s2 = 2 * ts;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = __ldg(&coords[i]);
+    const int g = inverse[i];
+    const int px = c.x / s2 * s2, py = c.y / s2 * s2, pz = c.z / s2 * s2;
+    const int k = ((c.x - px) / ts) * 4 + ((c.y - py) / ts) * 2 + (c.z - pz) / ts;     // even-kernel offset order: x slowest
+    if (flags[i]) out_coords[g] = make_int4(px, py, pz, c.w);
+    nbr_dn[(int64_t)k * ld_dn + g] = (int)i;
+    nbr_up[(int64_t)k * n + i] = g;
+  }
+}
+}  // namespace lb
+
+extern "C" size_t lb_group_by_key_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return align256(lb_hashtable_bytes(n)) + 3 * align256((size_t)n * 4) + align256(scan_ws_bytes(n)) + 256;
+}
+extern "C" int lb_group_by_key(const int64_t* keys, int64_t n, int32_t* inverse, int32_t* first_row, int32_t* n_groups,
+                               void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && n_groups && ws, "bad arguments");
+  if (ws_bytes < lb_group_by_key_ws_bytes(n)) { set_error("lb_group_by_key: workspace too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) { LB_CUDA(cudaMemsetAsync(n_groups, 0, 4, st)); return LB_OK; }
+  LB_CHECK_ARG(keys && inverse, "null pointer");
+  char* p = (char*)ws;
+  void* table = p; const size_t tb = lb_hashtable_bytes(n); p += align256(tb);
+  uint32_t* flags = (uint32_t*)p; p += align256((size_t)n * 4);
+  uint32_t* pos = (uint32_t*)p; p += align256((size_t)n * 4);
+  int* owner = (int*)p; p += align256((size_t)n * 4);
+  void* scan_ws = p;
+  int rc = lb_hashtable_build(keys, n, table, tb, stream);
+  if (rc != LB_OK) return rc;
+  int g = grid_for(n, 256);
+  gb_flags<<<g, 256, 0, st>>>(table_view(table, tb), keys, n, flags, owner); LB_LAUNCHED(1);
+  rc = exclusive_scan_u32(flags, pos, n, (uint32_t*)n_groups, scan_ws, st);
+  if (rc != LB_OK) return rc;
+  gb_emit<<<g, 256, 0, st>>>(flags, pos, owner, n, inverse, first_row); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" size_t lb_downsample_maps_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  return align256((size_t)n * 8) + align256((size_t)n * 4) + align256(lb_group_by_key_ws_bytes(n)) + 256;
+}
+extern "C" int lb_downsample_maps(const int32_t* coords, int64_t n, int tensor_stride, int32_t* out_coords, int32_t* n_out,
+                                  int32_t* nbr_dn, int64_t ld_dn, int32_t* nbr_up, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && tensor_stride > 0 && n_out && ws && ld_dn >= n, "bad arguments");
+  if (ws_bytes < lb_downsample_maps_ws_bytes(n)) { set_error("lb_downsample_maps: workspace too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) { LB_CUDA(cudaMemsetAsync(n_out, 0, 4, st)); return LB_OK; }
+  LB_CHECK_ARG(coords && out_coords && nbr_dn && nbr_up, "null pointer");
+  char* p = (char*)ws;
+  int64_t* keys = (int64_t*)p; p += align256((size_t)n * 8);
+  int* inverse = (int*)p; p += align256((size_t)n * 4);
+  void* gws = p;
+  int g = grid_for(n, 256);
+  dsm_keys<<<g, 256, 0, st>>>((const int4*)coords, n, 2 * tensor_stride, keys); LB_LAUNCHED(1);
+  int rc = lb_group_by_key(keys, n, inverse, nullptr, n_out, gws, lb_group_by_key_ws_bytes(n), stream);
+  if (rc != LB_OK) return rc;
+  LB_CUDA(cudaMemsetAsync(nbr_dn, 0xFF, (size_t)8 * ld_dn * 4, st));
+  LB_CUDA(cudaMemsetAsync(nbr_up, 0xFF, (size_t)8 * n * 4, st));
+  // flags live at a fixed place inside the group-by workspace: [table][flags]...
+  const uint32_t* flags = (const uint32_t*)((char*)gws + align256(lb_hashtable_bytes(n)));
+  dsm_emit<<<g, 256, 0, st>>>((const int4*)coords, inverse, flags, n, tensor_stride, (int4*)out_coords, nbr_dn, ld_dn, nbr_up); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

@@ -149,13 +149,19 @@ class Maps:
             self.nbr3.append(_mask_sorted(nbr3) if SORT_MAPS else nbr3)
             if lvl == 4:
                 break
-            cn = F.spdownsample(c, 2, 2, s)
-            off2 = _offsets(2, s, dev)
-            dn = torch.empty((8, cn.shape[0]), dtype=torch.int, device=dev)
-            L.check(L.lib().lb_kmap_query(L.ptr(table[0]), table[1], L.ptr(cn), cn.shape[0], None, L.ptr(off2), 8,
-                                          L.ptr(dn), L.stream()))
-            up = torch.empty((8, c.shape[0]), dtype=torch.int, device=dev)
-            L.check(L.lib().lb_kmap_transpose(L.ptr(dn), dn.stride(0), cn.shape[0], 8, L.ptr(up), c.shape[0], L.stream()))
+            # level transition in one pass (no sort, no hash queries): parents in first-occurrence order + both maps
+            n_c = c.shape[0]
+            cn_full = torch.empty_like(c)
+            n_out = torch.zeros(1, dtype=torch.int, device=dev)
+            dn_full = torch.empty((8, n_c), dtype=torch.int, device=dev)
+            up = torch.empty((8, n_c), dtype=torch.int, device=dev)
+            nbytes = L.lib().lb_downsample_maps_ws_bytes(n_c)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            L.check(L.lib().lb_downsample_maps(L.ptr(c), n_c, s, L.ptr(cn_full), L.ptr(n_out), L.ptr(dn_full), n_c, L.ptr(up),
+                                               L.ptr(ws), nbytes, L.stream()))
+            m_c = int(n_out.item())
+            cn = cn_full[:m_c]
+            dn = dn_full[:, :m_c]
             self.coords.append(cn)
             self.n.append(cn.shape[0])
             self.nbr_dn.append(_mask_sorted(dn) if SORT_MAPS else dn)
@@ -282,23 +288,25 @@ class InferenceEngine:
         return acc
 
     def _initial_voxelize(self, coords, feats):
-        """network/utils.py:13-33: voxels = unique hashes of the floored point coordinates, ascending hash order."""
+        """network/utils.py:13-33: voxels = unique hashes of the floored point coordinates (the reference orders them by
+        ascending hash; the engine keeps first-occurrence order, which only permutes internal rows)."""
         dev = coords.device
         zc = coords.float()
         zc = torch.cat([(zc[:, :3] * self.pres) / self.vres, zc[:, 3:]], 1).contiguous()       # new_float_coord
         cell = torch.floor(zc)
         h = F.sphash(cell.int())
         n = h.shape[0]
-        uniq = torch.empty(n, dtype=torch.int64, device=dev)
+        # voxel order inside the engine is free (outputs are per point): group by hash in first-occurrence order
         n_u = torch.zeros(1, dtype=torch.int, device=dev)
         inv = torch.empty(n, dtype=torch.int, device=dev)
-        nbytes = L.lib().lb_unique_ws_bytes(n)
+        first = torch.empty(n, dtype=torch.int, device=dev)
+        nbytes = L.lib().lb_group_by_key_ws_bytes(n)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        L.check(L.lib().lb_unique_i64(L.ptr(h), n, 60, L.ptr(uniq), L.ptr(n_u), L.ptr(inv), L.ptr(ws), nbytes, L.stream()))
+        L.check(L.lib().lb_group_by_key(L.ptr(h), n, L.ptr(inv), L.ptr(first), L.ptr(n_u), L.ptr(ws), nbytes, L.stream()))
         nv = int(n_u.item())
         counts = torch.empty(nv, dtype=torch.int, device=dev)
         L.check(L.lib().lb_count(L.ptr(inv), n, L.ptr(counts), nv, L.stream()))
-        vcoords = torch.round(self._vox(cell, inv, counts, nv)).int()
+        vcoords = cell.int()[first[:nv].long()].contiguous()        # every member of a voxel has the same floored coords
         vfeats = self._vox(feats.contiguous(), inv, counts, nv)
         return zc, vcoords, vfeats
 

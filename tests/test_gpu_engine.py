@@ -145,3 +145,27 @@ def test_devoxelize16_matches_fp32_kernel():
                                              L.LB_DT_BF16, c, L.stream()))
         want = ts.nn.functional.spdevoxelize(feats.float(), idx, w)
         assert torch.equal(out, want.bfloat16())
+
+
+def test_downsample_maps_equal_reference_maps_up_to_row_order(oracle_ts, small_scan):
+    """lb_downsample_maps: same coarse voxel SET as spdownsample, and nbr_dn / nbr_up encode the same (child, parent,
+    offset) triples as the reference's kernel map -- only the numbering of coarse rows differs."""
+    from lidal_b200 import engine
+    Fo = oracle_ts.nn.functional
+    coords = torch.from_numpy(small_scan[0])
+    m = engine.Maps(coords.cuda())
+    engine_sorted = engine.SORT_MAPS
+    for lvl in range(3):
+        s = 2 ** lvl
+        c_f = m.coords[lvl].cpu()
+        nb, ns, sz, oc, res = Fo.build_kernel_map(c_f, (s, s, s), (2, 2, 2), (2, 2, 2), (1, 1, 1))
+        c_c = m.coords[lvl + 1].cpu()
+        key = lambda t: (t[:, 3].long() << 48) | (t[:, 0].long() << 32) | (t[:, 1].long() << 16) | t[:, 2].long()   # noqa: E731
+        assert torch.equal(torch.sort(key(c_c)).values, key(oc))                 # same voxel set (oracle's is sorted)
+        # map oracle coarse row -> engine coarse row
+        order = torch.argsort(key(c_c))
+        to_engine = order                                                         # oracle row j == engine row order[j]
+        dn_s, perm = m.nbr_dn[lvl] if engine_sorted else (m.nbr_dn[lvl], None)
+        dn = torch.empty_like(dn_s.cpu())
+        dn[:, perm.cpu().long()] = dn_s.cpu() if perm is not None else dn_s.cpu()
+        assert torch.equal(dn[:, to_engine].long(), res)                          # child rows identical
