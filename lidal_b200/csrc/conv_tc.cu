@@ -21,6 +21,7 @@
 namespace lb {
 
 constexpr int TILE_M = 128;
+constexpr int MAX_T = 2;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int NUM_PROD_THREADS = 128;
 constexpr int NUM_THREADS = NUM_EPI_THREADS + NUM_PROD_THREADS + 32;
@@ -158,6 +159,8 @@ struct TcParams {
   int stages;
   int tmem_cols;
   int nb;                  // (offset, channel-block) blocks carried by one pipeline stage (1..4)
+  int T;                   // 128-row sub-tiles per CTA tile (1 or 2): T accumulators share every weight tile
+  int n_acc;               // TMEM accumulator sets (2 = epilogue overlaps the next tile, 1 when 2*T*c_out > 512)
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
 };
 
@@ -175,7 +178,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
 }
 
 // BK = channels per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
-template <int BK>
+template <int BK, int T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   constexpr int ROW_BYTES = BK * 2;
@@ -189,11 +192,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.c_out * ROW_BYTES;
   const int b_pad = (b_bytes + 1023) & ~1023;
-  const int stage_bytes = p.nb * (A_BYTES + b_pad);       // [nb A sub-tiles][nb B sub-tiles]
+  const int a_blk = T * A_BYTES;                        // A operand of one block: T sub-tiles of 128 rows
+  const int stage_bytes = p.nb * (a_blk + b_pad);         // [nb A blocks][nb B sub-tiles]
+  constexpr int TM = T * TILE_M;                          // output rows per CTA tile
   uint8_t* ring = smem;
   uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
-  int* s_idx = (int*)tail;                                         // [MAX_KVOL][TILE_M]
-  float* s_scale = (float*)(tail + MAX_KVOL * TILE_M * 4);         // [256]
+  int* s_idx = (int*)tail;                                         // [MAX_KVOL][T * TILE_M]
+  float* s_scale = (float*)(tail + MAX_KVOL * T * TILE_M * 4);   // [256]
   float* s_shift = s_scale + 256;                                  // [256]
   uint64_t* full_bar = (uint64_t*)(s_shift + 256);                 // [MAX_STAGES]
   uint64_t* empty_bar = full_bar + MAX_STAGES;                     // [MAX_STAGES]
@@ -205,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out;
-  const int64_t num_tiles = (n_out + TILE_M - 1) / TILE_M;
+  const int64_t num_tiles = (n_out + TM - 1) / TM;
   const int kc_blocks = p.c_in / BK;
 
   // ---------------- one-time setup
@@ -220,7 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], NUM_EPI_THREADS);
+      mbar_init(&tempty_bar[a], NUM_EPI_THREADS);   // every epilogue thread arrives once per tile
     }
     fence_barrier_init();
   }
@@ -250,23 +255,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(b_bytes * blk_goal));
         }
       }
-      if (t == 0) tma_load_2d(smem_u32(st_base + p.nb * A_BYTES + blk * b_pad), &w_map, b_col, b_row, &full_bar[stage]);
-      const uint32_t a_u32 = smem_u32(st_base + blk * A_BYTES);
+      if (t == 0) tma_load_2d(smem_u32(st_base + p.nb * a_blk + blk * b_pad), &w_map, b_col, b_row, &full_bar[stage]);
 #pragma unroll
-      for (int i = 0; i < TILE_M / ROWS_PER_PASS; ++i) {
-        const int r = row0 + i * ROWS_PER_PASS;
-        int nb;
-        const char* src;
-        if (p.pack8) {                                    // chunk <-> offset 8*cb + chunk, 16 bytes = its 8 channels
-          const int kk = cb * 8 + chunk;
-          nb = kk < p.k_vol ? s_idx[kk * TILE_M + r] : -1;
-          src = p.in + (int64_t)(nb >= 0 ? nb : 0) * p.ld_in * 2;
-        } else {
-          nb = s_idx[k * TILE_M + r];
-          src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + cb * BK + chunk * 8) * 2;
+      for (int sub = 0; sub < T; ++sub) {
+        const uint32_t a_u32 = smem_u32(st_base + blk * a_blk + sub * A_BYTES);
+#pragma unroll
+        for (int i = 0; i < TILE_M / ROWS_PER_PASS; ++i) {
+          const int r = row0 + i * ROWS_PER_PASS;
+          int nb;
+          const char* src;
+          if (p.pack8) {                                  // chunk <-> offset 8*cb + chunk, 16 bytes = its 8 channels
+            const int kk = cb * 8 + chunk;
+            nb = kk < p.k_vol ? s_idx[kk * TM + sub * TILE_M + r] : -1;
+            src = p.in + (int64_t)(nb >= 0 ? nb : 0) * p.ld_in * 2;
+          } else {
+            nb = s_idx[k * TM + sub * TILE_M + r];
+            src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + cb * BK + chunk * 8) * 2;
+          }
+          const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
+          cp_async16(a_u32 + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
         }
-        const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
-        cp_async16(a_u32 + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
       }
       if (++blk == blk_goal) {
         cp_async_arrive_noinc(&full_bar[stage]);          // asynchronous: fires when this thread's copies have landed
@@ -276,14 +284,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     };
     // Neighbour indices of the NEXT tile are fetched into registers while the current tile's stages are being issued
     // (27 independent loads in flight), so the tile prologue never waits on global memory.
-    int nb_reg[MAX_KVOL];
+    int nb_reg[T][MAX_KVOL];
     auto fetch_indices = [&](int64_t tile) {
-      const int64_t o = tile * TILE_M + t;
 #pragma unroll
-      for (int k = 0; k < MAX_KVOL; ++k) {
-        int nb = -1;
-        if (k < p.k_vol && o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
-        nb_reg[k] = nb;
+      for (int sub = 0; sub < T; ++sub) {
+        const int64_t o = tile * TM + sub * TILE_M + t;
+#pragma unroll
+        for (int k = 0; k < MAX_KVOL; ++k) {
+          int nb = -1;
+          if (k < p.k_vol && o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
+          nb_reg[sub][k] = nb;
+        }
       }
     };
     if ((int64_t)blockIdx.x < num_tiles) fetch_indices(blockIdx.x);
@@ -294,12 +305,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t my_mask = 0;
 #pragma unroll
-      for (int k = 0; k < MAX_KVOL; ++k) {
-        if (k < p.k_vol) {
-          int nb = nb_reg[k];
-          if (nb >= p.n_in) nb = -1;
-          s_idx[k * TILE_M + t] = nb;
-          if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
+      for (int sub = 0; sub < T; ++sub) {
+        {
+#pragma unroll
+          for (int k = 0; k < MAX_KVOL; ++k) {
+            if (k < p.k_vol) {
+              int nb = nb_reg[sub][k];
+              if (nb >= p.n_in) nb = -1;
+              s_idx[k * TM + sub * TILE_M + t] = nb;
+              if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
+            }
+          }
         }
       }
       if (lane == 0 && my_mask) atomicOr(&s_mask[par], my_mask);
@@ -330,11 +346,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     uint32_t ph = 0;
     int64_t tcount = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int acc = (int)(tcount & 1);
-      const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
-      mbar_wait(&tempty_bar[acc], acc_ph ^ 1);            // epilogue drained this accumulator
+      const int acc = (int)(tcount % p.n_acc);
+      const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+      mbar_wait(&tempty_bar[acc], acc_ph ^ 1);            // epilogue drained this accumulator set
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.c_out);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * p.c_out);
       while (true) {
         mbar_wait(&full_bar[stage], ph);
         fence_proxy_async();                              // gathered rows were written through the generic proxy (cp.async)
@@ -344,12 +360,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
           const uint32_t st_u32 = smem_u32(ring + (size_t)stage * stage_bytes);
           const int nblk = (int)(flags >> 8);
           for (int j = 0; j < nblk; ++j) {
-            const uint64_t a_desc = make_smem_desc(st_u32 + j * A_BYTES, SBO, LAYOUT);
-            const uint64_t b_desc = make_smem_desc(st_u32 + p.nb * A_BYTES + j * b_pad, SBO, LAYOUT);
+            const uint64_t b_desc = make_smem_desc(st_u32 + p.nb * a_blk + j * b_pad, SBO, LAYOUT);
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
-              umma_f16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                       ((flags & 1u) && j == 0 && kk == 0) ? 0u : 1u);
+            for (int sub = 0; sub < T; ++sub) {         // every sub-tile reuses the same weight tile
+              const uint64_t a_desc = make_smem_desc(st_u32 + j * a_blk + sub * A_BYTES, SBO, LAYOUT);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk)        // +32 bytes along K inside the swizzle atom = +2 in the address field
+                umma_f16(d_tmem + (uint32_t)(sub * p.c_out), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                         ((flags & 1u) && j == 0 && kk == 0) ? 0u : 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
           if (flags & 2u) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
@@ -364,18 +383,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     int64_t tcount = 0;
     const int out_es = (p.out_dtype == LB_DT_F32) ? 4 : 2;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int acc = (int)(tcount & 1);
-      const uint32_t acc_ph = (uint32_t)((tcount >> 1) & 1);
+      const int acc = (int)(tcount % p.n_acc);
+      const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      const int64_t o = tile * TILE_M + warp * 32 + lane;
+      for (int sub = 0; sub < T; ++sub) {
+      const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
       const bool live = o < n_out;
       const int64_t orow = live ? (p.out_rows ? (int64_t)__ldg(&p.out_rows[o]) : o) : 0;
       char* out_row = p.out + orow * p.ld_out * out_es;
       const char* res_row = p.residual ? p.residual + orow * p.ld_res * 2 : nullptr;
       for (int c0 = 0; c0 < p.c_out; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * p.c_out + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
         if (live) {
           float f[32];
 #pragma unroll
@@ -422,6 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
           }
         }
       }
+      }   // sub-tiles
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -465,8 +486,8 @@ int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
   return 1;
 }
 
-static size_t tail_bytes() {
-  return (size_t)MAX_KVOL * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64;
+static size_t tail_bytes(int T) {
+  return (size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64;
 }
 
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
@@ -504,12 +525,25 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.k_vol = a.k_vol; p.c_in = a.c_in; p.c_out = a.c_out;
   p.scale = a.scale; p.shift = a.shift; p.residual = (const char*)a.residual; p.ld_res = a.ld_res;
   p.out_dtype = a.out_dtype; p.relu = (a.flags & LB_CONV_RELU) ? ((a.flags & LB_CONV_RELU_FIRST) ? 2 : 1) : 0; p.is_bf16 = a.act_dtype == LB_DT_BF16;
+  // 256-row CTA tiles (two accumulators sharing every weight tile) when (a) there are enough rows to keep every SM
+  // busy and (b) the doubled A operand still leaves a deep (>= 6 stage) ring -- measured on B200: -15..-19 % on the
+  // 32/96-channel layers of the two finest levels, +13 % (worse) on 128->128 where the ring would drop to 4 stages.
+  const int64_t tiles128 = (a.n_out + TILE_M - 1) / TILE_M;
+  int T = 1;
+  {
+    const size_t blk2 = (size_t)2 * TILE_M * bk * 2 + (((size_t)a.c_out * bk * 2 + 1023) & ~(size_t)1023);
+    const size_t budget2 = 227 * 1024 - 1024 - tail_bytes(2);
+    if (tiles128 >= (int64_t)8 * sm_count() && budget2 / blk2 >= 6 && 2 * a.c_out <= 512) T = 2;
+  }
+  if (a.flags & LB_CONV_TILE128) T = 1;
+  p.T = T;
+  p.n_acc = (2 * T * a.c_out <= 512) ? 2 : 1;
   int cols = 32;
-  while (cols < 2 * a.c_out) cols <<= 1;
+  while (cols < p.n_acc * T * a.c_out) cols <<= 1;
   p.tmem_cols = cols;
   const int row_bytes = bk * 2;
-  const size_t block_bytes = (size_t)TILE_M * row_bytes + (((size_t)a.c_out * row_bytes + 1023) & ~(size_t)1023);
-  const size_t budget = 227 * 1024 - 1024 - tail_bytes();
+  const size_t block_bytes = (size_t)T * TILE_M * row_bytes + (((size_t)a.c_out * row_bytes + 1023) & ~(size_t)1023);
+  const size_t budget = 227 * 1024 - 1024 - tail_bytes(T);
   // blocks per stage: measured on B200, carrying several blocks per stage (fewer, coarser stages) is not faster than
   // a deep ring of single-block stages -- the kernel is bound by L2 traffic, not by the per-stage hand-shake.
   int nb = 1;
@@ -520,17 +554,21 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.stages = stages;
   p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
-  const size_t smem = (size_t)stages * stage_bytes + tail_bytes() + 1024;
-  int64_t tiles = (a.n_out + TILE_M - 1) / TILE_M;
+  const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + 1024;
+  int64_t tiles = (a.n_out + (int64_t)T * TILE_M - 1) / ((int64_t)T * TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-  if (bk == 64) {
-    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<64><<<grid, NUM_THREADS, smem, st>>>(map, p); LB_LAUNCHED(1);
-  } else {
-    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<32><<<grid, NUM_THREADS, smem, st>>>(map, p); LB_LAUNCHED(1);
-  }
+#define LB_TC_LAUNCH(BKV, TV)                                                                                         \
+  do {                                                                                                                \
+    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BKV, TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    conv_tc_kernel<BKV, TV><<<grid, NUM_THREADS, smem, st>>>(map, p);                                                  \
+    LB_LAUNCHED(1);                                                                                                   \
+  } while (0)
+  if (bk == 64 && T == 1) LB_TC_LAUNCH(64, 1);
+  else if (bk == 64) LB_TC_LAUNCH(64, 2);
+  else if (T == 1) LB_TC_LAUNCH(32, 1);
+  else LB_TC_LAUNCH(32, 2);
+#undef LB_TC_LAUNCH
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
