@@ -188,6 +188,8 @@ int lb_ti_weights(const float* coords, int64_t ld_c, const int64_t* idx, int64_t
  *                       F.calc_ti_weights, idx int32 [n,8], w f32 [n,8].   pts f32 [n, ld>=4] = (x,y,z,...,batch LAST).
  * table: lb_hashtable_build over lb_hash(voxel coords).
  * *_ex: 16-bit or fp32 features with a row stride (elements); voxelize accumulates in fp32. */
+/* out[i] = src[idx[i]] for 16-byte rows (int32 [.,4] coordinates). */
+int lb_gather_rows16(const void* src, const int32_t* idx, int64_t n, void* out, void* stream);
 int lb_point_cell_query(const float* pts, int64_t ld, int64_t n, int stride, const void* table, size_t table_bytes,
                         int32_t* idx, void* stream);
 int lb_point_corner_query(const float* pts, int64_t ld, int64_t n, int stride, const void* table, size_t table_bytes,

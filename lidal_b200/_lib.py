@@ -69,6 +69,7 @@ SIGNATURES = {
     "lb_devoxelize_fwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
     "lb_devoxelize_bwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
     "lb_ti_weights": (i32, [vp, i64, vp, i64, flt, vp, vp]),
+    "lb_gather_rows16": (i32, [vp, vp, i64, vp, vp]),
     "lb_point_cell_query": (i32, [vp, i64, i64, i32, vp, sz, vp, vp]),
     "lb_point_corner_query": (i32, [vp, i64, i64, i32, vp, sz, vp, vp, vp]),
     "lb_voxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, vp]),

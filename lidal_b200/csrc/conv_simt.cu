@@ -158,7 +158,7 @@ extern "C" int lb_conv_uses_tensor_cores(int k_vol, int c_in, int c_out, int act
 extern "C" int lb_conv_fwd(const lb_conv_args* a, void* stream) {
   LB_CHECK_ARG(a, "null args");
   LB_CHECK_ARG(a->n_in >= 0 && a->n_out >= 0, "negative row count");
-  if (a->n_out == 0) return LB_OK;
+  if (a->n_out == 0) return LB_OK;                  // empty outputs: nothing to do (strides of empty tensors are arbitrary)
   LB_CHECK_ARG(a->in && a->out && a->weight, "null tensor");
   LB_CHECK_ARG(a->k_vol >= 1 && a->c_in >= 1 && a->c_out >= 1 && a->c_out <= 256, "bad k_vol/c_in/c_out (c_out <= 256)");
   LB_CHECK_ARG(a->ld_in >= a->c_in && a->ld_out >= a->c_out, "row stride smaller than channel count");

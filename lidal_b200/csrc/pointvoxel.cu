@@ -278,8 +278,9 @@ static int cast_dispatch(const S* src, int64_t ld_s, void* dst, int dd, int64_t 
 }
 extern "C" int lb_cast(const void* src, int sd, int64_t ld_s, void* dst, int dd, int64_t ld_d, int64_t rows,
                        int64_t cols, void* stream) {
-  LB_CHECK_ARG(rows >= 0 && cols >= 0 && ld_s >= cols && ld_d >= cols, "bad sizes");
-  if (rows == 0 || cols == 0) return LB_OK;
+  LB_CHECK_ARG(rows >= 0 && cols >= 0, "bad sizes");
+  if (rows == 0 || cols == 0) return LB_OK;         // empty tensors carry arbitrary strides
+  LB_CHECK_ARG(ld_s >= cols && ld_d >= cols, "row stride smaller than the column count");
   LB_CHECK_ARG(src && dst, "null pointer");
   cudaStream_t st = as_stream(stream);
   if (sd == LB_DT_F32) return cast_dispatch((const float*)src, ld_s, dst, dd, ld_d, rows, cols, st);
@@ -477,10 +478,11 @@ extern "C" int lb_point_corner_query(const float* pts, int64_t ld, int64_t n, in
 }
 extern "C" int lb_voxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_f, const int32_t* idx,
                                   const int32_t* counts, int64_t n, int64_t m, int c, float* out, void* stream) {
-  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0 && ld_f >= c, "bad sizes");
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0, "bad sizes");
   cudaStream_t st = as_stream(stream);
   if (m > 0) { LB_CHECK_ARG(out, "null out"); LB_CUDA(cudaMemsetAsync(out, 0, (size_t)m * c * 4, st)); }
   if (n == 0 || m == 0) return LB_OK;
+  LB_CHECK_ARG(ld_f >= c, "row stride smaller than the channel count");
   LB_CHECK_ARG(feats && idx && counts, "null pointer");
   int g = rows_grid(n, 8);
   if (feats_dtype == LB_DT_F32) { voxelize_ex_kernel<float><<<g, 256, 0, st>>>((const float*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
@@ -503,8 +505,9 @@ static int devox_out(const TI* feats, int64_t ld_f, const int32_t* idx, const fl
 }
 extern "C" int lb_devoxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_f, const int32_t* idx, const float* w,
                                     int64_t n, int64_t m, int c, void* out, int out_dtype, int64_t ld_o, void* stream) {
-  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0 && ld_f >= c && ld_o >= c, "bad sizes");
+  LB_CHECK_ARG(n >= 0 && m >= 0 && c > 0, "bad sizes");
   if (n == 0) return LB_OK;
+  LB_CHECK_ARG(ld_o >= c && (m == 0 || ld_f >= c), "row stride smaller than the channel count");
   LB_CHECK_ARG(feats && idx && w && out, "null pointer");
   cudaStream_t st = as_stream(stream);
   if (feats_dtype == out_dtype && feats_dtype != LB_DT_F32 && c % 8 == 0 && ld_f % 8 == 0 && ld_o % 8 == 0 &&
@@ -521,4 +524,20 @@ extern "C" int lb_devoxelize_fwd_ex(const void* feats, int feats_dtype, int64_t 
   if (feats_dtype == LB_DT_F16) return devox_out((const __half*)feats, ld_f, idx, w, n, m, c, out, out_dtype, ld_o, st);
   set_error("lb_devoxelize_fwd_ex: bad feats dtype");
   return LB_EINVAL;
+}
+
+namespace lb {
+__global__ void gather_rows16_kernel(const int4* __restrict__ src, const int* __restrict__ idx, int64_t n, int4* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __ldg(&src[__ldg(&idx[i])]);
+}
+}  // namespace lb
+extern "C" int lb_gather_rows16(const void* src, const int32_t* idx, int64_t n, void* out, void* stream) {
+  LB_CHECK_ARG(n >= 0, "n < 0");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(src && idx && out && ((((uintptr_t)src) | ((uintptr_t)out)) & 15) == 0, "null or unaligned pointer");
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  gather_rows16_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>((const int4*)src, idx, n, (int4*)out); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
 }

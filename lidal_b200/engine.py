@@ -308,7 +308,9 @@ class InferenceEngine:
         nv = int(n_u.item())
         counts = torch.empty(nv, dtype=torch.int, device=dev)
         L.check(L.lib().lb_count(L.ptr(inv), n, L.ptr(counts), nv, L.stream()))
-        vcoords = cell.int()[first[:nv].long()].contiguous()        # every member of a voxel has the same floored coords
+        cell_i = cell.int()
+        vcoords = torch.empty((nv, 4), dtype=torch.int, device=dev)     # every member of a voxel has the same floored coords
+        L.check(L.lib().lb_gather_rows16(L.ptr(cell_i), L.ptr(first), nv, L.ptr(vcoords), L.stream()))
         vfeats = self._vox(feats.contiguous(), inv, counts, nv)
         return zc, vcoords, vfeats
 

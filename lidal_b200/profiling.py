@@ -78,6 +78,13 @@ def conv_roofline(run, resident, steps=3):
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK["bf16_tflops_sustained"]))
     achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     best = max(tc, key=lambda r: r["flops"] / max(r["ms"], 1e-6)) if tc else None
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tpath):          # dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed ncu pass
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_conv_traffic.json (ncu, per launch)"
+    alg_bytes = sum(2.0 * (r["n_out"] * r["cin"] + r["n_out"] * r["cout"]) + 4.0 * r["k"] * r["n_out"] + 2.0 * r["k"] * r["cin"] * r["cout"]
+                    for r in tc) / max(len(tc), 1)
     if os.environ.get("LIDAL_LAYER_TABLE"):
         import sys
         per = len(rows) // steps
@@ -87,7 +94,8 @@ def conv_roofline(run, resident, steps=3):
                   f"{r['ms']:7.3f} {r['flops'] / r['ms'] / 1e9:8.1f} {r['dense_flops'] / r['ms'] / 1e9:10.1f} {int(r['tc'])}", file=sys.stderr)
     return {
         "bound": "tensor", "kernel": "lb::conv_tc_kernel (tcgen05 implicit-GEMM sparse conv)",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
         "launches_per_step": len(tc) / steps, "avg_launch_ms": tc_ms / max(len(tc), 1),
         "algorithmic_gflop_per_step": tc_fl / steps / 1e9,

@@ -10,6 +10,8 @@ def main(path, top=30):
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot, n = 0.0, 0
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         v = float(row["Metric Value"].replace(",", ""))
         v = v / 1e3 if row["Metric Unit"] == "ns" else (v * 1e3 if row["Metric Unit"] == "ms" else v)
         name = re.sub(r"<.*", "", row["Kernel Name"])[:70]
