@@ -107,9 +107,15 @@ def test_mask_sorted_map_and_pack8(small_scan):
     nbr_s, perm = engine._mask_sorted(nbr)
     assert torch.equal(torch.sort(perm.long()).values.cpu(), torch.arange(n))
     assert torch.equal(nbr_s, nbr[:, perm.long()])
-    mask = ((nbr >= 0).long() << torch.arange(27, device="cuda").unsqueeze(1)).sum(0)
-    ms = mask[perm.long()]
+    valid = nbr >= 0
+    freq = valid.sum(1)
+    rank = torch.argsort(torch.argsort(freq * 32 + torch.arange(27, device="cuda")))     # ascending frequency, ties by offset
+    key = (valid.long() << (26 - rank).unsqueeze(1)).sum(0)                              # least frequent offset = MSB
+    ms = key[perm.long()]
     assert bool((ms[1:] >= ms[:-1]).all())
+    # rows with equal keys keep their original order (stable)
+    same = ms[1:] == ms[:-1]
+    assert bool((perm[1:][same] > perm[:-1][same]).all())
     g = torch.Generator().manual_seed(0)
     x = torch.randn(n, 64, generator=g).cuda().bfloat16()
     conv = engine._Conv((torch.randn(27, 64, 96, generator=g) * 0.05).cuda(), None, relu=True)
