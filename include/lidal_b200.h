@@ -88,11 +88,12 @@ int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int 
 int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* nbr_t, int64_t n_in,
                       void* stream);
 
-/* torch.unique(keys) with inverse (network/utils.py:18-19 fused): uniq int64 [<=n] ascending, n_unique device
- * int32[1], inverse int32 [n] (optional) = position of keys[i] in uniq.  key_bits: significant low bits of the keys. */
+/* torch.unique(keys) / np.unique(return_index, return_inverse) : uniq int64 [<=n] ascending, n_unique device int32[1],
+ * inverse int32 [n] (optional) = position of keys[i] in uniq, first_row int32 [<=n] (optional) = first occurrence of
+ * each unique key (network/utils.py:18-19, dataset/sk_dataset.py:167).  key_bits: significant low bits of the keys. */
 size_t lb_unique_ws_bytes(int64_t n);
 int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64_t* uniq, int32_t* n_unique, int32_t* inverse,
-                  void* ws, size_t ws_bytes, void* stream);
+                  int32_t* first_row, void* ws, size_t ws_bytes, void* stream);
 
 /* Engine-side map construction where the row ORDER of coarse levels is free (results are order independent):
  * lb_group_by_key: groups equal int64 keys without sorting; groups are numbered by first occurrence (deterministic).
@@ -199,6 +200,16 @@ int lb_voxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_feats, con
                        int64_t n, int64_t m, int c, float* out, void* stream);
 int lb_devoxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_feats, const int32_t* idx, const float* w,
                          int64_t n, int64_t m, int c, void* out, int out_dtype, int64_t ld_out, void* stream);
+
+/* Score-mode voxelizer (dataset/sk_dataset.py:143-169), two steps around the caller's
+ * data-dependent random shift:  lb_tta_transform: coords_f64 = (raw[:, :3] @ trans_m) * scale (float64 [n,3]) and
+ * feats f32 [n,4] = (transformed xyz as f32, intensity);  lb_tta_quantize: (coords_f64 + offset).astype(int) ->
+ * coords int32 [n,4] = (x, y, z, batch) and keys int64 [n] = x << 2b | y << b | z (b = coord_bits), whose ascending
+ * order is np.unique(axis=0)'s row order; err_flag (device int32[1]) is set if a coordinate leaves [0, 2^b). */
+int lb_tta_transform(const float* raw, int64_t n, const double* trans_m, double scale, double* coords_f64, float* feats,
+                     void* stream);
+int lb_tta_quantize(const double* coords_f64, int64_t n, const double* offset, int batch, int coord_bits, int32_t* coords,
+                    int64_t* keys, int32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------ prob_inference tail
  * score/prob_inference.py:100-113: gather logits by inverse index, softmax, mean over views, argmax.

@@ -52,7 +52,7 @@ SIGNATURES = {
     "lb_kmap_sort_by_mask": (i32, [vp, i64, i64, i32, vp, vp, vp, sz, vp]),
     "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
     "lb_unique_ws_bytes": (sz, [i64]),
-    "lb_unique_i64": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
+    "lb_unique_i64": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, sz, vp]),
     "lb_group_by_key_ws_bytes": (sz, [i64]),
     "lb_group_by_key": (i32, [vp, i64, vp, vp, vp, vp, sz, vp]),
     "lb_downsample_maps_ws_bytes": (sz, [i64]),
@@ -74,6 +74,8 @@ SIGNATURES = {
     "lb_point_corner_query": (i32, [vp, i64, i64, i32, vp, sz, vp, vp, vp]),
     "lb_voxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, vp]),
     "lb_devoxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, i32, i64, vp]),
+    "lb_tta_transform": (i32, [vp, i64, C.POINTER(dbl), dbl, vp, vp, vp]),
+    "lb_tta_quantize": (i32, [vp, i64, C.POINTER(dbl), i32, i32, vp, vp, vp, vp]),
     "lb_tta_softmax_mean_argmax": (i32, [vp, i64, i32, vp, i32, i64, vp, vp, vp]),
     "lb_frame_grid_bytes": (sz, [i64]),
     "lb_frame_grid_ws_bytes": (sz, [i64]),

@@ -2,12 +2,12 @@
 //
 //   out[o, :] = epilogue( sum_{k in offsets} in[nbr[k][o], :] @ W[k] )
 //
-// One persistent CTA per SM walks 128-row output tiles.  Warp roles (288 threads):
+// One persistent CTA per SM walks 128- or 256-row output tiles.  Warp roles (416 threads):
 //   warps 0-3  epilogue : tcgen05.ld accumulator rows from TMEM -> scale/shift/residual/ReLU -> global store
-//   warps 4-7  producers: gather the A operand -- 128 neighbour rows x BLOCK_K channels -- straight into the
+//   warps 4-11 producers: gather the A operand -- 128 neighbour rows x BLOCK_K channels -- straight into the
 //                         swizzled K-major shared-memory layout with 16-byte cp.async (zero-fill for missing
 //                         neighbours); thread 128 also issues the TMA load of the weight tile W[k][:, c0:c0+BK]
-//   warp  8    MMA      : one elected thread issues tcgen05.mma (M=128, N=c_out, K=16) per 16 channels,
+//   warp  12   MMA      : one elected thread issues tcgen05.mma (M=128, N=c_out, K=16) per 16 channels,
 //                         accumulating over all active offsets and channel blocks in TMEM (fp32)
 // Producers never block on their own copies: each thread posts `cp.async.mbarrier.arrive.noinc` on the stage's full
 // barrier, which the hardware fires when that thread's copies have landed, so the whole ring depth is in flight.
@@ -23,8 +23,9 @@ namespace lb {
 constexpr int TILE_M = 128;
 constexpr int MAX_T = 2;
 constexpr int NUM_EPI_THREADS = 128;
-constexpr int NUM_PROD_THREADS = 128;
+constexpr int NUM_PROD_THREADS = 256;   // 8 gather warps: two per scheduler, so dependent address/LDS/cp.async chains overlap
 constexpr int NUM_THREADS = NUM_EPI_THREADS + NUM_PROD_THREADS + 32;
+constexpr int MMA_WARP = (NUM_EPI_THREADS + NUM_PROD_THREADS) / 32;
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_KVOL = 27;
 constexpr int MAX_LAG = 10;           // cp.async groups a producer thread keeps in flight before signalling the oldest
@@ -229,13 +230,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+  if (warp == MMA_WARP) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < MMA_WARP) {
     // =============================================================== PRODUCERS
     const int t = threadIdx.x - NUM_EPI_THREADS;          // 0..127
     const int chunk = t % CHUNKS, row0 = t / CHUNKS;
@@ -284,17 +285,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     };
     // Neighbour indices of the NEXT tile are fetched into registers while the current tile's stages are being issued
     // (27 independent loads in flight), so the tile prologue never waits on global memory.
-    int nb_reg[T][MAX_KVOL];
+    int nb_reg[MAX_KVOL];
+    const bool idx_thread = t < TM;                       // thread t stages the indices of tile row t (rows 0..TM-1)
     auto fetch_indices = [&](int64_t tile) {
+      const int64_t o = tile * TM + t;
 #pragma unroll
-      for (int sub = 0; sub < T; ++sub) {
-        const int64_t o = tile * TM + sub * TILE_M + t;
-#pragma unroll
-        for (int k = 0; k < MAX_KVOL; ++k) {
-          int nb = -1;
-          if (k < p.k_vol && o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
-          nb_reg[sub][k] = nb;
-        }
+      for (int k = 0; k < MAX_KVOL; ++k) {
+        int nb = -1;
+        if (idx_thread && k < p.k_vol && o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
+        nb_reg[k] = nb;
       }
     };
     if ((int64_t)blockIdx.x < num_tiles) fetch_indices(blockIdx.x);
@@ -305,17 +304,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t my_mask = 0;
 #pragma unroll
-      for (int sub = 0; sub < T; ++sub) {
-        {
-#pragma unroll
-          for (int k = 0; k < MAX_KVOL; ++k) {
-            if (k < p.k_vol) {
-              int nb = nb_reg[sub][k];
-              if (nb >= p.n_in) nb = -1;
-              s_idx[k * TM + sub * TILE_M + t] = nb;
-              if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
-            }
-          }
+      for (int k = 0; k < MAX_KVOL; ++k) {
+        if (k < p.k_vol) {
+          int nb = nb_reg[k];
+          if (nb >= p.n_in) nb = -1;
+          if (idx_thread) s_idx[k * TM + t] = nb;         // row t of the tile == sub-tile t / 128, row t % 128
+          if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
         }
       }
       if (lane == 0 && my_mask) atomicOr(&s_mask[par], my_mask);
@@ -339,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       }
     }
     cp_async_wait<0>();                                   // nothing of ours may still be in flight at teardown
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // =============================================================== MMA ISSUER
     const uint32_t idesc = make_idesc(TILE_M, p.c_out, p.is_bf16 ? 1 : 0);
     int stage = 0;
@@ -451,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }

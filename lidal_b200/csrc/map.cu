@@ -503,10 +503,13 @@ __global__ void uq_iota(uint32_t* v, int64_t n) {
 }
 __global__ void uq_emit(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                         const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, int64_t n,
-                        int64_t* __restrict__ uniq, int* __restrict__ inverse) {
+                        int64_t* __restrict__ uniq, int* __restrict__ inverse, int* __restrict__ first_row) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t id = pos[i] + flags[i] - 1;          // exclusive scan of flags -> id of the run this element belongs to
-    if (flags[i]) uniq[id] = (int64_t)keys[i];
+    if (flags[i]) {
+      uniq[id] = (int64_t)keys[i];
+      if (first_row) first_row[id] = (int)vals[i];   // stable sort: the run's first element is the first occurrence
+    }
     if (inverse) inverse[vals[i]] = (int)id;
   }
 }
@@ -517,7 +520,7 @@ extern "C" size_t lb_unique_ws_bytes(int64_t n) {
          align256(lb_sort_pairs_ws_bytes(n)) + 256;
 }
 extern "C" int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64_t* uniq, int32_t* n_unique,
-                             int32_t* inverse, void* ws, size_t ws_bytes, void* stream) {
+                             int32_t* inverse, int32_t* first_row, void* ws, size_t ws_bytes, void* stream) {
   LB_CHECK_ARG(n >= 0 && n_unique && ws && key_bits > 0 && key_bits <= 64, "bad arguments");
   if (ws_bytes < lb_unique_ws_bytes(n)) { set_error("lb_unique_i64: workspace too small"); return LB_ECAP; }
   cudaStream_t st = as_stream(stream);
@@ -538,7 +541,7 @@ extern "C" int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64
   ds_flags<<<g, 256, 0, st>>>(k, n, flags); LB_LAUNCHED(1);
   rc = exclusive_scan_u32(flags, pos, n, (uint32_t*)n_unique, scan_ws, st);
   if (rc != LB_OK) return rc;
-  uq_emit<<<g, 256, 0, st>>>(k, v, flags, pos, n, uniq, inverse); LB_LAUNCHED(1);
+  uq_emit<<<g, 256, 0, st>>>(k, v, flags, pos, n, uniq, inverse, first_row); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -541,3 +541,63 @@ extern "C" int lb_gather_rows16(const void* src, const int32_t* idx, int64_t n, 
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+
+// ---------------------------------------------------------------------------------------- F1: score-mode voxelizer
+// dataset/sk_dataset.py:143-169 on device.  Step 1: coords_p = raw[:, :3] @ trans_m (float64), feats = (coords_p as f32,
+// intensity), coords_p *= scale.  Step 2 (after the caller derived the random shift from min/max): += offset,
+// astype(int), pack the (x, y, z) key whose ascending order is np.unique(axis=0)'s lexicographic row order.
+namespace lb {
+struct Mat3 { double m[9]; double off[3]; };
+__global__ void tta_transform_kernel(const float4* __restrict__ raw, int64_t n, const __grid_constant__ Mat3 M, double scale,
+                                     double* __restrict__ cp /*[n,3]*/, float4* __restrict__ feats) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 r = __ldg(&raw[i]);
+    const double x = r.x, y = r.y, z = r.z;
+    double c[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)     // row-vector times matrix: sum_k p[k] * m[k][j], accumulated in k order without FMA contraction
+      c[j] = __dadd_rn(__dadd_rn(__dmul_rn(x, M.m[j]), __dmul_rn(y, M.m[3 + j])), __dmul_rn(z, M.m[6 + j]));
+    feats[i] = make_float4((float)c[0], (float)c[1], (float)c[2], r.w);
+    cp[3 * i] = __dmul_rn(c[0], scale);
+    cp[3 * i + 1] = __dmul_rn(c[1], scale);
+    cp[3 * i + 2] = __dmul_rn(c[2], scale);
+  }
+}
+__global__ void tta_quantize_kernel(const double* __restrict__ cp, int64_t n, const __grid_constant__ Mat3 M, int batch,
+                                    int coord_bits, int4* __restrict__ coords, int64_t* __restrict__ keys, int* __restrict__ err) {
+  const long long lim = 1LL << coord_bits;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double fx = __dadd_rn(cp[3 * i], M.off[0]), fy = __dadd_rn(cp[3 * i + 1], M.off[1]), fz = __dadd_rn(cp[3 * i + 2], M.off[2]);
+    const long long x = (long long)fx, y = (long long)fy, z = (long long)fz;      // astype(int): truncation toward zero
+    if (fx < 0 || fy < 0 || fz < 0 || x >= lim || y >= lim || z >= lim) atomicOr(err, 1);   // the reference asserts validity (:160-161)
+    coords[i] = make_int4((int)x, (int)y, (int)z, batch);
+    keys[i] = (int64_t)(((unsigned long long)x << (2 * coord_bits)) | ((unsigned long long)y << coord_bits) | (unsigned long long)z);
+  }
+}
+}  // namespace lb
+extern "C" int lb_tta_transform(const float* raw, int64_t n, const double* trans_m /*[host] 9*/, double scale, double* coords_f64,
+                                float* feats, void* stream) {
+  LB_CHECK_ARG(n >= 0 && trans_m, "bad arguments");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(raw && coords_f64 && feats && ((((uintptr_t)raw) | ((uintptr_t)feats)) & 15) == 0, "null or unaligned pointer");
+  Mat3 M;
+  for (int i = 0; i < 9; ++i) M.m[i] = trans_m[i];
+  M.off[0] = M.off[1] = M.off[2] = 0;
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  tta_transform_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>((const float4*)raw, n, M, scale, coords_f64, (float4*)feats); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_tta_quantize(const double* coords_f64, int64_t n, const double* offset /*[host] 3*/, int batch, int coord_bits,
+                               int32_t* coords, int64_t* keys, int32_t* err_flag, void* stream) {
+  LB_CHECK_ARG(n >= 0 && offset && coord_bits > 0 && coord_bits <= 20 && err_flag, "bad arguments");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(coords_f64 && coords && keys && (((uintptr_t)coords) & 15) == 0, "null or unaligned pointer");
+  Mat3 M;
+  for (int i = 0; i < 9; ++i) M.m[i] = 0;
+  for (int i = 0; i < 3; ++i) M.off[i] = offset[i];
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  tta_quantize_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, as_stream(stream)>>>(coords_f64, n, M, batch, coord_bits, (int4*)coords, keys, err_flag); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

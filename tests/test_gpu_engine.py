@@ -68,10 +68,13 @@ def test_unique_and_point_queries_vs_oracle(oracle_ts, small_scan):
     nbytes = L.lib().lb_unique_ws_bytes(n)
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     kd = keys.cuda()
-    L.check(L.lib().lb_unique_i64(L.ptr(kd), n, 60, L.ptr(uniq), L.ptr(n_u), L.ptr(inv), L.ptr(ws), nbytes, L.stream()))
+    first = torch.empty(n, dtype=torch.int, device="cuda")
+    L.check(L.lib().lb_unique_i64(L.ptr(kd), n, 60, L.ptr(uniq), L.ptr(n_u), L.ptr(inv), L.ptr(first), L.ptr(ws), nbytes, L.stream()))
     want_u, want_inv = torch.unique(keys, return_inverse=True)
     assert int(n_u.item()) == want_u.numel()
     assert torch.equal(uniq[: want_u.numel()].cpu(), want_u) and torch.equal(inv.cpu().long(), want_inv)
+    _, np_first = np.unique(keys.numpy(), return_index=True)
+    assert np.array_equal(first[: want_u.numel()].cpu().numpy(), np_first)
     # fused corner query == sphash(offsets) + sphashquery + calc_ti_weights
     g = torch.Generator().manual_seed(0)
     pts = torch.cat([coords[:, :3].float() + torch.rand(coords.shape[0], 3, generator=g) * 0.97, coords[:, 3:].float()], 1)

@@ -77,3 +77,15 @@ def test_tta_tail_vs_oracle():
     # argmax may only differ where the top-2 probabilities are within float rounding of each other
     top2 = np.sort(want_p, 1)[:, -2:]
     assert (agree | (top2[:, 1] - top2[:, 0] < 1e-6)).all() and agree.mean() > 0.9999
+
+
+def test_gpu_voxelizer_matches_reference_transform():
+    """F1: device TTA views == dataset/sk_dataset.py:143-169 (restated in lidal_b200.synth.score_transform) with the same
+    RandomState: voxel coordinates, unique order, first-point rule and inverse indices bit-exact; features to 1 f32 ulp."""
+    from lidal_b200 import synth, voxelizer
+    raw = synth.raycast_scan(11, "NU")
+    want_c, want_f, want_inv = synth.tta_batch(raw, seed=5, inf_reps=3)
+    got_c, got_f, got_inv = voxelizer.tta_batch_gpu(torch.from_numpy(raw).cuda(), seed=5, inf_reps=3)
+    assert np.array_equal(got_c.cpu().numpy(), want_c)
+    assert np.array_equal(got_inv.cpu().numpy(), want_inv)
+    np.testing.assert_allclose(got_f.cpu().numpy(), want_f, rtol=2e-7, atol=1e-6)
