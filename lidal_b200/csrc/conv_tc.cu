@@ -190,7 +190,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   constexpr int ROWS_PER_PASS = NUM_PROD_THREADS / CHUNKS;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // align by OFFSET (not by integer round-trip of the pointer) so the compiler keeps the shared address space -> LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = p.c_out * ROW_BYTES;
   const int b_pad = (b_bytes + 1023) & ~1023;
   const int a_blk = T * A_BYTES;                        // A operand of one block: T sub-tiles of 128 rows
@@ -246,7 +247,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     // One block = 128 gathered rows x BK channels of one offset (+ its weight tile).  A stage carries up to p.nb
     // blocks; the slot is acquired at its first block and published (hardware arrive) after its last.
     int blk = 0, blk_goal = 0;                            // blocks issued / wanted in the open stage
-    auto issue = [&](int k, int cb, int b_col, int b_row, bool first, int remaining) {
+    constexpr int PASSES = TILE_M / ROWS_PER_PASS;
+    auto issue = [&](const int (&nbv)[T][PASSES], int cb, int b_col, int b_row, bool first, int remaining) {
       uint8_t* st_base = ring + (size_t)stage * stage_bytes;
       if (blk == 0) {
         blk_goal = remaining < p.nb ? remaining : p.nb;
@@ -261,18 +263,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       for (int sub = 0; sub < T; ++sub) {
         const uint32_t a_u32 = smem_u32(st_base + blk * a_blk + sub * A_BYTES);
 #pragma unroll
-        for (int i = 0; i < TILE_M / ROWS_PER_PASS; ++i) {
+        for (int i = 0; i < PASSES; ++i) {
           const int r = row0 + i * ROWS_PER_PASS;
-          int nb;
-          const char* src;
-          if (p.pack8) {                                  // chunk <-> offset 8*cb + chunk, 16 bytes = its 8 channels
-            const int kk = cb * 8 + chunk;
-            nb = kk < p.k_vol ? s_idx[kk * TM + sub * TILE_M + r] : -1;
-            src = p.in + (int64_t)(nb >= 0 ? nb : 0) * p.ld_in * 2;
-          } else {
-            nb = s_idx[k * TM + sub * TILE_M + r];
-            src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + cb * BK + chunk * 8) * 2;
-          }
+          const int nb = nbv[sub][i];
+          // pack8: 16 bytes = the 8 (padded) channels of one offset; otherwise channels [cb*BK + chunk*8, +8) of the row
+          const char* src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + (p.pack8 ? 0 : cb * BK + chunk * 8)) * 2;
           const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
           cp_async16(a_u32 + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
         }
@@ -319,16 +314,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       uint32_t mask = s_mask[par];
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
       if (tile + gridDim.x < num_tiles) fetch_indices(tile + gridDim.x);
+      int nbv[T][PASSES];                                 // neighbour rows of this thread's gather slots, one offset at a time
       if (p.pack8) {
         const int nkb = (p.k_vol * 8 + BK - 1) / BK;
-        for (int kb = 0; kb < nkb; ++kb) issue(0, kb, kb * BK, 0, kb == 0, nkb - kb);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int kk = kb * 8 + chunk;                  // chunk <-> offset 8*kb + chunk
+#pragma unroll
+          for (int sub = 0; sub < T; ++sub)
+#pragma unroll
+            for (int i = 0; i < PASSES; ++i)
+              nbv[sub][i] = kk < p.k_vol ? s_idx[kk * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS] : -1;
+          issue(nbv, kb, kb * BK, 0, kb == 0, nkb - kb);
+        }
       } else {
         int remaining = __popc(mask) * kc_blocks;
         bool first = true;
         for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
           if (!((mask >> k) & 1)) continue;
+#pragma unroll
+          for (int sub = 0; sub < T; ++sub)
+#pragma unroll
+            for (int i = 0; i < PASSES; ++i) nbv[sub][i] = s_idx[k * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS];
           for (int cb = 0; cb < kc_blocks; ++cb, --remaining, first = false)
-            issue(k, cb, cb * BK, k * p.c_out, first, remaining);
+            issue(nbv, cb, cb * BK, k * p.c_out, first, remaining);
         }
       }
     }
