@@ -379,6 +379,28 @@ __global__ void voxelize_ex_kernel(const TI* __restrict__ feats, int64_t ld_f_, 
     for (int j = lane; j < c; j += 32) atomicAdd(&out[(int64_t)v * c + j], ld_f<TI>(&feats[i * ld_f_ + j]) / fc);
   }
 }
+// c % 4 == 0, 16-byte aligned rows: one lane owns 4 channels -> one float4 atomic (sm_90+), or a plain 16-byte store when
+// the voxel holds a single point (no other writer exists for that row).
+template <typename TI>
+__global__ void voxelize_ex_vec4_kernel(const TI* __restrict__ feats, int64_t ld_f_, const int* __restrict__ idx,
+                                        const int* __restrict__ counts, int64_t n, int64_t m, int c, float* __restrict__ out) {
+  const int cpr = c >> 2;
+  const int64_t total = n * cpr;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / cpr;
+    const int j = (int)(t - i * cpr) * 4;
+    const int v = __ldg(&idx[i]);
+    if (v < 0 || v >= m) continue;
+    const int cnt = __ldg(&counts[v]);
+    if (cnt == 0) continue;
+    const float fc = (float)cnt;
+    const TI* f = &feats[i * ld_f_ + j];
+    const float4 val = make_float4(ld_f<TI>(f) / fc, ld_f<TI>(f + 1) / fc, ld_f<TI>(f + 2) / fc, ld_f<TI>(f + 3) / fc);
+    float4* dst = (float4*)&out[(int64_t)v * c + j];
+    if (cnt == 1) *dst = val;
+    else atomicAdd(dst, val);
+  }
+}
 template <typename TI, typename TO>
 __global__ void devoxelize_ex_kernel(const TI* __restrict__ feats, int64_t ld_f_, const int* __restrict__ idx,
                                      const float* __restrict__ w, int64_t n, int64_t m, int c, TO* __restrict__ out,
@@ -484,6 +506,16 @@ extern "C" int lb_voxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld
   if (n == 0 || m == 0) return LB_OK;
   LB_CHECK_ARG(ld_f >= c, "row stride smaller than the channel count");
   LB_CHECK_ARG(feats && idx && counts, "null pointer");
+  if (c % 4 == 0 && (((uintptr_t)out) & 15) == 0) {
+    const int64_t total = n * (c / 4), blocks = (total + 255) / 256, cap = (int64_t)sm_count() * 32;
+    const int g4 = (int)(blocks > cap ? cap : blocks);
+    if (feats_dtype == LB_DT_F32) { voxelize_ex_vec4_kernel<float><<<g4, 256, 0, st>>>((const float*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+    else if (feats_dtype == LB_DT_BF16) { voxelize_ex_vec4_kernel<__nv_bfloat16><<<g4, 256, 0, st>>>((const __nv_bfloat16*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+    else if (feats_dtype == LB_DT_F16) { voxelize_ex_vec4_kernel<__half><<<g4, 256, 0, st>>>((const __half*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+    else { set_error("lb_voxelize_fwd_ex: bad dtype"); return LB_EINVAL; }
+    LB_LAUNCH_CHECK();
+    return LB_OK;
+  }
   int g = rows_grid(n, 8);
   if (feats_dtype == LB_DT_F32) { voxelize_ex_kernel<float><<<g, 256, 0, st>>>((const float*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
   else if (feats_dtype == LB_DT_BF16) { voxelize_ex_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }

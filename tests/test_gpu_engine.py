@@ -178,3 +178,23 @@ def test_downsample_maps_equal_reference_maps_up_to_row_order(oracle_ts, small_s
         dn = torch.empty_like(dn_s.cpu())
         dn[:, perm.cpu().long()] = dn_s.cpu() if perm is not None else dn_s.cpu()
         assert torch.equal(dn[:, to_engine].long(), res)                          # child rows identical
+
+
+def test_voxelize_ex_vec4_matches_reference_kernel():
+    """float4-atomic / plain-store voxelize (engine) vs the scalar fp32 kernel: single-point and multi-point voxels."""
+    from lidal_b200 import _lib as L
+    import lidal_b200.compat as ts
+    F = ts.nn.functional
+    g = torch.Generator().manual_seed(1)
+    n, m = 30000, 4000
+    idx = torch.randint(-1, m, (n,), generator=g).int().cuda()
+    idx[:2000] = torch.arange(2000, dtype=torch.int).cuda() + m - 2000          # plenty of single-point voxels
+    idx[2000:][idx[2000:] >= m - 2000] = 5
+    counts = F.spcount(idx, m)
+    assert int((counts == 1).sum()) > 500 and int((counts > 4).sum()) > 500
+    for c in (4, 32, 256):
+        feats = torch.randn(n, c, generator=g).cuda().bfloat16()
+        out = torch.empty(m, c, dtype=torch.float32, device="cuda")
+        L.check(L.lib().lb_voxelize_fwd_ex(L.ptr(feats), L.LB_DT_BF16, c, L.ptr(idx), L.ptr(counts), n, m, c, L.ptr(out), L.stream()))
+        want = F.spvoxelize(feats.float(), idx, counts)
+        torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
