@@ -134,6 +134,7 @@ int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* 
                                 c_in == 8) and `weight` is [c_out][k_vol*8 -> padded to 64] with col = offset*8 + ch;
                                 8 offsets share one 64-wide K block of the tensor-core kernel               */
 #define LB_CONV_TILE128 16   /* force 128-row CTA tiles (default: 256-row tiles, two accumulators per weight tile, on large inputs) */
+#define LB_CONV_NO_STAGED_EPILOGUE 32 /* A/B switch: per-thread 16-byte epilogue stores instead of smem-staged bulk rows */
 #define LB_CONV_RELU_FIRST 4 /* with LB_CONV_RELU: relu(v*scale+shift) + residual (SPVCNN point branch)  */
 
 typedef struct lb_conv_args {

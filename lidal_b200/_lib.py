@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LIDAL_LIB") or os.path.join(HERE, "liblidal_b200.so")   # LIDAL_LIB: A/B kernel variants
 
 LB_DT_BF16, LB_DT_F16, LB_DT_F32 = 0, 1, 2
-LB_CONV_RELU, LB_CONV_FORCE_SIMT, LB_CONV_RELU_FIRST, LB_CONV_PACK8, LB_CONV_TILE128 = 1, 2, 4, 8, 16
+LB_CONV_RELU, LB_CONV_FORCE_SIMT, LB_CONV_RELU_FIRST, LB_CONV_PACK8, LB_CONV_TILE128, LB_CONV_NO_STAGED = 1, 2, 4, 8, 16, 32
 DT_OF = {torch.bfloat16: LB_DT_BF16, torch.float16: LB_DT_F16, torch.float32: LB_DT_F32}
 
 vp, i64, i32, sz, dbl, flt = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double, C.c_float

@@ -91,6 +91,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// 1-D bulk async copies (TMA engine, no tensor map): global row -> smem with mbarrier completion, smem row -> global
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -161,6 +174,7 @@ struct TcParams {
   int tmem_cols;
   int nb;                  // (offset, channel-block) blocks carried by one pipeline stage (1..4)
   int T;                   // 128-row sub-tiles per CTA tile (1 or 2): T accumulators share every weight tile
+  int staged;              // 1: smem-staged epilogue (per-row bulk async loads / stores), needs 16-bit output
   int n_acc;               // TMEM accumulator sets (2 = epilogue overlaps the next tile, 1 when 2*T*c_out > 512)
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
 };
@@ -209,6 +223,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   uint32_t* s_flags = (uint32_t*)(tempty_bar + 2);                 // [MAX_STAGES] bit0 = first k-block, bit1 = last
   uint32_t* s_tmem = s_flags + MAX_STAGES;                         // [1]
   uint32_t* s_mask = s_tmem + 1;                                   // [2] active-offset mask of the producers' tile (by parity)
+  uint64_t* res_bar = (uint64_t*)(s_mask + 2 + 1);                 // [4] residual rows landed (one per epilogue warp), 8-byte aligned
+  const int stg_pitch = p.c_out * 2 + 16;                          // staged epilogue: row pitch (+16 B: conflict-free 128-bit LDS)
+  uint8_t* s_stage = tail + (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 127) & ~(size_t)127);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out;
@@ -225,6 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       mbar_init(&full_bar[s], NUM_PROD_THREADS + 1);   // 128 gather threads + 1 expect_tx arrive for the TMA tile
       mbar_init(&empty_bar[s], 1);                     // released by tcgen05.commit
     }
+    for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], NUM_EPI_THREADS);   // every epilogue thread arrives once per tile
@@ -382,6 +400,89 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     }
   } else {
     // =============================================================== EPILOGUE (warps 0-3: TMEM lane quadrant = warp)
+    if (p.staged) {
+      // Shared-memory-staged epilogue: every lane owns one output row.  Its residual row arrives by ONE bulk async copy
+      // (completion on the warp's mbarrier), the row is finished in place in smem, and leaves by ONE bulk async store:
+      // global traffic is whole contiguous rows moved by the copy engine instead of 16-byte pieces per thread.
+      uint8_t* my_stage = s_stage + (size_t)warp * 32 * stg_pitch;
+      uint8_t* my_row = my_stage + (size_t)lane * stg_pitch;
+      const uint32_t row_bytes = (uint32_t)p.c_out * 2;
+      uint32_t res_ph = 0;
+      int64_t tcount = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = (int)(tcount % p.n_acc);
+        const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+        for (int sub = 0; sub < T; ++sub) {
+          const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
+          const bool live = o < n_out;
+          const int64_t orow = live ? (p.out_rows ? (int64_t)__ldg(&p.out_rows[o]) : o) : 0;
+          bulk_wait_read();                               // the previous stores have finished reading this staging buffer
+          __syncwarp();
+          if (p.residual) {
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            if (lane == 0) mbar_arrive_expect_tx(&res_bar[warp], row_bytes * (uint32_t)__popc(live_mask));
+            __syncwarp();
+            if (live) bulk_load(smem_u32(my_row), p.residual + orow * p.ld_res * 2, row_bytes, &res_bar[warp]);
+          }
+          if (sub == 0) {
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+          }
+          if (p.residual) {
+            mbar_wait(&res_bar[warp], res_ph);
+            res_ph ^= 1;
+          }
+          for (int c0 = 0; c0 < p.c_out; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+            if (p.relu == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4* chunk = (uint4*)(my_row + c0 * 2);
+            if (p.residual) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 rr = chunk[q];
+                const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (p.is_bf16) {
+                    f[q * 8 + 2 * j] += cvt_in<__nv_bfloat16>((uint16_t)(w[j] & 0xffff));
+                    f[q * 8 + 2 * j + 1] += cvt_in<__nv_bfloat16>((uint16_t)(w[j] >> 16));
+                  } else {
+                    f[q * 8 + 2 * j] += cvt_in<__half>((uint16_t)(w[j] & 0xffff));
+                    f[q * 8 + 2 * j + 1] += cvt_in<__half>((uint16_t)(w[j] >> 16));
+                  }
+                }
+              }
+            }
+            if (p.relu == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              w.x = pack2(f[q * 8], f[q * 8 + 1], p.is_bf16);
+              w.y = pack2(f[q * 8 + 2], f[q * 8 + 3], p.is_bf16);
+              w.z = pack2(f[q * 8 + 4], f[q * 8 + 5], p.is_bf16);
+              w.w = pack2(f[q * 8 + 6], f[q * 8 + 7], p.is_bf16);
+              chunk[q] = w;
+            }
+          }
+          fence_proxy_async();                            // my generic-proxy smem writes -> visible to the bulk-copy engine
+          if (live) bulk_store(p.out + orow * p.ld_out * 2, smem_u32(my_row), row_bytes);
+          bulk_commit();
+        }   // sub-tiles
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      }
+      bulk_wait_all();                                    // all rows are in global memory before the CTA retires
+    } else {
     int64_t tcount = 0;
     const int out_es = (p.out_dtype == LB_DT_F32) ? 4 : 2;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -448,6 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
+    }
   }
 
   // ---------------- teardown
@@ -489,8 +591,10 @@ int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
 }
 
 static size_t tail_bytes(int T) {
-  return (size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64;
+  // indices + scale/shift + ring/accumulator barriers + flags + (tmem ptr, masks, 4 residual barriers), rounded for staging
+  return (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 127) & ~(size_t)127);
 }
+static size_t staging_bytes(int c_out) { return (size_t)4 * 32 * (c_out * 2 + 16); }
 
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const bool pack8 = (a.flags & LB_CONV_PACK8) != 0;
@@ -550,13 +654,24 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   // a deep ring of single-block stages -- the kernel is bound by L2 traffic, not by the per-stage hand-shake.
   int nb = 1;
   const size_t stage_bytes = nb * block_bytes;
-  int stages = (int)(budget / stage_bytes);
+  // smem-staged epilogue (coalesced bulk row copies) when the output is 16-bit and the ring keeps enough stages:
+  // all blocks of a tile for short K loops (1x1 layers are pure epilogue), at least 5 stages otherwise
+  const int blocks_per_tile = pack8 ? (a.k_vol * 8 + bk - 1) / bk : a.k_vol * (a.c_in / bk);
+  const int want_stages = blocks_per_tile < 5 ? (blocks_per_tile < 3 ? 3 : blocks_per_tile) : 5;
+  p.staged = 0;
+  size_t budget_eff = budget;
+  if (a.out_dtype != LB_DT_F32 && !(a.flags & LB_CONV_NO_STAGED_EPILOGUE) && budget > staging_bytes(a.c_out) &&
+      (budget - staging_bytes(a.c_out)) / stage_bytes >= (size_t)want_stages) {
+    p.staged = 1;
+    budget_eff = budget - staging_bytes(a.c_out);
+  }
+  int stages = (int)(budget_eff / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { set_error("lb_conv_fwd: shared memory too small for the pipeline"); return LB_ECAP; }
   p.stages = stages;
   p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
-  const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + (p.staged ? staging_bytes(a.c_out) : 0) + 1024;
   int64_t tiles = (a.n_out + (int64_t)T * TILE_M - 1) / ((int64_t)T * TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;

@@ -84,7 +84,8 @@ class _Conv:
         a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
         a.act_dtype, a.out_dtype = L.DT_OF[x.dtype], L.DT_OF[out.dtype]
         a.flags = ((L.LB_CONV_RELU if self.relu else 0) | (L.LB_CONV_RELU_FIRST if relu_first else 0)
-                   | (L.LB_CONV_PACK8 if self.pack8 else 0) | (L.LB_CONV_TILE128 if FORCE_TILE128 else 0))
+                   | (L.LB_CONV_PACK8 if self.pack8 else 0) | (L.LB_CONV_TILE128 if FORCE_TILE128 else 0)
+                   | (L.LB_CONV_NO_STAGED if NO_STAGED else 0))
         trace = F.CONV_TRACE
         ev = trace.begin() if trace is not None else None
         L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
@@ -111,6 +112,7 @@ class _Res:
 _OFFSETS = {}
 import os as _os
 FORCE_TILE128 = bool(int(_os.environ.get('LIDAL_TILE128', '0')))   # A/B switch: 128-row CTA tiles everywhere
+NO_STAGED = bool(int(_os.environ.get('LIDAL_NO_STAGED', '0')))       # A/B switch: per-thread epilogue stores
 SORT_MAPS = True        # group rows by neighbour mask (tile-level offset skipping); False = natural row order
 
 
