@@ -230,18 +230,34 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
 
-    # ---- e2e: host buffers in, host logits out, every step
-    for i in range(2):
-        c, f = host[i % len(host)]
-        out_host[: c.shape[0]].copy_(run(c.to(dev, non_blocking=True), f.to(dev, non_blocking=True)), non_blocking=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        c, f = host[i % len(host)]
-        logits = run(c.to(dev, non_blocking=True), f.to(dev, non_blocking=True))
-        out_host[: c.shape[0]].copy_(logits, non_blocking=True)
-    e1.record()
-    barrier()
+    # ---- e2e: host buffers in, host logits out, every step (through the public host-buffer API)
+    if eng is not None:
+        from lidal_b200.engine import HostPipeline
+        pipe = HostPipeline(eng)
+        for i in range(6):                                        # warm-up: allocates the pinned output ring
+            pipe.submit(*host[i % len(host)])
+        pipe.collect()
+        barrier()
+        e0.record()
+        n_done = 0
+        for i in range(args.steps):
+            n_done += len(pipe.submit(*host[i % len(host)]))      # H2D (pinned) + forward + D2H of the logits, pipelined
+        n_done += len(pipe.collect())
+        e1.record()
+        barrier()
+        assert n_done == args.steps
+    else:
+        for i in range(2):
+            c, f = host[i % len(host)]
+            out_host[: c.shape[0]].copy_(run(c.to(dev, non_blocking=True), f.to(dev, non_blocking=True)), non_blocking=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            c, f = host[i % len(host)]
+            logits = run(c.to(dev, non_blocking=True), f.to(dev, non_blocking=True))
+            out_host[: c.shape[0]].copy_(logits, non_blocking=True)
+        e1.record()
+        barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)

@@ -343,3 +343,68 @@ class InferenceEngine:
         z3 = self.mlp[2](z2, None, z2.shape[0], residual=self._devox(y, iq0, w0), relu_first=True)   # [Np, 96]
         logits = self.classifier(z3, None, z3.shape[0], out_dtype=torch.float32)
         return logits[:, : self.n_cls]
+
+
+class HostPipeline:
+    """Host-buffer front end of the engine: ``submit(coords_host, feats_host)`` / ``collect()``.
+
+    The reference's loop (score/prob_inference.py:94-100) does ``.cuda()`` -> model -> ``.cpu()`` serially.  Here the H2D
+    copy of batch i+1 and the D2H copy of logits i-1 run on a copy stream while batch i computes, so PCIe traffic hides
+    behind the kernels.  Inputs must be pinned for the copies to be asynchronous; outputs land in pinned buffers.
+    """
+
+    def __init__(self, engine: "InferenceEngine", depth: int = 2):
+        self.engine = engine
+        self.copy_stream = torch.cuda.Stream(device=engine.device)
+        self.depth = depth
+        self.pending = []          # (logits_dev, out_host, done_event)
+        self._out_pool = {}
+        self._n_submitted = 0
+
+    def _out_buffer(self, shape, slot):
+        key = (slot, shape[1])
+        buf = self._out_pool.get(key)
+        if buf is None or buf.shape[0] < shape[0]:
+            buf = torch.empty((int(shape[0] * 1.25) + 1, shape[1]), dtype=torch.float32).pin_memory()
+            self._out_pool[key] = buf
+        return buf[: shape[0]]
+
+    def submit(self, coords_host: torch.Tensor, feats_host: torch.Tensor):
+        """Queue one batch (host tensors).  Returns immediately; results come back in order from ``collect``."""
+        dev = self.engine.device
+        with torch.cuda.stream(self.copy_stream):
+            c = coords_host.to(dev, non_blocking=True)
+            f = feats_host.to(dev, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready)
+        logits = self.engine(c, f)
+        c.record_stream(cur); f.record_stream(cur)
+        computed = torch.cuda.Event()
+        computed.record(cur)
+        out = self._out_buffer(logits.shape, self._n_submitted % (self.depth + 2))   # ring: never a buffer still in flight
+        self._n_submitted += 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(computed)
+            out.copy_(logits, non_blocking=True)
+            logits.record_stream(self.copy_stream)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        self.pending.append((out, done))
+        results = []
+        while len(self.pending) > self.depth:
+            results.append(self._pop())
+        return results
+
+    def _pop(self):
+        out, done = self.pending.pop(0)
+        done.synchronize()
+        return out
+
+    def collect(self):
+        """Wait for and return all outstanding results (host float32 [N, n_cls] tensors, pinned; valid until reused)."""
+        results = []
+        while self.pending:
+            results.append(self._pop())
+        return results
