@@ -264,6 +264,12 @@ size_t lb_region_pairs_ws_bytes(int64_t n);
 int lb_region_pairs(const float* centers, int64_t n, float radius, int32_t* row, int32_t* nbr_idx, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* Frame-level baselines on the same prob maps (score/frame_level/softmax_entropy.py:34,
+ * margin_sampling.py:33-34, least_confidence_sampling.py): out3 (device double[3]) = mean entropy(prob), mean
+ * (top1 - top2), mean top1 over the n points of one frame. */
+size_t lb_frame_level_ws_bytes(void);
+int lb_frame_level_scores(const float* prob, int64_t n, int n_cls, double* out3, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,8 @@ SIGNATURES = {
     "lb_frame_grid_ws_bytes": (sz, [i64]),
     "lb_frame_grid_build": (i32, [vp, i64, dbl, vp, sz, vp, sz, vp]),
     "lb_interframe_score": (i32, [vp, vp, i64, i32, C.POINTER(FrameRef), i32, dbl, dbl, vp, vp, vp, vp, vp]),
+    "lb_frame_level_ws_bytes": (sz, []),
+    "lb_frame_level_scores": (i32, [vp, i64, i32, vp, vp, sz, vp]),
     "lb_region_reduce": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     "lb_argsort_ws_bytes": (sz, [i64]),
     "lb_argsort_f32": (i32, [vp, i64, vp, vp, sz, vp]),

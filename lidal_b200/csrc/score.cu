@@ -442,3 +442,66 @@ extern "C" int lb_region_pairs(const float* centers, int64_t n, float radius, in
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+
+// ---------------------------------------------------------------------------------------- frame-level baselines (F3)
+// score/frame_level/{softmax_entropy.py:34, margin_sampling.py:33-34, least_confidence_sampling.py}: three per-frame means
+// over the points of one prob map: entropy(prob) (scipy: renormalise, entr in double -> float, float pairwise sum),
+// top1 - top2, top1.  One warp per point, lane = class; fixed-order block partials -> deterministic.
+namespace lb {
+__global__ void __launch_bounds__(256)
+frame_level_kernel(const float* __restrict__ prob, int64_t n, int n_cls, double* __restrict__ partial /*[grid,3]*/) {
+  __shared__ double sh[3][8];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double acc_e = 0, acc_m = 0, acc_c = 0;
+  for (int64_t p = warp; p < n; p += nwarps) {
+    const float x = lane < n_cls ? __ldg(&prob[p * n_cls + lane]) : 0.f;
+    float s = np_pairwise_sum32(x, n_cls, lane);
+    s = __shfl_sync(full, s, 0);
+    const float pk = __fdiv_rn(x, s);
+    float en = 0.f;
+    if (lane < n_cls) {
+      const double pd = (double)pk;
+      en = pd > 0.0 ? (float)__dmul_rn(-pd, log(pd)) : (pd == 0.0 ? 0.f : -INFINITY);
+    }
+    const float H = np_pairwise_sum32(en, n_cls, lane);
+    float v1 = lane < n_cls ? x : -INFINITY;              // top-1
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v1 = fmaxf(v1, __shfl_xor_sync(full, v1, d));
+    const unsigned at_max = __ballot_sync(full, lane < n_cls && x == v1);
+    const int first = __ffs(at_max) - 1;
+    float v2 = (lane < n_cls && lane != first) ? x : -INFINITY;   // top-2 (duplicates of the max count, as np.sort gives)
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v2 = fmaxf(v2, __shfl_xor_sync(full, v2, d));
+    if (lane == 0) { acc_e += (double)H; acc_m += (double)__fsub_rn(v1, v2); acc_c += (double)v1; }
+  }
+  if (lane == 0) { sh[0][w] = acc_e; sh[1][w] = acc_m; sh[2][w] = acc_c; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += sh[threadIdx.x][i];
+    partial[(int64_t)blockIdx.x * 3 + threadIdx.x] = t;
+  }
+}
+__global__ void frame_level_final(const double* __restrict__ partial, int blocks, int64_t n, double* __restrict__ out) {
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int b = 0; b < blocks; ++b) t += partial[(int64_t)b * 3 + threadIdx.x];
+    out[threadIdx.x] = n > 0 ? t / (double)n : 0.0;
+  }
+}
+}  // namespace lb
+extern "C" size_t lb_frame_level_ws_bytes(void) { return (size_t)sm_count() * 8 * 3 * 8 + 64; }
+extern "C" int lb_frame_level_scores(const float* prob, int64_t n, int n_cls, double* out3, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  LB_CHECK_ARG(n >= 0 && n_cls > 1 && n_cls <= 32 && out3 && ws, "bad arguments");
+  if (ws_bytes < lb_frame_level_ws_bytes()) { set_error("lb_frame_level_scores: workspace too small"); return LB_ECAP; }
+  LB_CHECK_ARG(prob || n == 0, "null prob");
+  const int blocks = sm_count() * 8;
+  frame_level_kernel<<<blocks, 256, 0, as_stream(stream)>>>(prob, n, n_cls, (double*)ws); LB_LAUNCHED(1);
+  frame_level_final<<<1, 32, 0, as_stream(stream)>>>((const double*)ws, blocks, n, out3); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

@@ -166,6 +166,20 @@ def worker_func(id):
     return var_dict["scorer"].score_frame(int(id), var_dict["sv_pre"])
 
 
+# ------------------------------------------------------------------------------------------- frame-level baselines
+def frame_level_scores(prob: torch.Tensor):
+    """(softmax-entropy, margin, least-confidence) frame scores of one prob map f32 [Np, C] on device
+    (score/frame_level/softmax_entropy.py:34, margin_sampling.py:33-34, least_confidence_sampling.py)."""
+    L.require_cuda(prob)
+    prob = prob.contiguous().float()
+    out = torch.empty(3, dtype=torch.float64, device=prob.device)
+    nbytes = L.lib().lb_frame_level_ws_bytes()
+    ws = _ws(nbytes, prob.device)
+    L.check(L.lib().lb_frame_level_scores(L.ptr(prob), prob.shape[0], prob.shape[1], L.ptr(out), L.ptr(ws), nbytes, L.stream()))
+    ent, mar, conf = out.cpu().tolist()
+    return ent, mar, conf
+
+
 # ------------------------------------------------------------------------------------------- selection
 def argsort_f32(keys: torch.Tensor) -> torch.Tensor:
     L.require_cuda(keys)

@@ -107,3 +107,19 @@ def test_argsort_and_region_pairs_vs_numpy():
         dist = np.sqrt(np.square(c[i] - c).sum(1, dtype=np.float32))
         want = np.where((dist < np.float32(5.0)) & (np.arange(4000) != i))[0]
         assert np.array_equal(np.sort(idx[ptr[i]:ptr[i + 1]]), want)
+
+
+def test_frame_level_baselines_vs_reference_formulas():
+    """F3: softmax entropy / margin / least confidence frame scores vs the reference's numpy expressions."""
+    from scipy.stats import entropy
+    from lidal_b200 import score, synth
+    rng = np.random.default_rng(3)
+    for n_cls in (19, 16):
+        xyz = rng.random((50000, 3)) * 40
+        prob = synth.synthetic_probs(xyz, n_cls, 7)
+        prob[::97, 3] = prob[::97, 5]                      # exact top-2 ties
+        ent, mar, conf = score.frame_level_scores(torch.from_numpy(prob).cuda())
+        srt = np.sort(prob, axis=-1)
+        np.testing.assert_allclose(ent, np.mean(entropy(prob, axis=1)), rtol=1e-5)
+        np.testing.assert_allclose(mar, np.mean(srt[:, -1] - srt[:, -2]), rtol=1e-5)
+        np.testing.assert_allclose(conf, np.mean(srt[:, -1]), rtol=1e-5)
