@@ -7,6 +7,7 @@ hand-written sm_100a kernels on the current CUDA stream.  CUDA tensors only.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -229,6 +230,22 @@ def build_kernel_map(coords, in_stride, kernel_size, stride, dilation) -> Kernel
 
 
 # ------------------------------------------------------------------------------------------- convolution
+_PACKED = weakref.WeakKeyDictionary()       # Parameter -> (version, dtype, packed weight): repack only after an update
+
+
+def packed_weight_cached(kernel, dtype):
+    """Packed weight of an nn.Parameter, re-packed only when the parameter was modified (optimizer step, load_state_dict)."""
+    try:
+        hit = _PACKED.get(kernel)
+    except TypeError:
+        return pack_weight(kernel, dtype)
+    if hit is not None and hit[0] == kernel._version and hit[1] == dtype and hit[2].device == kernel.device:
+        return hit[2]
+    packed = pack_weight(kernel, dtype)
+    _PACKED[kernel] = (kernel._version, dtype, packed)
+    return packed
+
+
 def pack_weight(kernel, dtype):
     """fp32 [K, Cin, Cout] (or [Cin, Cout]) -> 16-bit [K, Cout, Cin] for the implicit GEMM."""
     w = kernel.detach().contiguous().float()
@@ -285,7 +302,7 @@ class _ConvFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, feats, kernel, nbr, n_out, kmap, transposed):
-        w = pack_weight(kernel, ACT_DTYPE)
+        w = packed_weight_cached(kernel, ACT_DTYPE)
         x16 = _to16(feats.float(), ACT_DTYPE)
         out = conv_forward(x16, w, nbr, n_out)
         ctx.save_for_backward(feats, kernel)

@@ -53,3 +53,25 @@ def test_argument_validation_without_gpu():
     a = _lib.ConvArgs()
     a.n_out = 5
     assert L.lb_conv_fwd(ctypes.byref(a), None) == -1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/network"), reason="reference checkout only exists in the build container")
+def test_install_lets_the_unmodified_reference_networks_import():
+    """Drop-in check for boundary B1: after compat.install() the reference's own network/minkunet.py and network/spvcnn.py
+    import `torchsparse` from this package, construct, and expose exactly the golden state_dict keys / shapes."""
+    import importlib
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path[:0] = [%r, '/root/reference'];"
+        "import lidal_b200.compat as c; c.install();"
+        "import torchsparse, torchsparse.nn as spnn; assert torchsparse is c and spnn.Conv3d is c.nn.Conv3d;"
+        "from network.minkunet import MinkUNet; from network.spvcnn import SPVCNN;"
+        "g = np.load(%r, allow_pickle=True);"
+        "m = MinkUNet(19); s = SPVCNN(16);"
+        "assert [f'{k}:{tuple(v.shape)}' for k, v in m.state_dict().items()] == list(g['minkunet_keys']);"
+        "assert [f'{k}:{tuple(v.shape)}' for k, v in s.state_dict().items()] == list(g['spvcnn_keys']);"
+        "import torch.nn as nn; assert isinstance(m.stem[1], nn.BatchNorm1d); print('ok')"
+    ) % (ROOT, os.path.join(ROOT, "tests", "golden", "nets.npz"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
