@@ -164,6 +164,15 @@ int lb_conv_fwd(const lb_conv_args* args /*[host]*/, void* stream);
 /* which kernel lb_conv_fwd would run for this shape: 1 = tcgen05 implicit GEMM, 0 = CUDA-core. */
 int lb_conv_uses_tensor_cores(int k_vol, int c_in, int c_out, int act_dtype);
 
+/* Weight gradient (training; replaces the wgrad half of torchsparse.backend.convolution_backward_cuda, reached from
+ * loss.backward() at train.py:137):  grad_kernel[k][ci][co] = sum over pairs (i, o) of offset k  x[i][ci] * g[o][co].
+ * x [n_x, ld_x], g [n_g, ld_g] 16-bit; pairs device int32 [M,2] = (x_row, g_row) grouped by offset (the compacted
+ * kernel map; swap the columns for a transposed conv); pair_begin [host] int32 [k_vol+1] prefix offsets;
+ * grad_kernel fp32 [k_vol, c_in, c_out] (the `kernel` parameter layout), zeroed inside.  tcgen05 with MN-major gathered
+ * operands, split-K over pair tiles, fp32 atomics (summation order not deterministic).  c_in % 8 == 0, c_out % 32 == 0. */
+int lb_conv_wgrad(const void* x, int64_t n_x, int64_t ld_x, const void* g, int64_t n_g, int64_t ld_g, const int32_t* pairs,
+                  const int32_t* pair_begin, int k_vol, int c_in, int c_out, int act_dtype, float* grad_kernel, void* stream);
+
 /* fp32 <-> 16-bit row-strided casts used at the fp32 torchsparse boundary. */
 int lb_cast(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows,
             int64_t cols, void* stream);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "lb_sort_pairs": (i32, [vp, vp, i64, i32, vp, sz, vp]),
     "lb_conv_pack_weight": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "lb_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
+    "lb_conv_wgrad": (i32, [vp, i64, i64, vp, i64, i64, vp, C.POINTER(i32), i32, i32, i32, i32, vp, vp]),
     "lb_conv_uses_tensor_cores": (i32, [i32, i32, i32, i32]),
     "lb_cast": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, vp]),
     "lb_count": (i32, [vp, i64, vp, i64, vp]),

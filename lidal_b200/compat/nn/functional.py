@@ -298,7 +298,7 @@ def _to16(x, dtype):
 
 class _ConvFunction(torch.autograd.Function):
     """Forward on the implicit-GEMM kernel; dgrad reuses it with swapped map roles and W^T; wgrad is one
-    gathered [Cin, M_k] x [M_k, Cout] contraction per offset."""
+    tcgen05 split-K contraction over the map pairs (lb_conv_wgrad)."""
 
     @staticmethod
     def forward(ctx, feats, kernel, nbr, n_out, kmap, transposed):
@@ -328,8 +328,39 @@ class _ConvFunction(torch.autograd.Function):
 
 
 def _wgrad(feats, g, kmap, transposed, wshape):
-    # TODO(round 2): fused split-K wgrad kernel; the per-offset contraction below is host-orchestrated.
-    gw = torch.zeros(wshape, dtype=torch.float32, device=feats.device)
+    """grad of the `kernel` parameter [K, Cin, Cout].  Tensor-core kernel (lb_conv_wgrad) whenever Cout % 32 == 0; the
+    input is zero-padded to a multiple of 8 channels if needed.  Other shapes use one gathered GEMM per offset."""
+    k_vol, cin, cout = wshape
+    dev = feats.device
+    if cout % 32 == 0 and cout <= 256 and k_vol <= 27:
+        if kmap is None:
+            idx = torch.arange(feats.shape[0], dtype=torch.int, device=dev)
+            pairs = torch.stack([idx, idx], 1).contiguous()
+            begin = [0, feats.shape[0]]
+        else:
+            pairs = kmap.nbmaps                                             # (in_idx, out_idx), offset-major
+            if transposed:
+                pairs = pairs[:, [1, 0]]
+            pairs = pairs.contiguous()
+            sizes = kmap.nbsizes.tolist()
+            begin = [0]
+            for n in sizes:
+                begin.append(begin[-1] + n)
+        cin_p = (cin + 7) // 8 * 8
+        x16 = torch.zeros((feats.shape[0], cin_p), dtype=ACT_DTYPE, device=dev) if cin_p != cin else None
+        if x16 is None:
+            x16 = _to16(feats.float(), ACT_DTYPE)
+        else:
+            f32 = feats.float().contiguous()
+            L.check(L.lib().lb_cast(L.ptr(f32), L.LB_DT_F32, f32.stride(0), L.ptr(x16), L.DT_OF[ACT_DTYPE], cin_p,
+                                    f32.shape[0], cin, L.stream()))
+        g16 = _to16(g.float(), ACT_DTYPE)
+        gw = torch.empty((k_vol, cin_p, cout), dtype=torch.float32, device=dev)
+        pb = (C.c_int * len(begin))(*begin)
+        L.check(L.lib().lb_conv_wgrad(L.ptr(x16), x16.shape[0], x16.stride(0), L.ptr(g16), g16.shape[0], g16.stride(0),
+                                      L.ptr(pairs), pb, k_vol, cin_p, cout, L.DT_OF[ACT_DTYPE], L.ptr(gw), L.stream()))
+        return gw[:, :cin, :] if cin_p != cin else gw
+    gw = torch.zeros(wshape, dtype=torch.float32, device=dev)
     if kmap is None:
         gw[0] = feats.float().t() @ g.float()
         return gw

@@ -159,3 +159,32 @@ def test_tensor_core_path_matches_simt(ts, small_scan, cin, cout, k3):
     a = F.conv_forward(xh, wh, nbr, n)
     b = F.conv_forward(xh, wh, nbr, n, force_simt=True)
     torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("cin,cout,ks,stride,transposed", [
+    (32, 64, 3, 1, False), (4, 32, 3, 1, False), (96, 96, 3, 1, False), (64, 64, 2, 2, False), (64, 96, 2, 2, True),
+    (192, 128, 1, 1, False), (256, 256, 3, 1, False)])
+def test_conv_backward_shapes_vs_oracle(ts, oracle_ts, small_scan, cin, cout, ks, stride, transposed):
+    """dgrad (forward kernel with swapped map roles) and wgrad (tcgen05 split-K kernel) against the oracle's autograd."""
+    coords, _ = _sparse_input(oracle_ts, small_scan, 4)
+    g = torch.Generator().manual_seed(cin + cout)
+    if transposed:
+        # build the stride-2 map first, then run the transposed conv from the coarse level back to the fine one
+        down_o = oracle_ts.nn.Conv3d(cin, cin, kernel_size=2, stride=2)
+        down_g = ts.nn.Conv3d(cin, cin, kernel_size=2, stride=2).cuda()
+        down_g.load_state_dict(down_o.state_dict())
+    conv_o = oracle_ts.nn.Conv3d(cin, cout, kernel_size=ks, stride=stride, transposed=transposed)
+    conv_g = ts.nn.Conv3d(cin, cout, kernel_size=ks, stride=stride, transposed=transposed).cuda()
+    conv_g.load_state_dict(conv_o.state_dict())
+    feats = torch.randn(coords.shape[0], cin, generator=g)
+    xo = oracle_ts.SparseTensor(feats.clone().requires_grad_(True), coords); xo.cmaps[xo.stride] = xo.coords
+    xg = ts.SparseTensor(feats.clone().cuda().requires_grad_(True), coords.cuda()); xg.cmaps[xg.stride] = xg.coords
+    fo, fg = xo.F, xg.F
+    if transposed:
+        xo, xg = down_o(xo), down_g(xg)
+    yo, yg = conv_o(xo), conv_g(xg)
+    go = torch.randn(yo.F.shape, generator=g)
+    yo.F.backward(go)
+    yg.F.backward(go.cuda())
+    assert rel_err(conv_g.kernel.grad.cpu(), conv_o.kernel.grad)[1] < REL_TOL
+    assert rel_err(fg.grad.cpu(), fo.grad)[1] < 2 * REL_TOL
