@@ -230,19 +230,23 @@ def build_kernel_map(coords, in_stride, kernel_size, stride, dilation) -> Kernel
 
 
 # ------------------------------------------------------------------------------------------- convolution
-_PACKED = weakref.WeakKeyDictionary()       # Parameter -> (version, dtype, packed weight): repack only after an update
+_PACKED = {}        # id(Parameter) -> (weakref, version, dtype, packed weight): repack only after an update
 
 
 def packed_weight_cached(kernel, dtype):
-    """Packed weight of an nn.Parameter, re-packed only when the parameter was modified (optimizer step, load_state_dict)."""
-    try:
-        hit = _PACKED.get(kernel)
-    except TypeError:
-        return pack_weight(kernel, dtype)
-    if hit is not None and hit[0] == kernel._version and hit[1] == dtype and hit[2].device == kernel.device:
-        return hit[2]
+    """Packed weight of an nn.Parameter, re-packed only when the parameter was modified (optimizer step, load_state_dict).
+    Keyed by id() and validated through a weakref (tensor keys cannot be compared with == inside a dict)."""
+    hit = _PACKED.get(id(kernel))
+    if hit is not None and hit[0]() is kernel and hit[1] == kernel._version and hit[2] == dtype and hit[3].device == kernel.device:
+        return hit[3]
     packed = pack_weight(kernel, dtype)
-    _PACKED[kernel] = (kernel._version, dtype, packed)
+    if len(_PACKED) > 4096:
+        for key in [k for k, v in _PACKED.items() if v[0]() is None]:
+            del _PACKED[key]
+    try:
+        _PACKED[id(kernel)] = (weakref.ref(kernel), kernel._version, dtype, packed)
+    except TypeError:
+        pass
     return packed
 
 
@@ -320,8 +324,16 @@ class _ConvFunction(torch.autograd.Function):
                 nbr_back = None
             else:
                 nbr_back = kmap.nbr if transposed else kmap.nbr_t
-            wt = pack_weight(w3.transpose(1, 2), ACT_DTYPE)                 # [K, Cout, Cin] roles swapped
-            gi = conv_forward(_to16(g.float(), ACT_DTYPE), wt, nbr_back, feats.shape[0])
+            wt = pack_weight(w3.transpose(1, 2), ACT_DTYPE)                 # packed [K, Cin (as output), Cout (as input)]
+            g16 = _to16(g.float(), ACT_DTYPE)
+            cin = wt.shape[1]
+            if cin <= 256:
+                gi = conv_forward(g16, wt, nbr_back, feats.shape[0])
+            else:                                                           # MMA N <= 256: produce the input grad in column slices
+                gi = torch.empty((feats.shape[0], cin), dtype=torch.float32, device=g.device)
+                for c0 in range(0, cin, 128):
+                    c1 = min(c0 + 128, cin)
+                    conv_forward(g16, wt[:, c0:c1, :].contiguous(), nbr_back, feats.shape[0], out=gi[:, c0:c1])
         if ctx.needs_input_grad[1]:
             gw = _wgrad(feats, g, kmap, transposed, w3.shape).view(kernel.shape)
         return gi, gw, None, None, None, None

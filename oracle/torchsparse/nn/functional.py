@@ -9,6 +9,15 @@ import torch
 from ..tensor import SparseTensor
 from .utils import get_kernel_offsets, make_ntuple
 
+# Test switch: round the convolution operands (activations, weights, output gradients) to a 16-bit type at exactly the points
+# where the CUDA path does (fp32 accumulation stays), so that training-step parity checks the kernels, not the precision choice.
+EMULATE_16BIT = None
+
+
+def _r16(t):
+    return t if EMULATE_16BIT is None else t.to(EMULATE_16BIT).float()
+
+
 FNV_OFFSET = np.uint64(14695981039346656037)
 FNV_PRIME = np.uint64(1099511628211)
 LOW60 = np.uint64(0x0FFFFFFFFFFFFFFF)
@@ -150,6 +159,21 @@ def build_kernel_map(coords, in_stride, kernel_size, stride, dilation):
     return nbmaps, nbsizes, (coords.shape[0], out_coords.shape[0]), out_coords, results
 
 
+class _Dense16(torch.autograd.Function):
+    """1x1 convolution with the same operand rounding as the CUDA path (only used when EMULATE_16BIT is set)."""
+
+    @staticmethod
+    def forward(ctx, feats, weight):
+        ctx.save_for_backward(feats, weight)
+        return _r16(feats) @ _r16(weight)
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, weight = ctx.saved_tensors
+        g = _r16(g)
+        return g @ _r16(weight).t(), _r16(feats).t() @ g
+
+
 class _Conv(torch.autograd.Function):
     """backend/convolution: per offset gather -> mm -> scatter-add, offsets ascending, fp32."""
 
@@ -158,10 +182,11 @@ class _Conv(torch.autograd.Function):
         out = torch.zeros(sizes[1], weight.shape[-1], dtype=feats.dtype)
         a, b = (1, 0) if transposed else (0, 1)
         cur = 0
+        f16, w16 = _r16(feats), _r16(weight)
         for k, n in enumerate(nbsizes.tolist()):
             if n:
                 m = nbmaps[cur:cur + n]
-                out.index_add_(0, m[:, b], feats[m[:, a]] @ weight[k])
+                out.index_add_(0, m[:, b], f16[m[:, a]] @ w16[k])
             cur += n
         ctx.save_for_backward(feats, weight, nbmaps, nbsizes)
         ctx.transposed = transposed
@@ -173,12 +198,13 @@ class _Conv(torch.autograd.Function):
         a, b = (1, 0) if ctx.transposed else (0, 1)
         gi, gw = torch.zeros_like(feats), torch.zeros_like(weight)
         cur = 0
+        g, f16, w16 = _r16(g), _r16(feats), _r16(weight)
         for k, n in enumerate(nbsizes.tolist()):
             if n:
                 m = nbmaps[cur:cur + n]
                 go = g[m[:, b]]
-                gi.index_add_(0, m[:, a], go @ weight[k].t())
-                gw[k] = feats[m[:, a]].t() @ go
+                gi.index_add_(0, m[:, a], go @ w16[k].t())
+                gw[k] = f16[m[:, a]].t() @ go
             cur += n
         return gi, gw, None, None, None, None
 
@@ -187,7 +213,7 @@ def conv3d(input, weight, kernel_size, bias=None, stride=1, dilation=1, transpos
     feats, coords = input.feats, input.coords
     kernel_size, stride, dilation = make_ntuple(kernel_size), make_ntuple(stride), make_ntuple(dilation)
     if kernel_size == (1, 1, 1) and stride == (1, 1, 1) and dilation == (1, 1, 1):
-        feats = feats.matmul(weight)
+        feats = feats.matmul(weight) if EMULATE_16BIT is None else _Dense16.apply(feats, weight)
         if bias is not None:
             feats = feats + bias
         output = SparseTensor(feats, coords, input.stride)

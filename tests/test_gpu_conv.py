@@ -188,3 +188,45 @@ def test_conv_backward_shapes_vs_oracle(ts, oracle_ts, small_scan, cin, cout, ks
     yg.F.backward(go.cuda())
     assert rel_err(conv_g.kernel.grad.cpu(), conv_o.kernel.grad)[1] < REL_TOL
     assert rel_err(fg.grad.cpu(), fo.grad)[1] < 2 * REL_TOL
+
+
+def test_minkunet_training_step_vs_oracle(ts, oracle_ts, small_scan):
+    """Config 4 path: one MinkUNet fwd + cross-entropy + bwd through the drop-in layer (train-mode BatchNorm, tcgen05
+    fwd / dgrad / wgrad).  Two checks: (1) against the oracle with operands rounded to bf16 at the same points
+    (oracle EMULATE_16BIT) -- verifies the kernels; (2) against the pure fp32 oracle -- bounds the precision choice
+    (measured: gradient cosine ~0.91-0.93 with bf16 operands, ~0.99 with fp16, on this 5.5k-voxel random-label case)."""
+    from lidal_b200.network import MinkUNet, seeded_state_dict
+    Fo = oracle_ts.nn.functional
+    coords, feats, _ = small_scan
+    sel = np.arange(coords.shape[0]) % 3 == 0                      # keep the CPU oracle backward quick
+    coords, feats = np.ascontiguousarray(coords[sel]), np.ascontiguousarray(feats[sel])
+    labels = torch.from_numpy(np.random.default_rng(0).integers(0, 19, coords.shape[0]))
+    labels[::11] = 255
+
+    def run(be, dev):
+        model = MinkUNet(19, be)
+        model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
+        model = model.to(dev).train()
+        logits, _ = model(be.SparseTensor(torch.from_numpy(feats).to(dev), torch.from_numpy(coords).to(dev)))
+        loss = torch.nn.functional.cross_entropy(logits, labels.to(dev), ignore_index=255)
+        loss.backward()
+        return float(loss), {k: p.grad.detach().cpu().double() for k, p in model.named_parameters() if k.endswith("kernel")}
+
+    loss_g, grad_g = run(ts, "cuda")
+    loss_32, grad_32 = run(oracle_ts, "cpu")
+    try:
+        Fo.EMULATE_16BIT = torch.bfloat16
+        loss_16, grad_16 = run(oracle_ts, "cpu")
+    finally:
+        Fo.EMULATE_16BIT = None
+    assert abs(loss_g - loss_16) / abs(loss_16) < 2e-3 and abs(loss_g - loss_32) / abs(loss_32) < 2e-2
+    err16 = {k: float((grad_g[k] - grad_16[k]).norm() / grad_16[k].norm()) for k in grad_16}
+    cos32 = {k: float((grad_g[k] * grad_32[k]).sum() / (grad_g[k].norm() * grad_32[k].norm())) for k in grad_32}
+    print("vs bf16-emulating oracle: median rel-L2 %.3e, worst %.3e" % (np.median(list(err16.values())), max(err16.values())))
+    print("vs fp32 oracle: min cosine %.4f" % min(cos32.values()))
+    # Per-layer fwd/dgrad/wgrad are checked at 1e-2 above.  Through the whole train-mode network two bf16 computations
+    # decorrelate: activations agree to 6e-10 at the first conv and ~1e-2 at the last (rounding flips), and softmax + BN
+    # batch-statistics backward amplify that to 5 % at the last layer's gradient, growing smoothly to ~30 % at depth
+    # (tools/debug_train_grad.py prints the table; no layer type stands out).  Bound the drift, not bit parity.
+    assert np.median(list(err16.values())) < 0.35 and max(err16.values()) < 0.5, sorted(err16.items(), key=lambda kv: -kv[1])[:3]
+    assert min(cos32.values()) > 0.85
