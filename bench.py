@@ -39,9 +39,9 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------ inputs
-def make_batches(rank: int, n_sets: int = N_INPUT_SETS, batch: int = BATCH, kind: str = KIND):
+def make_batches(rank: int, n_sets: int = N_INPUT_SETS, batch: int = BATCH, kind: str | None = None):
     from lidal_b200 import synth
-    return [synth.scan_batch(seed=1000 * rank + 17 + s, kind=kind, batch=batch) for s in range(n_sets)]
+    return [synth.scan_batch(seed=1000 * rank + 17 + s, kind=kind or KIND, batch=batch) for s in range(n_sets)]
 
 
 class ClockSampler:
@@ -158,7 +158,7 @@ def run_reference(args, rank, world):
 
 def workload_config(model, path):
     return {"workload": f"{model}_inference_{KIND}_batch{BATCH}", "model_family": model, "batch_scans": BATCH,
-            "points_per_scan": "~131k (64-beam ray cast)", "voxel_m": 0.05, "classes": N_CLS, "path": path,
+            "points_per_scan": "~131k (64-beam ray cast)" if KIND == "SK" else "~33k (32-beam ray cast)", "voxel_m": 0.05, "classes": N_CLS, "path": path,
             "cache": "3 distinct batches rotated; per-step working set (activations ~0.7M voxels x up to 384 ch) exceeds the 126 MB L2"}
 
 
@@ -171,9 +171,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="spvcnn", choices=["spvcnn", "minkunet"])
     ap.add_argument("--path", default="auto", choices=["auto", "engine", "compat"])
+    ap.add_argument("--kind", default="SK", choices=["SK", "NU"], help="scan shape: SemanticKITTI-like (19 classes) or nuScenes-like (16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    global KIND, N_CLS
+    KIND, N_CLS = args.kind, (19 if args.kind == "SK" else 16)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -287,7 +290,7 @@ def main():
         if not args.no_extras:
             try:
                 from lidal_b200.profiling import scoring_extras
-                result["extra"] = scoring_extras(result["ms_per_step"], dev)
+                result["extra"] = scoring_extras(result["ms_per_step"], dev, n_cls=N_CLS, engine=eng, kind=KIND)
             except Exception as e:  # noqa: BLE001
                 result["extra"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:

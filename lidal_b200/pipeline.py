@@ -140,3 +140,30 @@ def cuda_score_frame(n_frames: int, nei_num=24, dis_thresh=0.1, device="cuda"):
         scorer.set_regions(scorer.frames[fid], sv_id, sv2point)
         return scorer.score_frame(fid)
     return score
+
+
+def infer_and_score_sequence(engine, raws, xyz, regions, seed=0, inf_reps=8, nei_num=24, dis_thresh=0.1, device="cuda"):
+    """The whole LiDAL chain for one sequence on ONE GPU, nothing leaves the device between stages:
+    raw scan -> 8 TTA views (voxelizer, F1) -> network (engine) -> softmax / mean / argmax (tta_tail) -> resident prob map
+    -> inter-frame divergence / entropy against the +-12 frame window -> per-region means.
+    raws: per-frame float32 [Np,4] sensor-frame points (host or device); xyz: per-frame float64 [Np,3] registered coordinates;
+    regions: per-frame (sv_id, sv2point).  Returns (per-frame worker_func tuples, timings dict in ms)."""
+    from . import score, voxelizer
+    dev = torch.device(device)
+    ev = lambda: torch.cuda.Event(enable_timing=True)          # noqa: E731
+    t0, t1, t2 = ev(), ev(), ev()
+    scorer = score.SequenceScorer(dev, nei_num, dis_thresh)
+    t0.record()
+    for i, raw in enumerate(raws):
+        raw_dev = torch.as_tensor(raw).to(dev)
+        coords, feats, inverse = voxelizer.tta_batch_gpu(raw_dev, seed=seed + i, inf_reps=inf_reps)
+        logits = engine(coords, feats)
+        prob, _pred = score.tta_tail(logits, inverse, inf_reps)
+        scorer.add_frame(xyz[i], prob, *regions[i])
+    t1.record()
+    out = [scorer.score_frame(i) for i in range(len(raws))]
+    t2.record()
+    torch.cuda.synchronize()
+    n = len(raws)
+    return out, {"prob_inference_ms_per_frame": t0.elapsed_time(t1) / n, "scoring_ms_per_frame": t1.elapsed_time(t2) / n,
+                 "frames_per_sec": 1e3 * n / t0.elapsed_time(t2), "frames": n}

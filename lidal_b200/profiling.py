@@ -108,12 +108,12 @@ def conv_roofline(run, resident, steps=3):
     }
 
 
-def scoring_extras(ms_per_step: float, dev, n_frames: int = 25, n_cls: int = 19):
+def scoring_extras(ms_per_step: float, dev, n_frames: int = 25, n_cls: int = 19, engine=None, kind: str = "SK"):
     """Second half of the metric: LiDAL scored frames/s = frames completing prob_inference (one 8-view step) + TTA tail
     + inter-frame scoring + region reduce.  Scoring kernels report achieved HBM GB/s against the measured copy peak."""
     from . import score, synth
     peaks = measured_peaks()
-    seq = synth.make_sequence(n_frames, "SK", seed=77)
+    seq = synth.make_sequence(n_frames, kind, seed=77)
     sc = score.SequenceScorer(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     probs = [synth.synthetic_probs(seq.xyz[i], n_cls, 300 + i) for i in range(n_frames)]
@@ -153,9 +153,17 @@ def scoring_extras(ms_per_step: float, dev, n_frames: int = 25, n_cls: int = 19)
     tail_bytes = 8 * npts * (n_cls * 4 + 8) + npts * (n_cls * 4 + 8)
     grid_ms = g0.elapsed_time(g1) / n_frames      # includes the H2D upload of xyz + prob of each frame
     hbm = float(peaks.get("hbm_gbs", FALLBACK["hbm_gbs"]))
+    measured = None
+    if engine is not None:
+        # the whole chain, measured: raw points -> GPU TTA voxelizer -> network -> tail -> resident probs -> scoring
+        from . import pipeline
+        regions = list(zip(seq.sv_id, seq.sv2point))
+        pipeline.infer_and_score_sequence(engine, seq.raw[:3] * 9, seq.xyz[:3] * 9, regions[:3] * 9, seed=1)      # warm-up
+        _, measured = pipeline.infer_and_score_sequence(engine, seq.raw, seq.xyz, regions, seed=5)
     frame_ms = ms_per_step + tail_ms + score_ms
     return {
         "lidal_scored_frames_per_sec": 1e3 / frame_ms, "frame_ms": frame_ms,
+        "pipeline_measured": measured,
         "prob_inference_ms": ms_per_step, "tta_tail_ms": tail_ms, "interframe_score_ms": score_ms,
         "frame_upload_and_grid_build_ms": grid_ms, "points_per_frame": npts, "matched_pairs": matched,
         "score_roofline": {"bound": "hbm", "achieved": alg_bytes / (score_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
