@@ -77,8 +77,10 @@ int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t* nbmaps, i
 
 /* Row permutation that groups output rows with equal neighbour masks (bit k = offset k present) so that the
  * 128-row tiles of lb_conv_fwd can skip whole offsets: perm int32 [n_out] (stable sort by the mask with its bits
- * re-ordered so the least frequent offset is most significant) and the permuted
+ * re-ordered so the least frequent offset is most significant; only the LB_MASK_KEY_BITS most significant key bits
+ * take part, i.e. for k = 27 the three most frequent offsets do not influence the order) and the permuted
  * table nbr_sorted[k][j] = nbr[k][perm[j]].  Use as  args.nbr = nbr_sorted, args.out_rows = perm. */
+#define LB_MASK_KEY_BITS 24
 size_t lb_kmap_sort_ws_bytes(int64_t n_out);
 int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm, int32_t* nbr_sorted,
                          void* ws, size_t ws_bytes, void* stream);

@@ -224,7 +224,132 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t* __restr
     }
   }
 }
+// ---- single-sweep variant: one kernel per pass.  Digit totals of every pass come from one up-front histogram of the
+// unsorted keys (digit counts do not depend on order); the per-tile prefix inside a pass is resolved by decoupled
+// look-back over a status word per (tile, digit) = flag (2 bits: 0 empty, 1 tile aggregate, 2 inclusive prefix) | count
+// (30 bits).  Tiles take their index from an atomic ticket so a tile only ever waits on tiles that already started.
+constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_LOOKBACK = 8;                   // predecessors polled per round (independent loads, one L2 latency)
+constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_VAL_MASK = (1u << 30) - 1;
+
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_digit_totals(const uint64_t* __restrict__ keys, int64_t n, int passes,
+                                                              uint32_t* __restrict__ totals /*[passes][256]*/) {
+  __shared__ uint32_t s_h[RS_MAX_PASSES][256];
+  for (int j = threadIdx.x; j < passes * 256; j += RS_THREADS) (&s_h[0][0])[j] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)RS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RS_THREADS) {
+    const uint64_t key = keys[i];
+    for (int ps = 0; ps < passes; ++ps) atomicAdd(&s_h[ps][(key >> (8 * ps)) & 255], 1u);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < passes * 256; j += RS_THREADS) {
+    const uint32_t c = (&s_h[0][0])[j];
+    if (c) atomicAdd(&totals[j], c);
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_sweep(const uint64_t* __restrict__ keys_in,
+                                                       const uint32_t* __restrict__ vals_in,
+                                                       uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                       int64_t n, int shift, const uint32_t* __restrict__ totals /*[256]*/,
+                                                       uint32_t* __restrict__ status /*[tiles][256]*/,
+                                                       uint32_t* __restrict__ ticket) {
+  __shared__ uint32_t s_cnt[RS_WARPS][256];
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint32_t s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int j = threadIdx.x; j < RS_WARPS * 256; j += RS_THREADS) (&s_cnt[0][0])[j] = 0;
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t wbase = tile * RS_TILE + (int64_t)warp * RS_PER_WARP;
+  for (int j = lane; j < RS_PER_WARP; j += 32) {
+    int64_t i = wbase + j;
+    if (i < n) atomicAdd(&s_cnt[warp][(keys_in[i] >> shift) & 255], 1u);
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;   // RS_THREADS == 256 digits
+    uint32_t mine = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) mine += s_cnt[w][d];
+    uint32_t* my_status = status + tile * 256 + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      st_relaxed_gpu(my_status, RS_FLAG_PREFIX | mine);
+    } else {
+      st_relaxed_gpu(my_status, RS_FLAG_AGG | mine);
+      int64_t t = tile - 1;
+      bool done = false;
+      while (!done) {
+        uint32_t v[RS_LOOKBACK];
+#pragma unroll
+        for (int j = 0; j < RS_LOOKBACK; ++j)
+          v[j] = (t - j >= 0) ? ld_relaxed_gpu(status + (t - j) * 256 + d) : RS_FLAG_PREFIX;
+        int used = 0;
+        bool stop = false;
+#pragma unroll
+        for (int j = 0; j < RS_LOOKBACK; ++j) {
+          if (!stop) {
+            const uint32_t f = v[j] & ~RS_VAL_MASK;
+            if (f == 0) {
+              stop = true;                         // not published yet: poll again from this tile
+            } else {
+              excl += v[j] & RS_VAL_MASK;
+              ++used;
+              if (f == RS_FLAG_PREFIX) { done = true; stop = true; }
+            }
+          }
+        }
+        t -= used;
+      }
+      st_relaxed_gpu(my_status, RS_FLAG_PREFIX | (excl + mine));
+    }
+    uint32_t all;
+    uint32_t run = block_exclusive_scan(totals[d], s_warp, all) + excl;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      uint32_t c = s_cnt[w][d];
+      s_cnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int j0 = 0; j0 < RS_PER_WARP; j0 += 32) {
+    int64_t i = wbase + j0 + lane;
+    bool ok = i < n;
+    uint64_t key = ok ? keys_in[i] : 0;
+    uint32_t digit = ok ? (uint32_t)((key >> shift) & 255) : 256u + lane;   // inactive lanes never match
+    uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    uint32_t rank = __popc(peers & ((1u << lane) - 1));
+    uint32_t pos = 0;
+    if (ok) pos = s_cnt[warp][digit] + rank;
+    __syncwarp();
+    if (ok && rank == __popc(peers) - 1) s_cnt[warp][digit] = pos + 1;
+    __syncwarp();
+    if (ok) {
+      keys_out[pos] = key;
+      if (vals_in) vals_out[pos] = vals_in[i];
+    }
+  }
+}
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static bool rs_use_sweep(int64_t n) {
+  static const bool off = getenv("LIDAL_SORT_3PHASE") != nullptr;    // A/B switch: the older hist/scan/scatter passes
+  return !off && n < ((int64_t)1 << 30);
+}
+static size_t rs_sweep_bytes(int tiles) {    // ticket[8] + totals[8][256] + status[8][tiles][256]
+  return align256(256 + (size_t)RS_MAX_PASSES * 256 * 4 + (size_t)RS_MAX_PASSES * tiles * 256 * 4);
+}
 
 }  // namespace lb
 
@@ -233,7 +358,7 @@ using namespace lb;
 extern "C" size_t lb_sort_pairs_ws_bytes(int64_t n) {
   int tiles = ceil_div(n > 0 ? n : 1, RS_TILE);
   return align256((size_t)n * 8) + align256((size_t)n * 4) + align256((size_t)256 * tiles * 4) +
-         align256(scan_ws_bytes((int64_t)256 * tiles)) + 1024;
+         align256(scan_ws_bytes((int64_t)256 * tiles)) + rs_sweep_bytes(tiles) + 1024;
 }
 extern "C" int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* ws, size_t ws_bytes,
                              void* stream) {
@@ -247,15 +372,29 @@ extern "C" int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_
   uint64_t* k2 = (uint64_t*)p; p += align256((size_t)n * 8);
   uint32_t* v2 = (uint32_t*)p; p += align256((size_t)n * 4);
   uint32_t* hist = (uint32_t*)p; p += align256((size_t)256 * tiles * 4);
-  void* sws = p;
+  void* sws = p; p += align256(scan_ws_bytes((int64_t)256 * tiles));
+  uint32_t* ticket = (uint32_t*)p;                       // [8] (padded to 256 bytes)
+  uint32_t* totals = (uint32_t*)(p + 256);               // [passes][256]
+  uint32_t* status = totals + RS_MAX_PASSES * 256;       // [passes][tiles][256]
   int passes = (end_bit + 7) / 8;
   uint64_t *ka = keys, *kb = k2;
   uint32_t *va = vals, *vb = v2;
+  const bool sweep = rs_use_sweep(n);
+  if (sweep) {
+    LB_CUDA(cudaMemsetAsync(p, 0, 256 + (size_t)RS_MAX_PASSES * 256 * 4 + (size_t)passes * tiles * 256 * 4, st));
+    int grid = tiles < 148 * 4 ? tiles : 148 * 4;
+    rs_digit_totals<<<grid, RS_THREADS, 0, st>>>(keys, n, passes, totals); LB_LAUNCHED(1);
+  }
   for (int ps = 0; ps < passes; ++ps) {
-    rs_hist<<<tiles, RS_THREADS, 0, st>>>(ka, n, ps * 8, hist, tiles); LB_LAUNCHED(1);
-    int rc = exclusive_scan_u32(hist, hist, (int64_t)256 * tiles, nullptr, sws, st);
-    if (rc != LB_OK) return rc;
-    rs_scatter<<<tiles, RS_THREADS, 0, st>>>(ka, vals ? va : nullptr, kb, vb, n, ps * 8, hist, tiles); LB_LAUNCHED(1);
+    if (sweep) {
+      rs_sweep<<<tiles, RS_THREADS, 0, st>>>(ka, vals ? va : nullptr, kb, vb, n, ps * 8, totals + ps * 256,
+                                             status + (size_t)ps * tiles * 256, ticket + ps); LB_LAUNCHED(1);
+    } else {
+      rs_hist<<<tiles, RS_THREADS, 0, st>>>(ka, n, ps * 8, hist, tiles); LB_LAUNCHED(1);
+      int rc = exclusive_scan_u32(hist, hist, (int64_t)256 * tiles, nullptr, sws, st);
+      if (rc != LB_OK) return rc;
+      rs_scatter<<<tiles, RS_THREADS, 0, st>>>(ka, vals ? va : nullptr, kb, vb, n, ps * 8, hist, tiles); LB_LAUNCHED(1);
+    }
     uint64_t* tk = ka; ka = kb; kb = tk;
     uint32_t* tv = va; va = vb; vb = tv;
   }
@@ -576,7 +715,9 @@ __global__ void ks_bitpos(const unsigned* __restrict__ counts, int k, int* __res
     if (counts[i] < counts[j] || (counts[i] == counts[j] && i < j)) ++rank;
   bitpos[j] = k - 1 - rank;
 }
-__global__ void ks_keys(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, const int* __restrict__ bitpos,
+// `drop`: the most frequent offsets (lowest key bits) are left out of the key - nearly every tile needs them anyway, and a
+// 27-offset map then sorts in three 8-bit passes instead of four.
+__global__ void ks_keys(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, const int* __restrict__ bitpos, int drop,
                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   __shared__ int s_pos[32];
   if (threadIdx.x < 32) s_pos[threadIdx.x] = threadIdx.x < k ? bitpos[threadIdx.x] : 0;
@@ -584,7 +725,7 @@ __global__ void ks_keys(const int* __restrict__ nbr, int64_t ld, int64_t n, int 
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
     uint64_t m = 0;
     for (int j = 0; j < k; ++j) m |= (uint64_t)(__ldg(&nbr[(int64_t)j * ld + o]) >= 0) << s_pos[j];
-    keys[o] = m;
+    keys[o] = m >> drop;
     vals[o] = (uint32_t)o;
   }
 }
@@ -616,8 +757,10 @@ extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t 
   LB_CUDA(cudaMemsetAsync(counts, 0, 256, st));
   ks_count<<<grid_for(n_out, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, counts); LB_LAUNCHED(1);
   ks_bitpos<<<1, 32, 0, st>>>(counts, k, bitpos); LB_LAUNCHED(1);
-  ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, bitpos, keys, (uint32_t*)perm); LB_LAUNCHED(1);
-  int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
+  static const int key_bits = getenv("LIDAL_MASK_KEY_BITS") ? atoi(getenv("LIDAL_MASK_KEY_BITS")) : LB_MASK_KEY_BITS;
+  const int drop = (key_bits > 0 && k > key_bits) ? k - key_bits : 0;
+  ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, bitpos, drop, keys, (uint32_t*)perm); LB_LAUNCHED(1);
+  int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k - drop, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
   if (rc != LB_OK) return rc;
   ks_permute<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, perm, nbr_sorted); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();

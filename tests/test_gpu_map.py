@@ -115,3 +115,30 @@ def test_sort_pairs_stable_and_sorted():
     L.check(L.lib().lb_sort_pairs(L.ptr(k2), L.ptr(v2), n, 32, L.ptr(ws), nbytes, L.stream()))
     want_k, want_i = torch.sort(keys.cpu(), stable=True)
     assert torch.equal(k2.cpu(), want_k) and torch.equal(v2.cpu().long(), want_i)
+
+
+@pytest.mark.parametrize("n,bits,dup", [(1, 8, 1), (4097, 16, 1), (1_000_003, 27, 1), (6_000_000, 64, 1), (2_000_000, 40, 1 << 39)])
+def test_sort_pairs_sizes(n, bits, dup):
+    """Single-sweep radix sort (decoupled look-back): tile counts below and above what is resident at once, 1..8 passes,
+    all-equal digits (dup = one huge multiplier leaves a single live bit)."""
+    from lidal_b200 import _lib as L
+    g = torch.Generator().manual_seed(n % 1000)
+    if bits == 64:
+        keys = torch.randint(-2 ** 63, 2 ** 63 - 1, (n,), dtype=torch.int64, generator=g)
+    elif dup > 1:
+        keys = torch.randint(0, 2, (n,), dtype=torch.int64, generator=g) * dup
+    else:
+        keys = torch.randint(0, 2 ** bits, (n,), dtype=torch.int64, generator=g)
+    keys = keys.cuda()
+    vals = torch.arange(n, dtype=torch.int32).cuda()
+    k2, v2 = keys.clone(), vals.clone()
+    nbytes = L.lib().lb_sort_pairs_ws_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    for _ in range(2):          # second call reuses the dirty workspace
+        k2.copy_(keys); v2.copy_(vals)
+        L.check(L.lib().lb_sort_pairs(L.ptr(k2), L.ptr(v2), n, bits, L.ptr(ws), nbytes, L.stream()))
+    # unsigned order: compare through a bias so torch's signed stable sort gives the same permutation
+    biased = keys ^ (-2 ** 63) if bits == 64 else keys
+    want_k, want_i = torch.sort(biased, stable=True)
+    assert torch.equal(v2.long(), want_i)
+    assert torch.equal(k2, keys[want_i])
