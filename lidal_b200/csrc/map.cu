@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_sweep(const uint64_t* __restric
                                                        int64_t n, int shift, const uint32_t* __restrict__ totals /*[256]*/,
                                                        uint32_t* __restrict__ status /*[tiles][256]*/,
                                                        uint32_t* __restrict__ ticket) {
+  constexpr int ITEMS = RS_PER_WARP / 32;        // keys per lane, kept in registers across the look-back
   __shared__ uint32_t s_cnt[RS_WARPS][256];
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_tile;
@@ -272,10 +273,15 @@ __global__ void __launch_bounds__(RS_THREADS) rs_sweep(const uint64_t* __restric
   __syncthreads();
   const int64_t tile = s_tile;
   const int64_t wbase = tile * RS_TILE + (int64_t)warp * RS_PER_WARP;
-  for (int j = lane; j < RS_PER_WARP; j += 32) {
-    int64_t i = wbase + j;
-    if (i < n) atomicAdd(&s_cnt[warp][(keys_in[i] >> shift) & 255], 1u);
+  uint64_t key[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int64_t i = wbase + j * 32 + lane;
+    key[j] = i < n ? keys_in[i] : 0;
   }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)
+    if (wbase + j * 32 + lane < n) atomicAdd(&s_cnt[warp][(key[j] >> shift) & 255], 1u);
   __syncthreads();
   {
     const int d = threadIdx.x;   // RS_THREADS == 256 digits
@@ -324,28 +330,30 @@ __global__ void __launch_bounds__(RS_THREADS) rs_sweep(const uint64_t* __restric
     }
   }
   __syncthreads();
-  for (int j0 = 0; j0 < RS_PER_WARP; j0 += 32) {
-    int64_t i = wbase + j0 + lane;
-    bool ok = i < n;
-    uint64_t key = ok ? keys_in[i] : 0;
-    uint32_t digit = ok ? (uint32_t)((key >> shift) & 255) : 256u + lane;   // inactive lanes never match
-    uint32_t peers = __match_any_sync(0xffffffffu, digit);
-    uint32_t rank = __popc(peers & ((1u << lane) - 1));
+  // stable ranking inside each warp's sub-range, 32 keys at a time (match_any keeps equal digits in input order)
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int64_t i = wbase + j * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t digit = ok ? (uint32_t)((key[j] >> shift) & 255) : 256u + lane;   // inactive lanes never match
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1));
     uint32_t pos = 0;
     if (ok) pos = s_cnt[warp][digit] + rank;
     __syncwarp();
     if (ok && rank == __popc(peers) - 1) s_cnt[warp][digit] = pos + 1;
     __syncwarp();
     if (ok) {
-      keys_out[pos] = key;
-      if (vals_in) vals_out[pos] = vals_in[i];
+      keys_out[pos] = key[j];
+      if (vals_in) vals_out[pos] = __ldg(&vals_in[i]);
     }
   }
 }
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static bool rs_use_sweep(int64_t n) {
   static const bool off = getenv("LIDAL_SORT_3PHASE") != nullptr;    // A/B switch: the older hist/scan/scatter passes
-  return !off && n < ((int64_t)1 << 30);
+  // beyond ~512 tiles the first wave's look-back chain outweighs the saved histogram/scan launches (measured, 4M keys)
+  return !off && n <= (int64_t)512 * RS_TILE;
 }
 static size_t rs_sweep_bytes(int tiles) {    // ticket[8] + totals[8][256] + status[8][tiles][256]
   return align256(256 + (size_t)RS_MAX_PASSES * 256 * 4 + (size_t)RS_MAX_PASSES * tiles * 256 * 4);
@@ -688,18 +696,22 @@ extern "C" int lb_unique_i64(const int64_t* keys, int64_t n, int key_bits, int64
 // ------------------------------------------------------------------------------------------ mask-sorted kernel maps
 namespace lb {
 // per-offset neighbour counts (how many rows have offset j)
-__global__ void ks_count(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, unsigned* __restrict__ counts) {
+__global__ void ks_count(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, unsigned* __restrict__ counts,
+                         uint32_t* __restrict__ masks) {
   __shared__ unsigned s_cnt[32];
   if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t n_pad = (n + 31) & ~(int64_t)31;          // whole warps stay converged for the ballots
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_pad; o += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t m = 0;
     for (int j = 0; j < k; ++j) {
       const bool v = o < n && __ldg(&nbr[(int64_t)j * ld + o]) >= 0;
       const unsigned b = __ballot_sync(0xffffffffu, v);
       if (lane == 0 && b) atomicAdd(&s_cnt[j], __popc(b));
+      m |= (uint32_t)v << j;
     }
+    if (o < n) masks[o] = m;                               // bit j = offset j present
   }
   __syncthreads();
   if (threadIdx.x < k && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
@@ -717,14 +729,15 @@ __global__ void ks_bitpos(const unsigned* __restrict__ counts, int k, int* __res
 }
 // `drop`: the most frequent offsets (lowest key bits) are left out of the key - nearly every tile needs them anyway, and a
 // 27-offset map then sorts in three 8-bit passes instead of four.
-__global__ void ks_keys(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, const int* __restrict__ bitpos, int drop,
+__global__ void ks_keys(const uint32_t* __restrict__ masks, int64_t n, int k, const int* __restrict__ bitpos, int drop,
                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   __shared__ int s_pos[32];
   if (threadIdx.x < 32) s_pos[threadIdx.x] = threadIdx.x < k ? bitpos[threadIdx.x] : 0;
   __syncthreads();
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t nat = masks[o];
     uint64_t m = 0;
-    for (int j = 0; j < k; ++j) m |= (uint64_t)(__ldg(&nbr[(int64_t)j * ld + o]) >= 0) << s_pos[j];
+    for (int j = 0; j < k; ++j) m |= (uint64_t)((nat >> j) & 1u) << s_pos[j];
     keys[o] = m >> drop;
     vals[o] = (uint32_t)o;
   }
@@ -741,7 +754,7 @@ __global__ void ks_permute(const int* __restrict__ nbr, int64_t ld, int64_t n, i
 }  // namespace lb
 extern "C" size_t lb_kmap_sort_ws_bytes(int64_t n) {
   if (n < 1) n = 1;
-  return align256((size_t)n * 8) + align256(lb_sort_pairs_ws_bytes(n)) + 512;
+  return align256((size_t)n * 8) + align256(lb_sort_pairs_ws_bytes(n)) + 512 + align256((size_t)n * 4);
 }
 extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm,
                                     int32_t* nbr_sorted, void* ws, size_t ws_bytes, void* stream) {
@@ -754,12 +767,13 @@ extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t 
   void* sort_ws = (char*)ws + align256((size_t)n_out * 8);
   unsigned* counts = (unsigned*)((char*)sort_ws + align256(lb_sort_pairs_ws_bytes(n_out)));   // [32] + bitpos [32]
   int* bitpos = (int*)(counts + 32);
+  uint32_t* masks = (uint32_t*)((char*)counts + 512);
   LB_CUDA(cudaMemsetAsync(counts, 0, 256, st));
-  ks_count<<<grid_for(n_out, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, counts); LB_LAUNCHED(1);
+  ks_count<<<grid_for(n_out, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, counts, masks); LB_LAUNCHED(1);
   ks_bitpos<<<1, 32, 0, st>>>(counts, k, bitpos); LB_LAUNCHED(1);
   static const int key_bits = getenv("LIDAL_MASK_KEY_BITS") ? atoi(getenv("LIDAL_MASK_KEY_BITS")) : LB_MASK_KEY_BITS;
   const int drop = (key_bits > 0 && k > key_bits) ? k - key_bits : 0;
-  ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, bitpos, drop, keys, (uint32_t*)perm); LB_LAUNCHED(1);
+  ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(masks, n_out, k, bitpos, drop, keys, (uint32_t*)perm); LB_LAUNCHED(1);
   int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k - drop, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
   if (rc != LB_OK) return rc;
   ks_permute<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, perm, nbr_sorted); LB_LAUNCHED(1);
