@@ -262,7 +262,7 @@ def pack_weight(kernel, dtype):
 
 
 def conv_forward(feats16, packed_w, nbr, n_out, *, scale=None, shift=None, residual=None, relu=False,
-                 out=None, out_dtype=torch.float32, force_simt=False):
+                 out=None, out_dtype=torch.float32, force_simt=False, extra_flags=0):
     """One lb_conv_fwd launch.  feats16 [n_in, c_in] 16-bit (may be a column slice); nbr int32 [K, >=n_out] or None."""
     k, cout, cin = packed_w.shape
     assert feats16.dtype == packed_w.dtype and feats16.stride(1) == 1
@@ -279,7 +279,7 @@ def conv_forward(feats16, packed_w, nbr, n_out, *, scale=None, shift=None, resid
     a.shift = shift.data_ptr() if shift is not None else None
     a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
     a.act_dtype, a.out_dtype = L.DT_OF[feats16.dtype], L.DT_OF[out.dtype]
-    a.flags = (L.LB_CONV_RELU if relu else 0) | (L.LB_CONV_FORCE_SIMT if force_simt else 0)
+    a.flags = (L.LB_CONV_RELU if relu else 0) | (L.LB_CONV_FORCE_SIMT if force_simt else 0) | extra_flags
     if CONV_TRACE is None:
         L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
         return out

@@ -50,7 +50,9 @@ struct TcParams {
   int tmem_cols;
   int nb;                  // (offset, channel-block) blocks carried by one pipeline stage (1..4)
   int T;                   // 128-row sub-tiles per CTA tile (1 or 2): T accumulators share every weight tile
-  int staged;              // 1: smem-staged epilogue (per-row bulk async loads / stores), needs 16-bit output
+  int staged;              // smem-staged epilogue (16-bit output): 1 = per-row bulk async copies (any row order),
+                           // 2 = TMA tile boxes [32 rows x 32 channels] through out_map / res_map (rows in natural order)
+  int stg_bufs;            // staging buffers per epilogue warp (2: the stores of one sub-tile drain while the next is built)
   int n_acc;               // TMEM accumulator sets (2 = epilogue overlaps the next tile, 1 when 2*T*c_out > 512)
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
 };
@@ -71,7 +73,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
 // BK = channels per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
 template <int BK, int T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap out_map,
+               const __grid_constant__ CUtensorMap res_map, const TcParams p) {
   constexpr int ROW_BYTES = BK * 2;
   constexpr int CHUNKS = ROW_BYTES / 16;                 // 16-byte chunks per row: 8 or 4
   constexpr int A_BYTES = TILE_M * ROW_BYTES;            // 16 KB or 8 KB
@@ -101,7 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
   uint32_t* s_mask = s_tmem + 1;                                   // [2] active-offset mask of the producers' tile (by parity)
   uint64_t* res_bar = (uint64_t*)(s_mask + 2 + 1);                 // [4] residual rows landed (one per epilogue warp), 8-byte aligned
   const int stg_pitch = p.c_out * 2 + 16;                          // staged epilogue: row pitch (+16 B: conflict-free 128-bit LDS)
-  uint8_t* s_stage = tail + (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 127) & ~(size_t)127);
+  uint8_t* s_stage = tail + (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 1023) & ~(size_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out;
@@ -276,12 +279,105 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
     }
   } else {
     // =============================================================== EPILOGUE (warps 0-3: TMEM lane quadrant = warp)
-    if (p.staged) {
+    if (p.staged == 2) {
+      // TMA-tile staging (output rows in natural order, 1x1 layers): a warp's 32 rows x c_out channels sit in smem as
+      // c_out/32 boxes of [32 rows][64 B] in the SWIZZLE_64B pattern (16-byte chunk q of row r at q ^ ((r >> 1) & 3):
+      // conflict-free 128-bit accesses without padding).  The residual tile arrives by one TMA load per box, the finished
+      // tile leaves by one TMA store per box -- c_out/32 copy instructions per warp instead of 32 per-row copies, which
+      // the uniform datapath issues one lane at a time.
+      const int groups = p.c_out >> 5;
+      const uint32_t buf_bytes = (uint32_t)groups * 2048u;
+      uint8_t* my_stage = s_stage + (size_t)warp * p.stg_bufs * buf_bytes;
+      const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = (uint32_t)(lane >> 1) & 3u;
+      const uint32_t row_bytes = (uint32_t)p.c_out * 2;
+      uint32_t res_ph = 0;
+      int buf = 0;
+      int64_t tcount = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = (int)(tcount % p.n_acc);
+        const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+        for (int sub = 0; sub < T; ++sub) {
+          const int64_t row0 = tile * TM + sub * TILE_M + warp * 32;
+          const bool any_live = row0 < n_out;
+          uint8_t* sbuf = my_stage + (size_t)buf * buf_bytes;
+          if (lane == 0) {                                  // lane 0 owns the warp's bulk groups
+            if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read();
+          }
+          if (p.stg_bufs == 2) buf ^= 1;
+          __syncwarp();
+          if (p.residual && any_live && lane == 0) {
+            mbar_arrive_expect_tx(&res_bar[warp], 32u * row_bytes);      // whole boxes; rows past the end are zero-filled
+            for (int g = 0; g < groups; ++g) tma_load_2d(smem_u32(sbuf + g * 2048), &res_map, g * 32, (int)row0, &res_bar[warp]);
+          }
+          if (sub == 0) {
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+          }
+          if (p.residual && any_live) {
+            mbar_wait(&res_bar[warp], res_ph);
+            res_ph ^= 1;
+          }
+          for (int c0 = 0; c0 < p.c_out; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+            if (p.relu == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint8_t* grp = sbuf + (size_t)(c0 >> 5) * 2048 + sw_row;
+            if (p.residual) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 rr = *(const uint4*)(grp + (((uint32_t)q ^ sw_x) << 4));
+                const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (p.is_bf16) {
+                    f[q * 8 + 2 * j] += cvt_in<__nv_bfloat16>((uint16_t)(w[j] & 0xffff));
+                    f[q * 8 + 2 * j + 1] += cvt_in<__nv_bfloat16>((uint16_t)(w[j] >> 16));
+                  } else {
+                    f[q * 8 + 2 * j] += cvt_in<__half>((uint16_t)(w[j] & 0xffff));
+                    f[q * 8 + 2 * j + 1] += cvt_in<__half>((uint16_t)(w[j] >> 16));
+                  }
+                }
+              }
+            }
+            if (p.relu == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              w.x = pack2(f[q * 8], f[q * 8 + 1], p.is_bf16);
+              w.y = pack2(f[q * 8 + 2], f[q * 8 + 3], p.is_bf16);
+              w.z = pack2(f[q * 8 + 4], f[q * 8 + 5], p.is_bf16);
+              w.w = pack2(f[q * 8 + 6], f[q * 8 + 7], p.is_bf16);
+              *(uint4*)(grp + (((uint32_t)q ^ sw_x) << 4)) = w;
+            }
+          }
+          fence_proxy_async();                              // generic-proxy smem writes -> visible to the copy engine
+          __syncwarp();
+          if (lane == 0) {
+            if (any_live)
+              for (int g = 0; g < groups; ++g) tma_store_2d(&out_map, g * 32, (int)row0, smem_u32(sbuf + g * 2048));
+            bulk_commit();
+          }
+        }   // sub-tiles
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      }
+      if (lane == 0) bulk_wait_all();
+    } else if (p.staged) {
       // Shared-memory-staged epilogue: every lane owns one output row.  Its residual row arrives by ONE bulk async copy
       // (completion on the warp's mbarrier), the row is finished in place in smem, and leaves by ONE bulk async store:
       // global traffic is whole contiguous rows moved by the copy engine instead of 16-byte pieces per thread.
-      uint8_t* my_stage = s_stage + (size_t)warp * 32 * stg_pitch;
-      uint8_t* my_row = my_stage + (size_t)lane * stg_pitch;
+      uint8_t* my_stage = s_stage + (size_t)warp * p.stg_bufs * 32 * stg_pitch;
+      const size_t buf_bytes = (size_t)32 * stg_pitch;
+      int buf = 0;
       const uint32_t row_bytes = (uint32_t)p.c_out * 2;
       uint32_t res_ph = 0;
       int64_t tcount = 0;
@@ -292,7 +388,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const TcParams p) {
           const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
           const bool live = o < n_out;
           const int64_t orow = live ? (p.out_rows ? (int64_t)__ldg(&p.out_rows[o]) : o) : 0;
-          bulk_wait_read();                               // the previous stores have finished reading this staging buffer
+          uint8_t* my_row = my_stage + buf * buf_bytes + (size_t)lane * stg_pitch;
+          if (p.stg_bufs == 2) { bulk_wait_read1(); buf ^= 1; }   // the stores that last used THIS buffer have read it
+          else bulk_wait_read();
           __syncwarp();
           if (p.residual) {
             const unsigned live_mask = __ballot_sync(0xffffffffu, live);
@@ -468,9 +566,9 @@ int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
 
 static size_t tail_bytes(int T) {
   // indices + scale/shift + ring/accumulator barriers + flags + (tmem ptr, masks, 4 residual barriers), rounded for staging
-  return (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 127) & ~(size_t)127);
+  return (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 1023) & ~(size_t)1023);
 }
-static size_t staging_bytes(int c_out) { return (size_t)4 * 32 * (c_out * 2 + 16); }
+static size_t staging_bytes(int c_out, int bufs = 1) { return (size_t)bufs * 4 * 32 * (c_out * 2 + 16); }
 
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const bool pack8 = (a.flags & LB_CONV_PACK8) != 0;
@@ -517,6 +615,9 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
     const size_t budget2 = 227 * 1024 - 1024 - tail_bytes(2);
     if (tiles128 >= (int64_t)8 * sm_count() && budget2 / blk2 >= 6 && 2 * a.c_out <= 512) T = 2;
   }
+  // a single-block 1x1 layer with a wide output is pure epilogue: 128-row tiles keep two accumulator sets and leave
+  // room for double-buffered staging
+  if (!pack8 && a.k_vol * (a.c_in / bk) == 1 && a.c_out > 128) T = 1;
   if (a.flags & LB_CONV_TILE128) T = 1;
   p.T = T;
   p.n_acc = (2 * T * a.c_out <= 512) ? 2 : 1;
@@ -535,11 +636,36 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const int blocks_per_tile = pack8 ? (a.k_vol * 8 + bk - 1) / bk : a.k_vol * (a.c_in / bk);
   const int want_stages = blocks_per_tile < 5 ? (blocks_per_tile < 3 ? 3 : blocks_per_tile) : 5;
   p.staged = 0;
+  p.stg_bufs = 1;
   size_t budget_eff = budget;
   if (a.out_dtype != LB_DT_F32 && !(a.flags & LB_CONV_NO_STAGED_EPILOGUE) && budget > staging_bytes(a.c_out) &&
       (budget - staging_bytes(a.c_out)) / stage_bytes >= (size_t)want_stages) {
     p.staged = 1;
-    budget_eff = budget - staging_bytes(a.c_out);
+    // short K loops (1x1 layers) are pure epilogue: a second staging buffer per warp lets the copy engine drain one
+    // sub-tile while the next one is converted (single-buffered, the warp idles for the store's read latency)
+    static const bool no_dbuf = getenv("LIDAL_NO_STAGE_DBUF") != nullptr;
+    if (!no_dbuf && blocks_per_tile < 5 && budget > staging_bytes(a.c_out, 2) &&
+        (budget - staging_bytes(a.c_out, 2)) / stage_bytes >= (size_t)want_stages)
+      p.stg_bufs = 2;
+    budget_eff = budget - staging_bytes(a.c_out, p.stg_bufs);
+    // natural row order (no out_rows permutation, host-known row count): whole [32 x 32] boxes through tensor maps
+    static const bool no_tile = getenv("LIDAL_NO_TILE_EPILOGUE") != nullptr;
+    if (!no_tile && !a.out_rows && !a.n_out_dev && a.n_out < ((int64_t)1 << 31)) p.staged = 2;
+  }
+  CUtensorMap out_map = map, res_map = map;     // placeholders unless staged == 2
+  if (p.staged == 2) {
+    const CUtensorMapDataType dt = a.act_dtype == LB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t od[2] = {(cuuint64_t)a.c_out, (cuuint64_t)a.n_out};
+    cuuint32_t obox[2] = {32, 32};
+    cuuint64_t os[1] = {(cuuint64_t)a.ld_out * 2};
+    r = encode(&out_map, dt, 2, a.out, od, os, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && a.residual) {
+      cuuint64_t rs[1] = {(cuuint64_t)a.ld_res * 2};
+      r = encode(&res_map, dt, 2, const_cast<void*>(a.residual), od, rs, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) p.staged = 1;         // e.g. a stride the tensor map cannot express: per-row copies still work
   }
   int stages = (int)(budget_eff / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -547,14 +673,14 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.stages = stages;
   p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
-  const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + (p.staged ? staging_bytes(a.c_out) : 0) + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + (p.staged ? staging_bytes(a.c_out, p.stg_bufs) : 0) + 1024;
   int64_t tiles = (a.n_out + (int64_t)T * TILE_M - 1) / ((int64_t)T * TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
 #define LB_TC_LAUNCH(BKV, TV)                                                                                         \
   do {                                                                                                                \
     LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BKV, TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    conv_tc_kernel<BKV, TV><<<grid, NUM_THREADS, smem, st>>>(map, p);                                                  \
+    conv_tc_kernel<BKV, TV><<<grid, NUM_THREADS, smem, st>>>(map, out_map, res_map, p);                                                  \
     LB_LAUNCHED(1);                                                                                                   \
   } while (0)
   if (bk == 64 && T == 1) LB_TC_LAUNCH(64, 1);

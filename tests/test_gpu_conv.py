@@ -230,3 +230,26 @@ def test_minkunet_training_step_vs_oracle(ts, oracle_ts, small_scan):
     # (tools/debug_train_grad.py prints the table; no layer type stands out).  Bound the drift, not bit parity.
     assert np.median(list(err16.values())) < 0.35 and max(err16.values()) < 0.5, sorted(err16.items(), key=lambda kv: -kv[1])[:3]
     assert min(cos32.values()) > 0.85
+
+
+@pytest.mark.parametrize("cin,cout,res", [(32, 256, False), (256, 128, True), (64, 64, True), (128, 96, False)])
+def test_1x1_tile_epilogue_matches_direct_stores(ts, cin, cout, res):
+    """1x1 layers (no neighbour table, natural row order) leave through TMA tile boxes; the arithmetic is the same as the
+    direct-store epilogue, so the two must agree bit for bit -- ragged row count, column-slice output."""
+    from lidal_b200 import _lib as L
+    F = ts.nn.functional
+    g = torch.Generator().manual_seed(cin + cout)
+    n = 10_007
+    x = torch.randn(n, cin, generator=g).cuda().bfloat16()
+    w = F.pack_weight((torch.randn(1, cin, cout, generator=g) * 0.1).cuda(), torch.bfloat16)
+    sc, sh = (torch.rand(cout, generator=g) + 0.5).cuda(), torch.randn(cout, generator=g).cuda()
+    r = torch.randn(n, cout + 8, generator=g).cuda().bfloat16()[:, :cout] if res else None
+    outs = []
+    for fl in (0, L.LB_CONV_NO_STAGED):
+        wide = torch.full((n, cout + 32), 7.0, dtype=torch.bfloat16, device="cuda")
+        F.conv_forward(x, w, None, n, scale=sc, shift=sh, residual=r, relu=True, out=wide[:, 32:], extra_flags=fl)
+        assert float((wide[:, :32].float() - 7.0).abs().max()) == 0.0
+        outs.append(wide[:, 32:].clone())
+    assert torch.equal(outs[0], outs[1])
+    want = torch.relu(x.float() @ w[0].float().t() * sc + sh + (r.float() if res else 0.0))
+    torch.testing.assert_close(outs[0].float(), want, rtol=2e-2, atol=2e-2)
