@@ -71,7 +71,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
 }
 
 // BK = channels per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)
-template <int BK, int T>
+// KMAX = compile-time bound of the per-tile offset loops (1, 8 or 27): the index registers and the mask votes are unrolled
+// over it, so a 1x1 or 2x2x2 layer does not pay the 27-offset prologue on every tile.
+template <int BK, int T, int KMAX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap out_map,
                const __grid_constant__ CUtensorMap res_map, const TcParams p) {
@@ -177,12 +179,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     };
     // Neighbour indices of the NEXT tile are fetched into registers while the current tile's stages are being issued
     // (27 independent loads in flight), so the tile prologue never waits on global memory.
-    int nb_reg[MAX_KVOL];
+    int nb_reg[KMAX];
     const bool idx_thread = t < TM;                       // thread t stages the indices of tile row t (rows 0..TM-1)
     auto fetch_indices = [&](int64_t tile) {
       const int64_t o = tile * TM + t;
 #pragma unroll
-      for (int k = 0; k < MAX_KVOL; ++k) {
+      for (int k = 0; k < KMAX; ++k) {
         int nb = -1;
         if (idx_thread && k < p.k_vol && o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
         nb_reg[k] = nb;
@@ -196,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t my_mask = 0;
 #pragma unroll
-      for (int k = 0; k < MAX_KVOL; ++k) {
+      for (int k = 0; k < KMAX; ++k) {
         if (k < p.k_vol) {
           int nb = nb_reg[k];
           if (nb >= p.n_in) nb = -1;
@@ -677,16 +679,23 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   int64_t tiles = (a.n_out + (int64_t)T * TILE_M - 1) / ((int64_t)T * TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
-#define LB_TC_LAUNCH(BKV, TV)                                                                                         \
+#define LB_TC_LAUNCH(BKV, TV, KV)                                                                                     \
   do {                                                                                                                \
-    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BKV, TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    conv_tc_kernel<BKV, TV><<<grid, NUM_THREADS, smem, st>>>(map, out_map, res_map, p);                                                  \
+    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BKV, TV, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_tc_kernel<BKV, TV, KV><<<grid, NUM_THREADS, smem, st>>>(map, out_map, res_map, p);                              \
     LB_LAUNCHED(1);                                                                                                   \
   } while (0)
-  if (bk == 64 && T == 1) LB_TC_LAUNCH(64, 1);
-  else if (bk == 64) LB_TC_LAUNCH(64, 2);
-  else if (T == 1) LB_TC_LAUNCH(32, 1);
-  else LB_TC_LAUNCH(32, 2);
+#define LB_TC_LAUNCH_K(BKV, TV)                                                                                       \
+  do {                                                                                                                \
+    if (a.k_vol == 1) LB_TC_LAUNCH(BKV, TV, 1);                                                                       \
+    else if (a.k_vol <= 8) LB_TC_LAUNCH(BKV, TV, 8);                                                                  \
+    else LB_TC_LAUNCH(BKV, TV, MAX_KVOL);                                                                             \
+  } while (0)
+  if (bk == 64 && T == 1) LB_TC_LAUNCH_K(64, 1);
+  else if (bk == 64) LB_TC_LAUNCH_K(64, 2);
+  else if (T == 1) LB_TC_LAUNCH_K(32, 1);
+  else LB_TC_LAUNCH_K(32, 2);
+#undef LB_TC_LAUNCH_K
 #undef LB_TC_LAUNCH
   LB_LAUNCH_CHECK();
   return LB_OK;
