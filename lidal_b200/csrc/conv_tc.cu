@@ -190,22 +190,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         nb_reg[k] = nb;
       }
     };
+    const uint32_t n_in_u = p.n_in > 0x7fffffff ? 0x7fffffffu : (uint32_t)p.n_in;
     if ((int64_t)blockIdx.x < num_tiles) fetch_indices(blockIdx.x);
     if (t < 2) s_mask[t] = 0;
     uint32_t par = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, par ^= 1) {
       // (A) every producer has finished reading s_idx / s_mask[par^1] of the previous tile
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
-      uint32_t my_mask = 0;
+      uint32_t my_bits = 0;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < p.k_vol) {
-          int nb = nb_reg[k];
-          if (nb >= p.n_in) nb = -1;
-          if (idx_thread) s_idx[k * TM + t] = nb;         // row t of the tile == sub-tile t / 128, row t % 128
-          if (__any_sync(0xffffffffu, nb >= 0)) my_mask |= 1u << k;
+          const int nb = nb_reg[k];
+          const bool ok = (uint32_t)nb < n_in_u;          // one compare rejects both "no neighbour" (-1) and out-of-range rows
+          if (idx_thread) s_idx[k * TM + t] = ok ? nb : -1;   // row t of the tile == sub-tile t / 128, row t % 128
+          if (ok) my_bits |= 1u << k;
         }
       }
+      const uint32_t my_mask = __reduce_or_sync(0xffffffffu, my_bits);   // one warp reduction instead of a vote per offset
       if (lane == 0 && my_mask) atomicOr(&s_mask[par], my_mask);
       if (t == 0) s_mask[par ^ 1] = 0;
       // (B) indices and mask of this tile are complete
