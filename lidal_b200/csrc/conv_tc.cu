@@ -15,6 +15,9 @@
 // accumulator ring (tmem_full/tmem_empty) between MMA and epilogue, so the epilogue of tile t overlaps the
 // gathers and MMAs of tile t+1.  Offsets for which no row of the tile has a neighbour are skipped entirely.
 // No atomics: every output row is written exactly once, by one thread.
+#include <map>
+#include <mutex>
+#include <utility>
 #include "tc_ptx.cuh"
 
 namespace lb {
@@ -55,6 +58,8 @@ struct TcParams {
   int stg_bufs;            // staging buffers per epilogue warp (2: the stores of one sub-tile drain while the next is built)
   int n_acc;               // TMEM accumulator sets (2 = epilogue overlaps the next tile, 1 when 2*T*c_out > 512)
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
+  unsigned* sched;         // dynamic tile scheduler: [0] next ticket, [1] retired CTAs (both zero between launches);
+                           // nullptr = static round-robin
 };
 
 template <typename T> __device__ __forceinline__ float cvt_in(uint16_t raw);
@@ -105,13 +110,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   uint32_t* s_tmem = s_flags + MAX_STAGES;                         // [1]
   uint32_t* s_mask = s_tmem + 1;                                   // [2] active-offset mask of the producers' tile (by parity)
   uint64_t* res_bar = (uint64_t*)(s_mask + 2 + 1);                 // [4] residual rows landed (one per epilogue warp), 8-byte aligned
+  uint64_t* tstart_bar = res_bar + 4;                              // [2] tile id of an accumulator set published (MMA warp -> epilogue)
+  int* s_next = (int*)(tstart_bar + 2);                            // [1] next ticket of this CTA (-1: none), producers only
+  int* s_stage_tile = s_next + 2;                                  // [MAX_STAGES] tile id carried by a tile's first stage
+  int* s_acc_tile = s_stage_tile + MAX_STAGES;                     // [2] tile id held by each accumulator set (-1: no more work)
   const int stg_pitch = p.c_out * 2 + 16;                          // staged epilogue: row pitch (+16 B: conflict-free 128-bit LDS)
-  uint8_t* s_stage = tail + (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 1023) & ~(size_t)1023);
+  uint8_t* s_stage = tail + (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 256 + 1023) & ~(size_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out;
   const int64_t num_tiles = (n_out + TM - 1) / TM;
   const int kc_blocks = p.c_in / BK;
+  // Work is handed out as tickets.  Static mode: CTA b owns tickets b, b + grid, ...  and ticket == tile.  Dynamic mode
+  // (p.sched): the first ticket is b, later ones come from a global counter, and tickets walk the tiles from the LAST one
+  // down -- with mask-sorted rows the late tiles carry the most offsets, so the expensive tiles start first and the cheap
+  // ones fill the tail (longest-processing-time order).
+  auto tile_of = [&](int64_t ticket) -> int64_t { return p.sched ? num_tiles - 1 - ticket : ticket; };
 
   // ---------------- one-time setup
   for (int i = threadIdx.x; i < 256; i += NUM_THREADS) {
@@ -126,6 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tstart_bar[a], 1);
       mbar_init(&tempty_bar[a], NUM_EPI_THREADS);   // every epilogue thread arrives once per tile
     }
     fence_barrier_init();
@@ -146,6 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     // One block = 128 gathered rows x BK channels of one offset (+ its weight tile).  A stage carries up to p.nb
     // blocks; the slot is acquired at its first block and published (hardware arrive) after its last.
     int blk = 0, blk_goal = 0;                            // blocks issued / wanted in the open stage
+    int cur_tile = 0;                                     // tile being issued (published with its first stage)
     constexpr int PASSES = TILE_M / ROWS_PER_PASS;
     auto issue = [&](const int (&nbv)[T][PASSES], int cb, int b_col, int b_row, bool first, int remaining) {
       uint8_t* st_base = ring + (size_t)stage * stage_bytes;
@@ -154,6 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         mbar_wait(&empty_bar[stage], ph ^ 1);             // slot free (first lap passes immediately)
         if (t == 0) {
           s_flags[stage] = (first ? 1u : 0u) | (remaining <= p.nb ? 2u : 0u) | ((uint32_t)blk_goal << 8);
+          s_stage_tile[stage] = cur_tile;
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(b_bytes * blk_goal));
         }
       }
@@ -191,10 +208,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
     };
     const uint32_t n_in_u = p.n_in > 0x7fffffff ? 0x7fffffffu : (uint32_t)p.n_in;
-    if ((int64_t)blockIdx.x < num_tiles) fetch_indices(blockIdx.x);
+    int64_t cur = blockIdx.x;                             // this CTA's current ticket
+    if (cur < num_tiles) fetch_indices(tile_of(cur));
     if (t < 2) s_mask[t] = 0;
+    unsigned ahead = 0;                                   // thread 0: ticket drawn one tile ahead (its latency is hidden)
+    if (t == 0 && p.sched && cur < num_tiles) ahead = atomicAdd(&p.sched[0], 1u);
     uint32_t par = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, par ^= 1) {
+    for (; cur < num_tiles; par ^= 1) {
+      const int64_t tile = tile_of(cur);
+      cur_tile = (int)tile;
       // (A) every producer has finished reading s_idx / s_mask[par^1] of the previous tile
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t my_bits = 0;
@@ -209,12 +231,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
       const uint32_t my_mask = __reduce_or_sync(0xffffffffu, my_bits);   // one warp reduction instead of a vote per offset
       if (lane == 0 && my_mask) atomicOr(&s_mask[par], my_mask);
-      if (t == 0) s_mask[par ^ 1] = 0;
+      if (t == 0) {
+        s_mask[par ^ 1] = 0;
+        const int64_t nx = p.sched ? (int64_t)gridDim.x + ahead : cur + gridDim.x;
+        s_next[0] = nx < num_tiles ? (int)nx : -1;
+        if (p.sched && nx < num_tiles) ahead = atomicAdd(&p.sched[0], 1u);
+      }
       // (B) indices and mask of this tile are complete
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t mask = s_mask[par];
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
-      if (tile + gridDim.x < num_tiles) fetch_indices(tile + gridDim.x);
+      const int nx = s_next[0];                           // stable until barrier (A) of the next tile
+      if (nx >= 0) fetch_indices(tile_of(nx));
       int nbv[T][PASSES];                                 // neighbour rows of this thread's gather slots, one offset at a time
       if (p.pack8) {
         const int nkb = (p.k_vol * 8 + BK - 1) / BK;
@@ -240,15 +268,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             issue(nbv, cb, cb * BK, k * p.c_out, first, remaining);
         }
       }
+      cur = nx >= 0 ? nx : num_tiles;
     }
+    // sentinel stage: no data, flag bit 2 tells the MMA warp (and through it the epilogue) that this CTA is out of work
+    mbar_wait(&empty_bar[stage], ph ^ 1);
+    if (t == 0) {
+      s_flags[stage] = 4u;
+      mbar_arrive(&full_bar[stage]);                      // stands in for the expect_tx arrival of a normal stage
+    }
+    mbar_arrive(&full_bar[stage]);
     cp_async_wait<0>();                                   // nothing of ours may still be in flight at teardown
   } else if (warp == MMA_WARP) {
     // =============================================================== MMA ISSUER
     const uint32_t idesc = make_idesc(TILE_M, p.c_out, p.is_bf16 ? 1 : 0);
     int stage = 0;
     uint32_t ph = 0;
-    int64_t tcount = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    bool more = true;
+    for (int64_t tcount = 0; more; ++tcount) {
       const int acc = (int)(tcount % p.n_acc);
       const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);            // epilogue drained this accumulator set
@@ -259,7 +295,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         fence_proxy_async();                              // gathered rows were written through the generic proxy (cp.async)
         tc_fence_after();
         const uint32_t flags = s_flags[stage];
+        if (flags & 4u) {                                 // sentinel: hand the "no more work" mark to the epilogue
+          if (lane == 0) {
+            s_acc_tile[acc] = -1;
+            mbar_arrive(&tstart_bar[acc]);
+          }
+          more = false;
+          break;
+        }
         if (lane == 0) {
+          if (flags & 1u) {                               // first stage of a tile: publish which tile this accumulator holds
+            s_acc_tile[acc] = s_stage_tile[stage];
+            mbar_arrive(&tstart_bar[acc]);
+          }
           const uint32_t st_u32 = smem_u32(ring + (size_t)stage * stage_bytes);
           const int nblk = (int)(flags >> 8);
           for (int j = 0; j < nblk; ++j) {
@@ -297,9 +345,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       uint32_t res_ph = 0;
       int buf = 0;
       int64_t tcount = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      for (;; ++tcount) {
         const int acc = (int)(tcount % p.n_acc);
         const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+        mbar_wait(&tstart_bar[acc], acc_ph);              // the MMA warp has published this accumulator's tile
+        const int64_t tile = s_acc_tile[acc];
+        if (tile < 0) break;
         for (int sub = 0; sub < T; ++sub) {
           const int64_t row0 = tile * TM + sub * TILE_M + warp * 32;
           const bool any_live = row0 < n_out;
@@ -385,9 +436,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       const uint32_t row_bytes = (uint32_t)p.c_out * 2;
       uint32_t res_ph = 0;
       int64_t tcount = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      for (;; ++tcount) {
         const int acc = (int)(tcount % p.n_acc);
         const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+        mbar_wait(&tstart_bar[acc], acc_ph);              // the MMA warp has published this accumulator's tile
+        const int64_t tile = s_acc_tile[acc];
+        if (tile < 0) break;
         for (int sub = 0; sub < T; ++sub) {
           const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
           const bool live = o < n_out;
@@ -463,9 +517,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     } else {
     int64_t tcount = 0;
     const int out_es = (p.out_dtype == LB_DT_F32) ? 4 : 2;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    for (;; ++tcount) {
       const int acc = (int)(tcount % p.n_acc);
       const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+      mbar_wait(&tstart_bar[acc], acc_ph);                // the MMA warp has published this accumulator's tile
+      const int64_t tile = s_acc_tile[acc];
+      if (tile < 0) break;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       for (int sub = 0; sub < T; ++sub) {
@@ -537,6 +594,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  // the last CTA to retire re-arms the scheduler for the next launch on this stream (nobody draws tickets any more)
+  if (p.sched && threadIdx.x == 0 && atomicAdd(&p.sched[1], 1u) == gridDim.x - 1) {
+    p.sched[0] = 0;
+    p.sched[1] = 0;
+    __threadfence();
+  }
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -570,9 +633,25 @@ int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
 
 static size_t tail_bytes(int T) {
   // indices + scale/shift + ring/accumulator barriers + flags + (tmem ptr, masks, 4 residual barriers), rounded for staging
-  return (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 64 + 1023) & ~(size_t)1023);
+  return (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 256 + 1023) & ~(size_t)1023);
 }
 static size_t staging_bytes(int c_out, int bufs = 1) { return (size_t)bufs * 4 * 32 * (c_out * 2 + 16); }
+
+// One 2-word scheduler cell per (device, stream): launches on a stream are ordered, and the kernel leaves the cell zeroed.
+static unsigned* sched_cell(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, unsigned*> cells;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cells.find({dev, st});
+  if (it != cells.end()) return it->second;
+  unsigned* cell = nullptr;
+  if (cudaMalloc(&cell, 256) != cudaSuccess) return nullptr;
+  if (cudaMemset(cell, 0, 256) != cudaSuccess) { cudaFree(cell); return nullptr; }
+  cells[{dev, st}] = cell;
+  return cell;
+}
 
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const bool pack8 = (a.flags & LB_CONV_PACK8) != 0;
@@ -677,6 +756,8 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.stages = stages;
   p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
+  static const bool static_tiles = getenv("LIDAL_STATIC_TILES") != nullptr;   // A/B switch
+  p.sched = static_tiles ? nullptr : sched_cell(st);
   const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + (p.staged ? staging_bytes(a.c_out, p.stg_bufs) : 0) + 1024;
   int64_t tiles = (a.n_out + (int64_t)T * TILE_M - 1) / ((int64_t)T * TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
