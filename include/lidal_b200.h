@@ -81,6 +81,7 @@ int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t* nbmaps, i
  * take part, i.e. for k = 27 the three most frequent offsets do not influence the order) and the permuted
  * table nbr_sorted[k][j] = nbr[k][perm[j]].  Use as  args.nbr = nbr_sorted, args.out_rows = perm. */
 #define LB_MASK_KEY_BITS 24
+#define LB_MASK_CHUNK_SHIFT 0   /* > 0: group rows into chunks of 2^shift consecutive rows before the mask (L2 locality) */
 size_t lb_kmap_sort_ws_bytes(int64_t n_out);
 int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm, int32_t* nbr_sorted,
                          void* ws, size_t ws_bytes, void* stream);

@@ -280,13 +280,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     cp_async_wait<0>();                                   // nothing of ours may still be in flight at teardown
   } else if (warp == MMA_WARP) {
     // =============================================================== MMA ISSUER
+    // The issuing warp is a single instruction stream: every instruction here is on the critical path of every stage,
+    // so descriptors are advanced with 32-bit adds on their low word and nothing is rebuilt per stage.
     const uint32_t idesc = make_idesc(TILE_M, p.c_out, p.is_bf16 ? 1 : 0);
+    const uint32_t desc_hi = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);             // bits 32-45 SBO, 46 version, 61-63 swizzle
+    const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);      // bits 0-13 address >> 4, 16-29 LBO = 1
+    const uint32_t stage_units = (uint32_t)stage_bytes >> 4, b_units = (uint32_t)(p.nb * a_blk) >> 4;
+    constexpr uint32_t A_UNITS = A_BYTES >> 4;
     int stage = 0;
-    uint32_t ph = 0;
+    uint32_t ph = 0, st_lo = ring_lo;
     bool more = true;
     for (int64_t tcount = 0; more; ++tcount) {
-      const int acc = (int)(tcount % p.n_acc);
-      const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+      const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
+      const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);            // epilogue drained this accumulator set
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * p.c_out);
@@ -308,24 +314,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             s_acc_tile[acc] = s_stage_tile[stage];
             mbar_arrive(&tstart_bar[acc]);
           }
-          const uint32_t st_u32 = smem_u32(ring + (size_t)stage * stage_bytes);
-          const int nblk = (int)(flags >> 8);
-          for (int j = 0; j < nblk; ++j) {
-            const uint64_t b_desc = make_smem_desc(st_u32 + p.nb * a_blk + j * b_pad, SBO, LAYOUT);
+          const uint32_t keep = (flags & 1u) ? 0u : 1u;   // the tile's first MMA overwrites the accumulator
+          const uint32_t b_lo = st_lo + b_units;
 #pragma unroll
-            for (int sub = 0; sub < T; ++sub) {         // every sub-tile reuses the same weight tile
-              const uint64_t a_desc = make_smem_desc(st_u32 + j * a_blk + sub * A_BYTES, SBO, LAYOUT);
+          for (int sub = 0; sub < T; ++sub) {             // every sub-tile reuses the same weight tile
 #pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk)        // +32 bytes along K inside the swizzle atom = +2 in the address field
-                umma_f16(d_tmem + (uint32_t)(sub * p.c_out), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                         ((flags & 1u) && j == 0 && kk == 0) ? 0u : 1u);
-            }
+            for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
+              umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), st_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
+                            b_lo + (uint32_t)kk * 2u, desc_hi, idesc, kk == 0 ? keep : 1u);
           }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
           if (flags & 2u) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        st_lo += stage_units;
+        if (++stage == p.stages) { stage = 0; ph ^= 1; st_lo = ring_lo; }
         if (flags & 2u) break;
       }
     }
@@ -346,8 +349,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       int buf = 0;
       int64_t tcount = 0;
       for (;; ++tcount) {
-        const int acc = (int)(tcount % p.n_acc);
-        const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+        const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
+        const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
         mbar_wait(&tstart_bar[acc], acc_ph);              // the MMA warp has published this accumulator's tile
         const int64_t tile = s_acc_tile[acc];
         if (tile < 0) break;
@@ -437,8 +440,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       uint32_t res_ph = 0;
       int64_t tcount = 0;
       for (;; ++tcount) {
-        const int acc = (int)(tcount % p.n_acc);
-        const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+        const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
+        const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
         mbar_wait(&tstart_bar[acc], acc_ph);              // the MMA warp has published this accumulator's tile
         const int64_t tile = s_acc_tile[acc];
         if (tile < 0) break;
@@ -518,8 +521,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     int64_t tcount = 0;
     const int out_es = (p.out_dtype == LB_DT_F32) ? 4 : 2;
     for (;; ++tcount) {
-      const int acc = (int)(tcount % p.n_acc);
-      const uint32_t acc_ph = (uint32_t)((tcount / p.n_acc) & 1);
+      const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
+      const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
       mbar_wait(&tstart_bar[acc], acc_ph);                // the MMA warp has published this accumulator's tile
       const int64_t tile = s_acc_tile[acc];
       if (tile < 0) break;

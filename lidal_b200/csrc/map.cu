@@ -729,8 +729,11 @@ __global__ void ks_bitpos(const unsigned* __restrict__ counts, int k, int* __res
 }
 // `drop`: the most frequent offsets (lowest key bits) are left out of the key - nearly every tile needs them anyway, and a
 // 27-offset map then sorts in three 8-bit passes instead of four.
+// `chunk_shift` > 0: rows are first grouped into chunks of 2^chunk_shift consecutive rows (key = chunk : mask) -- when the
+// row order is spatially coherent (scan order), the tiles in flight then gather from a slice of the input that stays in
+// L2 instead of every mask group sweeping the whole feature matrix.
 __global__ void ks_keys(const uint32_t* __restrict__ masks, int64_t n, int k, const int* __restrict__ bitpos, int drop,
-                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                        int chunk_shift, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   __shared__ int s_pos[32];
   if (threadIdx.x < 32) s_pos[threadIdx.x] = threadIdx.x < k ? bitpos[threadIdx.x] : 0;
   __syncthreads();
@@ -738,7 +741,9 @@ __global__ void ks_keys(const uint32_t* __restrict__ masks, int64_t n, int k, co
     const uint32_t nat = masks[o];
     uint64_t m = 0;
     for (int j = 0; j < k; ++j) m |= (uint64_t)((nat >> j) & 1u) << s_pos[j];
-    keys[o] = m >> drop;
+    m >>= drop;
+    if (chunk_shift > 0) m |= (uint64_t)(o >> chunk_shift) << (k - drop);
+    keys[o] = m;
     vals[o] = (uint32_t)o;
   }
 }
@@ -773,8 +778,12 @@ extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t 
   ks_bitpos<<<1, 32, 0, st>>>(counts, k, bitpos); LB_LAUNCHED(1);
   static const int key_bits = getenv("LIDAL_MASK_KEY_BITS") ? atoi(getenv("LIDAL_MASK_KEY_BITS")) : LB_MASK_KEY_BITS;
   const int drop = (key_bits > 0 && k > key_bits) ? k - key_bits : 0;
-  ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(masks, n_out, k, bitpos, drop, keys, (uint32_t*)perm); LB_LAUNCHED(1);
-  int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k - drop, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
+  static const int chunk_shift = getenv("LIDAL_MASK_CHUNK_SHIFT") ? atoi(getenv("LIDAL_MASK_CHUNK_SHIFT")) : LB_MASK_CHUNK_SHIFT;
+  int chunk_bits = 0;
+  if (chunk_shift > 0)
+    while (((n_out - 1) >> chunk_shift) >> chunk_bits) ++chunk_bits;
+  ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(masks, n_out, k, bitpos, drop, chunk_bits ? chunk_shift : 0, keys, (uint32_t*)perm); LB_LAUNCHED(1);
+  int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k - drop + chunk_bits, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
   if (rc != LB_OK) return rc;
   ks_permute<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, perm, nbr_sorted); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
