@@ -309,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           more = false;
           break;
         }
-        if (lane == 0) {
+        if (elect_one()) {
           if (flags & 1u) {                               // first stage of a tile: publish which tile this accumulator holds
             s_acc_tile[acc] = s_stage_tile[stage];
             mbar_arrive(&tstart_bar[acc]);
