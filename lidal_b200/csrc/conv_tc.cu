@@ -158,41 +158,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     if (t == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&w_map) : "memory");
     int stage = 0;                                        // ring position of the open stage
     uint32_t ph = 0;
-    // One block = 128 gathered rows x BK channels of one offset (+ its weight tile).  A stage carries up to p.nb
-    // blocks; the slot is acquired at its first block and published (hardware arrive) after its last.
-    int blk = 0, blk_goal = 0;                            // blocks issued / wanted in the open stage
+    // One stage = 128*T gathered rows x BK channels of one offset + its weight tile.  Every instruction of this path
+    // runs once per stage in each of the 8 producer warps, so it is kept minimal: running stage address, precomputed
+    // per-thread smem offsets, no per-stage bookkeeping beyond the flag word.
     int cur_tile = 0;                                     // tile being issued (published with its first stage)
     constexpr int PASSES = TILE_M / ROWS_PER_PASS;
-    auto issue = [&](const int (&nbv)[T][PASSES], int cb, int b_col, int b_row, bool first, int remaining) {
-      uint8_t* st_base = ring + (size_t)stage * stage_bytes;
-      if (blk == 0) {
-        blk_goal = remaining < p.nb ? remaining : p.nb;
-        mbar_wait(&empty_bar[stage], ph ^ 1);             // slot free (first lap passes immediately)
-        if (t == 0) {
-          s_flags[stage] = (first ? 1u : 0u) | (remaining <= p.nb ? 2u : 0u) | ((uint32_t)blk_goal << 8);
-          s_stage_tile[stage] = cur_tile;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(b_bytes * blk_goal));
-        }
+    const uint32_t ring_u32 = smem_u32(ring);
+    uint32_t st_u32 = ring_u32;                           // smem address of the open stage
+    const int64_t ld_in_b = p.ld_in * 2;
+    const char* in_col = p.in + (p.pack8 ? 0 : chunk * 16);
+    auto issue = [&](const int (&nbv)[T][PASSES], int cb, int b_col, int b_row, uint32_t first_last) {
+      mbar_wait(&empty_bar[stage], ph ^ 1);               // slot free (first lap passes immediately)
+      if (t == 0) {
+        s_flags[stage] = first_last | (1u << 8);
+        s_stage_tile[stage] = cur_tile;
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+        tma_load_2d(st_u32 + a_blk, &w_map, b_col, b_row, &full_bar[stage]);
       }
-      if (t == 0) tma_load_2d(smem_u32(st_base + p.nb * a_blk + blk * b_pad), &w_map, b_col, b_row, &full_bar[stage]);
+      const char* in_cb = in_col + (p.pack8 ? 0 : cb * (BK * 2));
 #pragma unroll
       for (int sub = 0; sub < T; ++sub) {
-        const uint32_t a_u32 = smem_u32(st_base + blk * a_blk + sub * A_BYTES);
 #pragma unroll
         for (int i = 0; i < PASSES; ++i) {
           const int r = row0 + i * ROWS_PER_PASS;
           const int nb = nbv[sub][i];
           // pack8: 16 bytes = the 8 (padded) channels of one offset; otherwise channels [cb*BK + chunk*8, +8) of the row
-          const char* src = p.in + ((int64_t)(nb >= 0 ? nb : 0) * p.ld_in + (p.pack8 ? 0 : cb * BK + chunk * 8)) * 2;
+          const char* src = in_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b;
           const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
-          cp_async16(a_u32 + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
+          cp_async16(st_u32 + sub * A_BYTES + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
         }
       }
-      if (++blk == blk_goal) {
-        cp_async_arrive_noinc(&full_bar[stage]);          // asynchronous: fires when this thread's copies have landed
-        blk = 0;
-        if (++stage == p.stages) { stage = 0; ph ^= 1; }
-      }
+      cp_async_arrive_noinc(&full_bar[stage]);            // asynchronous: fires when this thread's copies have landed
+      st_u32 += stage_bytes;
+      if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
     };
     // Neighbour indices of the NEXT tile are fetched into registers while the current tile's stages are being issued
     // (27 independent loads in flight), so the tile prologue never waits on global memory.
@@ -239,9 +237,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
       // (B) indices and mask of this tile are complete
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
-      uint32_t mask = s_mask[par];
+      uint32_t mask = __reduce_or_sync(0xffffffffu, s_mask[par]);   // same value in every lane; REDUX makes it provably uniform
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
-      const int nx = s_next[0];                           // stable until barrier (A) of the next tile
+      const int nx = (int)__reduce_or_sync(0xffffffffu, (uint32_t)s_next[0]);   // stable until barrier (A) of the next tile
       if (nx >= 0) fetch_indices(tile_of(nx));
       int nbv[T][PASSES];                                 // neighbour rows of this thread's gather slots, one offset at a time
       if (p.pack8) {
@@ -253,7 +251,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < PASSES; ++i)
               nbv[sub][i] = kk < p.k_vol ? s_idx[kk * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS] : -1;
-          issue(nbv, kb, kb * BK, 0, kb == 0, nkb - kb);
+          issue(nbv, kb, kb * BK, 0, (kb == 0 ? 1u : 0u) | (kb == nkb - 1 ? 2u : 0u));
         }
       } else {
         int remaining = __popc(mask) * kc_blocks;
@@ -265,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < PASSES; ++i) nbv[sub][i] = s_idx[k * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS];
           for (int cb = 0; cb < kc_blocks; ++cb, --remaining, first = false)
-            issue(nbv, cb, cb * BK, k * p.c_out, first, remaining);
+            issue(nbv, cb, cb * BK, k * p.c_out, (first ? 1u : 0u) | (remaining == 1 ? 2u : 0u));
         }
       }
       cur = nx >= 0 ? nx : num_tiles;
@@ -300,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         mbar_wait(&full_bar[stage], ph);
         fence_proxy_async();                              // gathered rows were written through the generic proxy (cp.async)
         tc_fence_after();
-        const uint32_t flags = s_flags[stage];
+        const uint32_t flags = __reduce_or_sync(0xffffffffu, s_flags[stage]);     // uniform for the compiler
         if (flags & 4u) {                                 // sentinel: hand the "no more work" mark to the epilogue
           if (lane == 0) {
             s_acc_tile[acc] = -1;
