@@ -690,14 +690,16 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.scale = a.scale; p.shift = a.shift; p.residual = (const char*)a.residual; p.ld_res = a.ld_res;
   p.out_dtype = a.out_dtype; p.relu = (a.flags & LB_CONV_RELU) ? ((a.flags & LB_CONV_RELU_FIRST) ? 2 : 1) : 0; p.is_bf16 = a.act_dtype == LB_DT_BF16;
   // 256-row CTA tiles (two accumulators sharing every weight tile) when (a) there are enough rows to keep every SM
-  // busy and (b) the doubled A operand still leaves a deep (>= 6 stage) ring -- measured on B200: -15..-19 % on the
-  // 32/96-channel layers of the two finest levels, +13 % (worse) on 128->128 where the ring would drop to 4 stages.
+  // busy (>= 8 waves of 128-row tiles) and (b) the doubled A operand still leaves a >= 4 stage ring.  The kernel is bound
+  // by per-stage issue overhead (producer + MMA warps), so halving the stage count per row wins wherever it fits.
   const int64_t tiles128 = (a.n_out + TILE_M - 1) / TILE_M;
   int T = 1;
   {
     const size_t blk2 = (size_t)2 * TILE_M * bk * 2 + (((size_t)a.c_out * bk * 2 + 1023) & ~(size_t)1023);
     const size_t budget2 = 227 * 1024 - 1024 - tail_bytes(2);
-    if (tiles128 >= (int64_t)8 * sm_count() && budget2 / blk2 >= 6 && 2 * a.c_out <= 512) T = 2;
+    static const int t2_min_stages = getenv("LIDAL_T2_MIN_STAGES") ? atoi(getenv("LIDAL_T2_MIN_STAGES")) : 4;
+    static const int t2_min_waves = getenv("LIDAL_T2_MIN_WAVES") ? atoi(getenv("LIDAL_T2_MIN_WAVES")) : 8;
+    if (tiles128 >= (int64_t)t2_min_waves * sm_count() && budget2 / blk2 >= (size_t)t2_min_stages && 2 * a.c_out <= 512) T = 2;
   }
   // a single-block 1x1 layer with a wide output is pure epilogue: 128-row tiles keep two accumulator sets and leave
   // room for double-buffered staging
