@@ -85,6 +85,10 @@ int lb_kmap_compact(const int32_t* nbr, int64_t n_out, int k, int32_t* nbmaps, i
 size_t lb_kmap_sort_ws_bytes(int64_t n_out);
 int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm, int32_t* nbr_sorted,
                          void* ws, size_t ws_bytes, void* stream);
+/* Same, with an explicit row stride for the permuted table (nbr_sorted[k][j] at k * sorted_ld + j).  A stride that is a
+ * multiple of 4 (16-byte aligned rows) lets lb_conv_fwd read the table with 128-bit loads. */
+int lb_kmap_sort_by_mask_ld(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm, int32_t* nbr_sorted,
+                            int64_t sorted_ld, void* ws, size_t ws_bytes, void* stream);
 
 /* Per-offset inverse of a neighbour table (transposed convolution / dgrad roles):
  * nbr int32 [k, nbr_ld] with values in [0, n_in) or -1  ->  nbr_t int32 [k, n_in], nbr_t[k][nbr[k][o]] = o. */

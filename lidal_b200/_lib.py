@@ -50,6 +50,7 @@ SIGNATURES = {
     "lb_kmap_compact": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
     "lb_kmap_sort_ws_bytes": (sz, [i64]),
     "lb_kmap_sort_by_mask": (i32, [vp, i64, i64, i32, vp, vp, vp, sz, vp]),
+    "lb_kmap_sort_by_mask_ld": (i32, [vp, i64, i64, i32, vp, vp, i64, vp, sz, vp]),
     "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
     "lb_unique_ws_bytes": (sz, [i64]),
     "lb_unique_i64": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, sz, vp]),

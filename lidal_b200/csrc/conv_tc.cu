@@ -194,15 +194,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     };
     // Neighbour indices of the NEXT tile are fetched into registers while the current tile's stages are being issued
     // (27 independent loads in flight), so the tile prologue never waits on global memory.
-    int nb_reg[KMAX];
-    const bool idx_thread = t < TM;                       // thread t stages the indices of tile row t (rows 0..TM-1)
+    // Work item q = (offset k, group of 4 consecutive tile rows): one 16-byte load from the table (when its rows are
+    // 16-byte aligned: nbr_ld % 4 == 0), one 16-byte store into s_idx -- a quarter of the instructions of a load per row.
+    constexpr int R4 = TM / 4;                            // 4-row groups per offset
+    constexpr int ITEMS = (KMAX * R4 + NUM_PROD_THREADS - 1) / NUM_PROD_THREADS;
+    int4 nb_reg[ITEMS];
+    const bool vec_ok = p.nbr && (p.nbr_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.nbr) & 15) == 0;
     auto fetch_indices = [&](int64_t tile) {
-      const int64_t o = tile * TM + t;
+      const int64_t o0 = tile * TM;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        int nb = -1;
-        if (idx_thread && k < p.k_vol && o < n_out) nb = p.nbr ? __ldg(&p.nbr[(int64_t)k * p.nbr_ld + o]) : (int)o;
-        nb_reg[k] = nb;
+      for (int j = 0; j < ITEMS; ++j) {
+        const int q = t + j * NUM_PROD_THREADS;
+        const int k = q / R4;
+        const int64_t o = o0 + (q % R4) * 4;
+        int4 v = make_int4(-1, -1, -1, -1);
+        if (k < KMAX && k < p.k_vol && o < n_out) {
+          if (!p.nbr) {
+            v.x = (int)o;
+            if (o + 1 < n_out) v.y = (int)o + 1;
+            if (o + 2 < n_out) v.z = (int)o + 2;
+            if (o + 3 < n_out) v.w = (int)o + 3;
+          } else {
+            const int* src = p.nbr + (int64_t)k * p.nbr_ld + o;
+            if (vec_ok && o + 3 < n_out) {
+              v = __ldg(reinterpret_cast<const int4*>(src));
+            } else {
+              v.x = __ldg(src);
+              if (o + 1 < n_out) v.y = __ldg(src + 1);
+              if (o + 2 < n_out) v.z = __ldg(src + 2);
+              if (o + 3 < n_out) v.w = __ldg(src + 3);
+            }
+          }
+        }
+        nb_reg[j] = v;
       }
     };
     const uint32_t n_in_u = p.n_in > 0x7fffffff ? 0x7fffffffu : (uint32_t)p.n_in;
@@ -219,12 +243,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t my_bits = 0;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k < p.k_vol) {
-          const int nb = nb_reg[k];
-          const bool ok = (uint32_t)nb < n_in_u;          // one compare rejects both "no neighbour" (-1) and out-of-range rows
-          if (idx_thread) s_idx[k * TM + t] = ok ? nb : -1;   // row t of the tile == sub-tile t / 128, row t % 128
-          if (ok) my_bits |= 1u << k;
+      for (int j = 0; j < ITEMS; ++j) {
+        const int q = t + j * NUM_PROD_THREADS;
+        const int k = q / R4;
+        if (k < KMAX && k < p.k_vol) {
+          int4 v = nb_reg[j];
+          // one unsigned compare rejects both "no neighbour" (-1) and out-of-range rows
+          const bool ox = (uint32_t)v.x < n_in_u, oy = (uint32_t)v.y < n_in_u, oz = (uint32_t)v.z < n_in_u, ow = (uint32_t)v.w < n_in_u;
+          v.x = ox ? v.x : -1; v.y = oy ? v.y : -1; v.z = oz ? v.z : -1; v.w = ow ? v.w : -1;
+          *reinterpret_cast<int4*>(&s_idx[k * TM + (q % R4) * 4]) = v;
+          if (ox | oy | oz | ow) my_bits |= 1u << k;
         }
       }
       const uint32_t my_mask = __reduce_or_sync(0xffffffffu, my_bits);   // one warp reduction instead of a vote per offset

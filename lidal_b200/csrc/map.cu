@@ -748,12 +748,12 @@ __global__ void ks_keys(const uint32_t* __restrict__ masks, int64_t n, int k, co
   }
 }
 __global__ void ks_permute(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, const int* __restrict__ perm,
-                           int* __restrict__ out) {
+                           int* __restrict__ out, int64_t out_ld) {
   const int64_t total = n * k;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int j = (int)(t / n);
     int64_t i = t - (int64_t)j * n;
-    out[t] = __ldg(&nbr[(int64_t)j * ld + __ldg(&perm[i])]);
+    out[(int64_t)j * out_ld + i] = __ldg(&nbr[(int64_t)j * ld + __ldg(&perm[i])]);
   }
 }
 }  // namespace lb
@@ -763,8 +763,12 @@ extern "C" size_t lb_kmap_sort_ws_bytes(int64_t n) {
 }
 extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm,
                                     int32_t* nbr_sorted, void* ws, size_t ws_bytes, void* stream) {
-  LB_CHECK_ARG(n_out >= 0 && k > 0 && k <= 32 && nbr_ld >= n_out && ws, "bad arguments");
-  if (ws_bytes < lb_kmap_sort_ws_bytes(n_out)) { set_error("lb_kmap_sort_by_mask: workspace too small"); return LB_ECAP; }
+  return lb_kmap_sort_by_mask_ld(nbr, nbr_ld, n_out, k, perm, nbr_sorted, n_out, ws, ws_bytes, stream);
+}
+extern "C" int lb_kmap_sort_by_mask_ld(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm,
+                                       int32_t* nbr_sorted, int64_t sorted_ld, void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n_out >= 0 && k > 0 && k <= 32 && nbr_ld >= n_out && sorted_ld >= n_out && ws, "bad arguments");
+  if (ws_bytes < lb_kmap_sort_ws_bytes(n_out)) { set_error("lb_kmap_sort_by_mask_ld: workspace too small"); return LB_ECAP; }
   if (n_out == 0) return LB_OK;
   LB_CHECK_ARG(nbr && perm && nbr_sorted, "null pointer");
   cudaStream_t st = as_stream(stream);
@@ -785,7 +789,7 @@ extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t 
   ks_keys<<<grid_for(n_out, 256), 256, 0, st>>>(masks, n_out, k, bitpos, drop, chunk_bits ? chunk_shift : 0, keys, (uint32_t*)perm); LB_LAUNCHED(1);
   int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k - drop + chunk_bits, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
   if (rc != LB_OK) return rc;
-  ks_permute<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, perm, nbr_sorted); LB_LAUNCHED(1);
+  ks_permute<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, perm, nbr_sorted, sorted_ld); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -127,10 +127,12 @@ def _mask_sorted(nbr):
     """(nbr_sorted, perm): rows grouped by neighbour mask so 128-row tiles skip absent offsets (lb_kmap_sort_by_mask)."""
     k, n = nbr.shape
     perm = torch.empty(n, dtype=torch.int, device=nbr.device)
-    out = torch.empty_like(nbr)
+    ld = (n + 3) // 4 * 4                # 16-byte aligned table rows: the conv kernel reads them with 128-bit loads
+    out = torch.empty((k, ld), dtype=torch.int, device=nbr.device)[:, :n]
     nbytes = L.lib().lb_kmap_sort_ws_bytes(n)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=nbr.device)
-    L.check(L.lib().lb_kmap_sort_by_mask(L.ptr(nbr), nbr.stride(0), n, k, L.ptr(perm), L.ptr(out), L.ptr(ws), nbytes, L.stream()))
+    L.check(L.lib().lb_kmap_sort_by_mask_ld(L.ptr(nbr), nbr.stride(0), n, k, L.ptr(perm), L.ptr(out), ld, L.ptr(ws), nbytes,
+                                            L.stream()))
     return out, perm
 
 
