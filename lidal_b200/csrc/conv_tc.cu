@@ -161,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     // One stage = 128*T gathered rows x BK channels of one offset + its weight tile.  Every instruction of this path
     // runs once per stage in each of the 8 producer warps, so it is kept minimal: running stage address, precomputed
     // per-thread smem offsets, no per-stage bookkeeping beyond the flag word.
-    int cur_tile = 0;                                     // tile being issued (published with its first stage)
+    int cur_word = 0;                                     // tile being issued | its stage count << 24 (published with its first stage)
     constexpr int PASSES = TILE_M / ROWS_PER_PASS;
     const uint32_t ring_u32 = smem_u32(ring);
     uint32_t st_u32 = ring_u32;                           // smem address of the open stage
@@ -170,8 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     auto issue = [&](const int (&nbv)[T][PASSES], int cb, int b_col, int b_row, uint32_t first_last) {
       mbar_wait(&empty_bar[stage], ph ^ 1);               // slot free (first lap passes immediately)
       if (t == 0) {
-        s_flags[stage] = first_last | (1u << 8);
-        s_stage_tile[stage] = cur_tile;
+        if (first_last & 1u) s_stage_tile[stage] = cur_word;     // tile id | stage count << 24, read once per tile
         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
         tma_load_2d(st_u32 + a_blk, &w_map, b_col, b_row, &full_bar[stage]);
       }
@@ -238,7 +237,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     uint32_t par = 0;
     for (; cur < num_tiles; par ^= 1) {
       const int64_t tile = tile_of(cur);
-      cur_tile = (int)tile;
       // (A) every producer has finished reading s_idx / s_mask[par^1] of the previous tile
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
       uint32_t my_bits = 0;
@@ -272,6 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       int nbv[T][PASSES];                                 // neighbour rows of this thread's gather slots, one offset at a time
       if (p.pack8) {
         const int nkb = (p.k_vol * 8 + BK - 1) / BK;
+        cur_word = (int)((uint32_t)tile | ((uint32_t)nkb << 24));
         for (int kb = 0; kb < nkb; ++kb) {
           const int kk = kb * 8 + chunk;                  // chunk <-> offset 8*kb + chunk
 #pragma unroll
@@ -283,6 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         }
       } else {
         int remaining = __popc(mask) * kc_blocks;
+        cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
         bool first = true;
         for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
           if (!((mask >> k) & 1)) continue;
@@ -296,10 +296,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
       cur = nx >= 0 ? nx : num_tiles;
     }
-    // sentinel stage: no data, flag bit 2 tells the MMA warp (and through it the epilogue) that this CTA is out of work
+    // sentinel stage: no data, tile word -1 tells the MMA warp (and through it the epilogue) that this CTA is out of work
     mbar_wait(&empty_bar[stage], ph ^ 1);
     if (t == 0) {
-      s_flags[stage] = 4u;
+      s_stage_tile[stage] = -1;
       mbar_arrive(&full_bar[stage]);                      // stands in for the expect_tx arrival of a normal stage
     }
     mbar_arrive(&full_bar[stage]);
@@ -315,47 +315,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     constexpr uint32_t A_UNITS = A_BYTES >> 4;
     int stage = 0;
     uint32_t ph = 0, st_lo = ring_lo;
-    bool more = true;
-    for (int64_t tcount = 0; more; ++tcount) {
+    for (int64_t tcount = 0;; ++tcount) {
       const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
       const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);            // epilogue drained this accumulator set
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * p.c_out);
-      while (true) {
-        mbar_wait(&full_bar[stage], ph);
+      // first stage of the tile: its slot carries the tile word (tile id | stage count << 24; -1 = this CTA is done)
+      mbar_wait(&full_bar[stage], ph);
+      const uint32_t word = __reduce_or_sync(0xffffffffu, (uint32_t)s_stage_tile[stage]);   // uniform for the compiler
+      if (word == 0xffffffffu) {
+        if (lane == 0) {
+          s_acc_tile[acc] = -1;
+          mbar_arrive(&tstart_bar[acc]);
+        }
+        break;
+      }
+      const int n_st = (int)(word >> 24);
+      if (lane == 0) {
+        s_acc_tile[acc] = (int)(word & 0xffffffu);               // the epilogue learns its tile before the MMAs finish
+        mbar_arrive(&tstart_bar[acc]);
+      }
+      for (int e = 0; e < n_st; ++e) {
+        if (e) mbar_wait(&full_bar[stage], ph);
         fence_proxy_async();                              // gathered rows were written through the generic proxy (cp.async)
         tc_fence_after();
-        const uint32_t flags = __reduce_or_sync(0xffffffffu, s_flags[stage]);     // uniform for the compiler
-        if (flags & 4u) {                                 // sentinel: hand the "no more work" mark to the epilogue
-          if (lane == 0) {
-            s_acc_tile[acc] = -1;
-            mbar_arrive(&tstart_bar[acc]);
-          }
-          more = false;
-          break;
-        }
         if (elect_one()) {
-          if (flags & 1u) {                               // first stage of a tile: publish which tile this accumulator holds
-            s_acc_tile[acc] = s_stage_tile[stage];
-            mbar_arrive(&tstart_bar[acc]);
-          }
-          const uint32_t keep = (flags & 1u) ? 0u : 1u;   // the tile's first MMA overwrites the accumulator
           const uint32_t b_lo = st_lo + b_units;
 #pragma unroll
           for (int sub = 0; sub < T; ++sub) {             // every sub-tile reuses the same weight tile
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
               umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), st_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
-                            b_lo + (uint32_t)kk * 2u, desc_hi, idesc, kk == 0 ? keep : 1u);
+                            b_lo + (uint32_t)kk * 2u, desc_hi, idesc, (kk == 0 && e == 0) ? 0u : 1u);   // first MMA overwrites
           }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-          if (flags & 2u) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+          if (e == n_st - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
         __syncwarp();
         st_lo += stage_units;
         if (++stage == p.stages) { stage = 0; ph ^= 1; st_lo = ring_lo; }
-        if (flags & 2u) break;
       }
     }
   } else {
@@ -655,7 +654,7 @@ int conv_tc_pack8_supported(int k_vol, int c_in, int c_out, int act_dtype) {
 int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
   if (act_dtype != LB_DT_BF16 && act_dtype != LB_DT_F16) return 0;
   if (k_vol < 1 || k_vol > MAX_KVOL) return 0;
-  if (block_k_for(c_in) == 0) return 0;
+  if (block_k_for(c_in) == 0 || c_in > 512) return 0;   // a tile's stage count (<= 27 * c_in / 64) travels in 8 bits
   if (c_out % 32 != 0 || c_out < 32 || c_out > 256) return 0;
   return 1;
 }
