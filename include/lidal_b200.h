@@ -69,6 +69,13 @@ int lb_downsample(const int32_t* coords, int64_t n, const int32_t sample_stride[
 int lb_kmap_query(const void* table, size_t table_bytes, const int32_t* out_coords, int64_t n_out_cap,
                   const int32_t* n_out_dev, const int32_t* offsets, int k, int32_t* nbr, void* stream);
 
+/* Submanifold (stride-1) special case of lb_kmap_query: the table was built from `coords` itself and the offsets are
+ * point-symmetric (offsets[k-1-j] == -offsets[j], k odd -- true for get_kernel_offsets of an odd kernel).  Then
+ * nbr[j][o] = r  <=>  nbr[k-1-j][r] = o, so only (k+1)/2 offsets are probed and the rest is mirrored.  Same result as
+ * lb_kmap_query, bit for bit.  nbr int32 [k, nbr_ld]. */
+int lb_kmap_query_sym(const void* table, size_t table_bytes, const int32_t* coords, int64_t n, const int32_t* offsets, int k,
+                      int32_t* nbr, int64_t nbr_ld, void* stream);
+
 /* Compaction to the reference's (nbmaps, nbsizes): rows (in_idx, out_idx) enumerated k-major then o ascending.
  * nbmaps int32 [k*n_out,2] (worst case), nbsizes int32 [k], total device int32[1]. */
 size_t lb_kmap_compact_ws_bytes(int64_t n_out, int k);

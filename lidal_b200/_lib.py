@@ -46,6 +46,7 @@ SIGNATURES = {
     "lb_downsample_ws_bytes": (sz, [i64]),
     "lb_downsample": (i32, [vp, i64, C.POINTER(i32), i32, vp, vp, vp, sz, vp]),
     "lb_kmap_query": (i32, [vp, sz, vp, i64, vp, vp, i32, vp, vp]),
+    "lb_kmap_query_sym": (i32, [vp, sz, vp, i64, vp, i32, vp, i64, vp]),
     "lb_kmap_compact_ws_bytes": (sz, [i64, i32]),
     "lb_kmap_compact": (i32, [vp, i64, i32, vp, vp, vp, vp, sz, vp]),
     "lb_kmap_sort_ws_bytes": (sz, [i64]),

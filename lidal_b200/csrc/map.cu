@@ -561,6 +561,24 @@ __global__ void kmap_query_kernel(TableView t, const int4* __restrict__ out_coor
     nbr[idx] = r;
   }
 }
+// Symmetric (submanifold) maps: in == out coordinates and offsets[k-1-j] == -offsets[j], so nbr[j][o] = r implies
+// nbr[k-1-j][r] = o.  Only the first (k+1)/2 offsets are probed; the mirrored half (pre-filled with -1) is scattered.
+__global__ void kmap_query_sym_kernel(TableView t, const int4* __restrict__ coords, int64_t n, const int* __restrict__ offsets,
+                                      int k, int* __restrict__ nbr, int64_t ld) {
+  extern __shared__ int s_off[];
+  for (int i = threadIdx.x; i < 3 * k; i += blockDim.x) s_off[i] = offsets[i];
+  __syncthreads();
+  const int half = (k + 1) / 2;
+  const int64_t total = n * half;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / n);
+    const int64_t o = idx - (int64_t)j * n;
+    const int4 c = __ldg(&coords[o]);
+    const int r = table_find(t, (uint64_t)fnv60(c.x + s_off[3 * j], c.y + s_off[3 * j + 1], c.z + s_off[3 * j + 2], c.w));
+    nbr[(int64_t)j * ld + o] = r;
+    if (r >= 0 && j != k - 1 - j) nbr[(int64_t)(k - 1 - j) * ld + r] = (int)o;
+  }
+}
 __global__ void kmap_flags(const int* __restrict__ nbr, int64_t total, uint32_t* __restrict__ flags) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     flags[i] = nbr[i] >= 0 ? 1u : 0u;
@@ -587,6 +605,19 @@ extern "C" int lb_kmap_query(const void* table, size_t bytes, const int32_t* out
   LB_CHECK_ARG(table && out_coords && offsets && nbr, "null pointer");
   kmap_query_kernel<<<grid_for(cap * k, 256), 256, 3 * k * sizeof(int), as_stream(stream)>>>(
       table_view(table, bytes), (const int4*)out_coords, cap, n_dev, offsets, k, nbr); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_kmap_query_sym(const void* table, size_t bytes, const int32_t* coords, int64_t n, const int32_t* offsets,
+                                 int k, int32_t* nbr, int64_t nbr_ld, void* stream) {
+  LB_CHECK_ARG(n >= 0 && k > 0 && (k & 1) && k <= 343 && nbr_ld >= n, "bad arguments (k must be odd)");
+  if (n == 0) return LB_OK;
+  LB_CHECK_ARG(table && coords && offsets && nbr, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int half = (k + 1) / 2;
+  LB_CUDA(cudaMemsetAsync(nbr + (int64_t)half * nbr_ld, 0xFF, (size_t)(k - half) * nbr_ld * 4, st));
+  kmap_query_sym_kernel<<<grid_for(n * half, 256), 256, 3 * k * sizeof(int), st>>>(table_view(table, bytes), (const int4*)coords, n,
+                                                                              offsets, k, nbr, nbr_ld); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

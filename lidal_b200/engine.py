@@ -150,8 +150,9 @@ class Maps:
             self.tables.append(table)
             off3 = _offsets(3, s, dev)
             nbr3 = torch.empty((27, c.shape[0]), dtype=torch.int, device=dev)
-            L.check(L.lib().lb_kmap_query(L.ptr(table[0]), table[1], L.ptr(c), c.shape[0], None, L.ptr(off3), 27,
-                                          L.ptr(nbr3), L.stream()))
+            # submanifold map: in == out coordinates, point-symmetric offsets -> probe 14 offsets, mirror the other 13
+            L.check(L.lib().lb_kmap_query_sym(L.ptr(table[0]), table[1], L.ptr(c), c.shape[0], L.ptr(off3), 27,
+                                              L.ptr(nbr3), nbr3.stride(0), L.stream()))
             self.nbr3.append(_mask_sorted(nbr3) if SORT_MAPS else nbr3)
             if lvl == 4:
                 break
@@ -351,16 +352,19 @@ class HostPipeline:
     """Host-buffer front end of the engine: ``submit(coords_host, feats_host)`` / ``collect()``.
 
     The reference's loop (score/prob_inference.py:94-100) does ``.cuda()`` -> model -> ``.cpu()`` serially.  Here the H2D
-    copy of batch i+1 and the D2H copy of logits i-1 run on a copy stream while batch i computes, so PCIe traffic hides
-    behind the kernels.  Inputs must be pinned for the copies to be asynchronous; outputs land in pinned buffers.
+    copy of batch i+1 and the D2H copy of logits i-1 run on their own streams (one per direction, so an upload never
+    queues behind a download that is still waiting for its kernels) while batch i computes: PCIe traffic hides behind
+    the kernels.  Inputs must be pinned for the copies to be asynchronous; outputs land in pinned buffers.
     """
 
     def __init__(self, engine: "InferenceEngine", depth: int = 2):
         self.engine = engine
-        self.copy_stream = torch.cuda.Stream(device=engine.device)
+        self.h2d_stream = torch.cuda.Stream(device=engine.device)
+        self.d2h_stream = torch.cuda.Stream(device=engine.device)
         self.depth = depth
         self.pending = []          # (logits_dev, out_host, done_event)
         self._out_pool = {}
+        self._in_pool = {}
         self._n_submitted = 0
 
     def _out_buffer(self, shape, slot):
@@ -371,28 +375,48 @@ class HostPipeline:
             self._out_pool[key] = buf
         return buf[: shape[0]]
 
+    def _in_buffers(self, slot, coords_host, feats_host):
+        """Persistent device input buffers per ring slot (no caching-allocator traffic on the copy streams)."""
+        n = coords_host.shape[0]
+        ent = self._in_pool.get(slot)
+        if ent is None or ent[0].shape[0] < n or ent[1].shape[1] != feats_host.shape[1] or ent[0].dtype != coords_host.dtype \
+                or ent[1].dtype != feats_host.dtype:
+            cap = int(n * 1.25) + 1
+            dev = self.engine.device
+            ent = [torch.empty((cap, coords_host.shape[1]), dtype=coords_host.dtype, device=dev),
+                   torch.empty((cap, feats_host.shape[1]), dtype=feats_host.dtype, device=dev), None]
+            self._in_pool[slot] = ent
+        return ent
+
     def submit(self, coords_host: torch.Tensor, feats_host: torch.Tensor):
         """Queue one batch (host tensors).  Returns immediately; results come back in order from ``collect``."""
         dev = self.engine.device
-        with torch.cuda.stream(self.copy_stream):
-            c = coords_host.to(dev, non_blocking=True)
-            f = feats_host.to(dev, non_blocking=True)
+        slot = self._n_submitted % (self.depth + 2)
+        ent = self._in_buffers(slot, coords_host, feats_host)
+        n = coords_host.shape[0]
+        with torch.cuda.stream(self.h2d_stream):
+            if ent[2] is not None:
+                self.h2d_stream.wait_event(ent[2])        # the step that last read this slot has finished
+            c = ent[0][:n]
+            f = ent[1][:n]
+            c.copy_(coords_host, non_blocking=True)
+            f.copy_(feats_host, non_blocking=True)
             ready = torch.cuda.Event()
-            ready.record(self.copy_stream)
+            ready.record(self.h2d_stream)
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ready)
         logits = self.engine(c, f)
-        c.record_stream(cur); f.record_stream(cur)
         computed = torch.cuda.Event()
         computed.record(cur)
-        out = self._out_buffer(logits.shape, self._n_submitted % (self.depth + 2))   # ring: never a buffer still in flight
+        ent[2] = computed
+        out = self._out_buffer(logits.shape, slot)        # ring: never a buffer still in flight
         self._n_submitted += 1
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(computed)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(computed)
             out.copy_(logits, non_blocking=True)
-            logits.record_stream(self.copy_stream)
+            logits.record_stream(self.d2h_stream)
             done = torch.cuda.Event()
-            done.record(self.copy_stream)
+            done.record(self.d2h_stream)
         self.pending.append((out, done))
         results = []
         while len(self.pending) > self.depth:

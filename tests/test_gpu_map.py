@@ -142,3 +142,23 @@ def test_sort_pairs_sizes(n, bits, dup):
     want_k, want_i = torch.sort(biased, stable=True)
     assert torch.equal(v2.long(), want_i)
     assert torch.equal(k2, keys[want_i])
+
+
+def test_symmetric_kernel_map_query_matches_plain(ts, small_scan):
+    """lb_kmap_query_sym (probe half the offsets, mirror the rest) == lb_kmap_query, bit for bit, at strides 1 and 2."""
+    from lidal_b200 import _lib as L
+    from lidal_b200 import engine
+    F = ts.nn.functional
+    coords = torch.from_numpy(small_scan[0]).cuda()
+    for stride in (1, 2):
+        c = coords if stride == 1 else F.spdownsample(coords, 2, 2, 1)
+        n = c.shape[0]
+        table = F._build_table(F.sphash(c))
+        off = engine._offsets(3, stride, c.device)
+        a = torch.empty((27, n), dtype=torch.int, device="cuda")
+        b = torch.full((27, n + 5), 123, dtype=torch.int, device="cuda")
+        L.check(L.lib().lb_kmap_query(L.ptr(table[0]), table[1], L.ptr(c), n, None, L.ptr(off), 27, L.ptr(a), L.stream()))
+        L.check(L.lib().lb_kmap_query_sym(L.ptr(table[0]), table[1], L.ptr(c), n, L.ptr(off), 27, L.ptr(b), b.stride(0), L.stream()))
+        assert torch.equal(a, b[:, :n])
+        assert int((a >= 0).sum()) > n          # non-trivial map
+        assert torch.equal(a[13].long().cpu(), torch.arange(n))
