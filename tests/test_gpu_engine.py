@@ -192,12 +192,16 @@ def test_voxelize_ex_vec4_matches_reference_kernel():
     idx[2000:][idx[2000:] >= m - 2000] = 5
     counts = F.spcount(idx, m)
     assert int((counts == 1).sum()) > 500 and int((counts > 4).sum()) > 500
-    for c in (4, 32, 256):
-        feats = torch.randn(n, c, generator=g).cuda().bfloat16()
-        out = torch.empty(m, c, dtype=torch.float32, device="cuda")
-        L.check(L.lib().lb_voxelize_fwd_ex(L.ptr(feats), L.LB_DT_BF16, c, L.ptr(idx), L.ptr(counts), n, m, c, L.ptr(out), L.stream()))
-        want = F.spvoxelize(feats.float(), idx, counts)
-        torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    runs = torch.sort(torch.randint(0, m, (n,), generator=g)).values.int().cuda()     # scan-like order: long runs per voxel
+    runs[::97] = -1
+    for ids in (idx, runs):
+        cnts = F.spcount(ids, m)
+        for c in (4, 32, 256):
+            feats = torch.randn(n, c, generator=g).cuda().bfloat16()
+            out = torch.empty(m, c, dtype=torch.float32, device="cuda")
+            L.check(L.lib().lb_voxelize_fwd_ex(L.ptr(feats), L.LB_DT_BF16, c, L.ptr(ids), L.ptr(cnts), n, m, c, L.ptr(out), L.stream()))
+            want = F.spvoxelize(feats.float(), ids, cnts)
+            torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
 
 
 def test_host_pipeline_matches_direct_calls(small_scan):
