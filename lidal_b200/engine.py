@@ -123,6 +123,34 @@ def _offsets(ks, stride, dev):
     return _OFFSETS[key]
 
 
+class _HostCounters:
+    """Row counts that kernels write straight into pinned host memory (the pointer is device-visible under UVA).  Reading
+    one costs an event wait -- not a 4-byte D2H copy, which would queue on the copy engine behind the logits download of
+    the previous step (HostPipeline) and stall map construction for milliseconds."""
+
+    def __init__(self, slots: int = 8):
+        self.buf = torch.zeros(slots, dtype=torch.int32).pin_memory()
+        self.ev = torch.cuda.Event()
+
+    def ptr(self, i):
+        return C.c_void_p(self.buf.data_ptr() + 4 * i)
+
+    def read(self, i) -> int:
+        self.ev.record()
+        self.ev.synchronize()
+        return int(self.buf[i])
+
+
+_COUNTERS = {}
+
+
+def _counters(dev) -> _HostCounters:
+    key = str(dev)
+    if key not in _COUNTERS:
+        _COUNTERS[key] = _HostCounters()
+    return _COUNTERS[key]
+
+
 def _mask_sorted(nbr):
     """(nbr_sorted, perm): rows grouped by neighbour mask so 128-row tiles skip absent offsets (lb_kmap_sort_by_mask)."""
     k, n = nbr.shape
@@ -159,14 +187,14 @@ class Maps:
             # level transition in one pass (no sort, no hash queries): parents in first-occurrence order + both maps
             n_c = c.shape[0]
             cn_full = torch.empty_like(c)
-            n_out = torch.zeros(1, dtype=torch.int, device=dev)
+            cnt = _counters(dev)
             dn_full = torch.empty((8, n_c), dtype=torch.int, device=dev)
             up = torch.empty((8, n_c), dtype=torch.int, device=dev)
             nbytes = L.lib().lb_downsample_maps_ws_bytes(n_c)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            L.check(L.lib().lb_downsample_maps(L.ptr(c), n_c, s, L.ptr(cn_full), L.ptr(n_out), L.ptr(dn_full), n_c, L.ptr(up),
+            L.check(L.lib().lb_downsample_maps(L.ptr(c), n_c, s, L.ptr(cn_full), cnt.ptr(lvl), L.ptr(dn_full), n_c, L.ptr(up),
                                                L.ptr(ws), nbytes, L.stream()))
-            m_c = int(n_out.item())
+            m_c = cnt.read(lvl)
             cn = cn_full[:m_c]
             dn = dn_full[:, :m_c]
             self.coords.append(cn)
@@ -304,13 +332,13 @@ class InferenceEngine:
         h = F.sphash(cell.int())
         n = h.shape[0]
         # voxel order inside the engine is free (outputs are per point): group by hash in first-occurrence order
-        n_u = torch.zeros(1, dtype=torch.int, device=dev)
+        cnt = _counters(dev)
         inv = torch.empty(n, dtype=torch.int, device=dev)
         first = torch.empty(n, dtype=torch.int, device=dev)
         nbytes = L.lib().lb_group_by_key_ws_bytes(n)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        L.check(L.lib().lb_group_by_key(L.ptr(h), n, L.ptr(inv), L.ptr(first), L.ptr(n_u), L.ptr(ws), nbytes, L.stream()))
-        nv = int(n_u.item())
+        L.check(L.lib().lb_group_by_key(L.ptr(h), n, L.ptr(inv), L.ptr(first), cnt.ptr(7), L.ptr(ws), nbytes, L.stream()))
+        nv = cnt.read(7)
         counts = torch.empty(nv, dtype=torch.int, device=dev)
         L.check(L.lib().lb_count(L.ptr(inv), n, L.ptr(counts), nv, L.stream()))
         cell_i = cell.int()
