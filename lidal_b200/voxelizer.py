@@ -22,7 +22,8 @@ def _dbl(values):
     return (C.c_double * len(values))(*[float(v) for v in values])
 
 
-def voxelize_view(raw_dev: torch.Tensor, rs: np.random.RandomState, batch: int, scale: float = 20.0, full_scale: float = 8192.0):
+def voxelize_view(raw_dev: torch.Tensor, rs: np.random.RandomState, batch: int, scale: float = 20.0, full_scale: float = 8192.0,
+                  err_out: list | None = None):
     """One augmented view.  raw_dev float32 [Np,4] on device.  Returns coords int32 [Nv,4], feats f32 [Nv,4], inverse int32 [Np]."""
     L.require_cuda(raw_dev)
     raw_dev = raw_dev.contiguous()
@@ -34,8 +35,9 @@ def voxelize_view(raw_dev: torch.Tensor, rs: np.random.RandomState, batch: int, 
     cp = torch.empty((n, 3), dtype=torch.float64, device=dev)
     feats_p = torch.empty((n, 4), dtype=torch.float32, device=dev)
     L.check(L.lib().lb_tta_transform(L.ptr(raw_dev), n, _dbl(trans_m.reshape(-1)), float(scale), L.ptr(cp), L.ptr(feats_p), L.stream()))
-    lo, hi = torch.aminmax(cp, dim=0)                                               # :154-155 (6 doubles to the host)
-    cmin, cmax = lo.cpu().numpy(), hi.cpu().numpy()
+    lo, hi = torch.aminmax(cp, dim=0)                                               # :154-155 (6 doubles to the host, one copy)
+    mm = torch.stack((lo, hi)).cpu().numpy()
+    cmin, cmax = mm[0], mm[1]
     fs = np.array([full_scale] * 3)
     offset = (-cmin + np.clip(fs - cmax + cmin - 0.001, 0, None) * rs.rand(3)
               + np.clip(fs - cmax + cmin + 0.001, None, 0) * rs.rand(3))            # :156
@@ -44,15 +46,19 @@ def voxelize_view(raw_dev: torch.Tensor, rs: np.random.RandomState, batch: int, 
     err = torch.zeros(1, dtype=torch.int, device=dev)
     L.check(L.lib().lb_tta_quantize(L.ptr(cp), n, _dbl(offset), batch, COORD_BITS, L.ptr(coords_p), L.ptr(keys), L.ptr(err), L.stream()))
     uniq = torch.empty(n, dtype=torch.int64, device=dev)
-    n_u = torch.zeros(1, dtype=torch.int, device=dev)
+    from .engine import _counters
+    cnt = _counters(dev)                                                            # count lands in pinned host memory
     inverse = torch.empty(n, dtype=torch.int, device=dev)
     first = torch.empty(n, dtype=torch.int, device=dev)
     nbytes = L.lib().lb_unique_ws_bytes(n)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    L.check(L.lib().lb_unique_i64(L.ptr(keys), n, 3 * COORD_BITS, L.ptr(uniq), L.ptr(n_u), L.ptr(inverse), L.ptr(first), L.ptr(ws),
+    L.check(L.lib().lb_unique_i64(L.ptr(keys), n, 3 * COORD_BITS, L.ptr(uniq), cnt.ptr(6), L.ptr(inverse), L.ptr(first), L.ptr(ws),
                                   nbytes, L.stream()))
-    nv = int(n_u.item())
-    assert int(err.item()) == 0, "input voxels are not valid"                       # :160-161
+    nv = cnt.read(6)
+    if err_out is None:
+        assert int(err.item()) == 0, "input voxels are not valid"                   # :160-161
+    else:
+        err_out.append(err)                                                         # checked once per batch by the caller
     coords_v = torch.empty((nv, 4), dtype=torch.int, device=dev)
     feats_v = torch.empty((nv, 4), dtype=torch.float32, device=dev)
     L.check(L.lib().lb_gather_rows16(L.ptr(coords_p), L.ptr(first), nv, L.ptr(coords_v), L.stream()))
@@ -63,9 +69,10 @@ def voxelize_view(raw_dev: torch.Tensor, rs: np.random.RandomState, batch: int, 
 def tta_batch_gpu(raw_dev: torch.Tensor, seed: int, inf_reps: int = 8):
     """The batch score/prob_inference.py:91-97 consumes, built on device: (coords [N,4], feats [N,4], inverse int64 [reps*Np])."""
     rs = np.random.RandomState(seed)
-    coords, feats, inverse, off = [], [], [], 0
+    coords, feats, inverse, off, errs = [], [], [], 0, []
     for b in range(inf_reps):
-        c, f, inv = voxelize_view(raw_dev, rs, b)
+        c, f, inv = voxelize_view(raw_dev, rs, b, err_out=errs)
         coords.append(c); feats.append(f); inverse.append(inv.long() + off)
         off += c.shape[0]
+    assert int(torch.cat(errs).max().item()) == 0, "input voxels are not valid"             # :160-161
     return torch.cat(coords), torch.cat(feats), torch.cat(inverse)
