@@ -235,11 +235,34 @@ int lb_tta_transform(const float* raw, int64_t n, const double* trans_m, double 
 int lb_tta_quantize(const double* coords_f64, int64_t n, const double* offset, int batch, int coord_bits, int32_t* coords,
                     int64_t* keys, int32_t* err_flag, void* stream);
 
+/* All `reps` TTA views of ONE scan at once (the batch score/prob_inference.py:91-97 consumes): lb_tta_transform +
+ * the min/max of dataset/sk_dataset.py:154-155 + the random shift of :156 + lb_tta_quantize for every view, two launches,
+ * no host round trip.  The caller draws the random numbers in the reference's order (per view: randn(3,3), randint,
+ * rand, rand(3), rand(3)) and passes [host] trans_m f64 [reps,9] (after the flip / yaw product), r1, r2 f64 [reps,3].
+ * Outputs are view-major: feats_p f32 [reps*n,4], coords_p int32 [reps*n,4] (batch column = view), keys int64 [reps*n]
+ * = view << 3b | x << 2b | y << b | z  (b = coord_bits): ONE ascending unique over all keys (lb_unique_i64 with
+ * key_bits = 3b + 4) yields the collated voxel order, first-point rows and the already offset inverse indices of
+ * dataset/sk_dataset.py:188-242.  err_flag: device int32[1], set if a coordinate leaves [0, full_scale).  reps <= 16. */
+size_t lb_tta_views_ws_bytes(int64_t n, int reps);
+int lb_tta_views(const float* raw, int64_t n, int reps, const double* trans_m, const double* r1, const double* r2,
+                 double scale, double full_scale, int coord_bits, float* feats_p, int32_t* coords_p, int64_t* keys,
+                 int32_t* err_flag, void* ws, size_t ws_bytes, void* stream);
+
+/* Pose registration (dataset/prepare_kdtree_sk.py:76-80):
+ * xyz[i] = (hstack(raw[i,:3], 1) as float32 -> float64 products with pose.T, summed in column order)[:3].
+ * raw f32 [n, ld_raw >= 3]; pose [host] f64 [16] row-major 4x4 sensor->world; xyz f64 [n,3].  Bit-equal to numpy. */
+int lb_register_points(const float* raw, int64_t ld_raw, int64_t n, const double* pose, double* xyz, void* stream);
+
 /* ------------------------------------------------------------------ prob_inference tail
  * score/prob_inference.py:100-113: gather logits by inverse index, softmax, mean over views, argmax.
  * logits f32 [n_vox, n_cls]; inverse int64 [reps*n_pts]; prob f32 [n_pts, n_cls]; pred int64 [n_pts]. */
 int lb_tta_softmax_mean_argmax(const float* logits, int64_t n_vox, int n_cls, const int64_t* inverse, int reps,
                                int64_t n_pts, float* prob, int64_t* pred, void* stream);
+
+/* The out_feat branch of the same tail (score/prob_inference.py:103-105,116-118): out[p] = mean over views of
+ * feat[inverse[v*n_pts + p]] in float32, views added in order.  feat [n_vox, ld] of feat_dtype (LB_DT_*), c channels. */
+int lb_tta_feat_mean(const void* feat, int feat_dtype, int64_t ld, int64_t n_vox, const int64_t* inverse, int reps,
+                     int64_t n_pts, int c, float* out, void* stream);
 
 /* ------------------------------------------------------------------ inter-frame scoring
  * score/sv_level/LiDAL.py:59-103.  One uniform grid per frame replaces the pickled sklearn KD-tree; the match rule
@@ -271,7 +294,8 @@ int lb_interframe_score(const void* q_grid, const float* q_prob, int64_t nq, int
 
 /* LiDAL.py:87-98: per-region means over the ragged `sv2point` lists given in CSR form:
  * region_ptr int32 [r+1], region_pts int32 [region_ptr[r]].  Outs: d,e f32 [r]; optional pnums i64 [r],
- * centers f32 [r,3].  One block per region, fixed reduction order (deterministic). */
+ * centers f32 [r,3].  One block per region; the two score means follow numpy's pairwise summation order (float64 for
+ * interd, float32 for intere) so they equal the reference's `.mean()` bit for bit; deterministic. */
 int lb_region_reduce(const double* interd, const float* intere, const double* xyz, const int32_t* region_ptr,
                      const int32_t* region_pts, int n_regions, float* sv_interds, float* sv_interes,
                      int64_t* sv_pnums, float* sv_centers, void* stream);
@@ -292,6 +316,25 @@ int lb_region_pairs(const float* centers, int64_t n, float radius, int32_t* row,
  * (top1 - top2), mean top1 over the n points of one frame. */
 size_t lb_frame_level_ws_bytes(void);
 int lb_frame_level_scores(const float* prob, int64_t n, int n_cls, double* out3, void* ws, size_t ws_bytes, void* stream);
+
+/* score/frame_level/segment_entropy.py:41-48: frame_sege = sum over regions of (sum_c -q_c log2(q_c + 1e-12)) * len / n,
+ * q_c = share of class c among the region's predictions (float64, class order, region order).  pred int64 [n];
+ * regions in CSR form; out: device double[1]; ws >= 8 * n_regions bytes.  n_cls <= 64. */
+int lb_segment_entropy(const int64_t* pred, int64_t n, int n_cls, const int32_t* region_ptr, const int32_t* region_pts,
+                       int n_regions, double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ReDAL region scoring (score/sv_level/ReDAL.py:63-79):
+ * lb_redal_point_scores: point_score = alpha * mean_c(-p log2(p + 1e-12)) + gamma * curvature, float32 throughout
+ *   (numpy pairwise order over classes); curvature f32 [n] may be NULL (treated as 0).
+ * lb_region_mean_f32:   out[r] = vals[region r].mean() in numpy's float32 pairwise order (sv_scores, ReDAL.py:78).
+ * lb_region_feat_mean:  out[r,:] = feat[region r, :].mean(0), float32, rows added in order (sv_feats, ReDAL.py:79);
+ *   feat f32 [n, ld], c channels (the 96-dim out_feat of lb_tta_feat_mean). */
+int lb_redal_point_scores(const float* prob, int64_t n, int n_cls, const float* curvature, float alpha, float gamma,
+                          float* point_score, void* stream);
+int lb_region_mean_f32(const float* vals, const int32_t* region_ptr, const int32_t* region_pts, int n_regions, float* out,
+                       void* stream);
+int lb_region_feat_mean(const float* feat, int64_t ld, int c, const int32_t* region_ptr, const int32_t* region_pts,
+                        int n_regions, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,14 @@ SIGNATURES = {
     "lb_devoxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, i32, i64, vp]),
     "lb_tta_transform": (i32, [vp, i64, C.POINTER(dbl), dbl, vp, vp, vp]),
     "lb_tta_quantize": (i32, [vp, i64, C.POINTER(dbl), i32, i32, vp, vp, vp, vp]),
+    "lb_tta_views_ws_bytes": (sz, [i64, i32]),
+    "lb_tta_views": (i32, [vp, i64, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl), dbl, dbl, i32, vp, vp, vp, vp, vp, sz, vp]),
+    "lb_register_points": (i32, [vp, i64, i64, C.POINTER(dbl), vp, vp]),
+    "lb_tta_feat_mean": (i32, [vp, i32, i64, i64, vp, i32, i64, i32, vp, vp]),
+    "lb_segment_entropy": (i32, [vp, i64, i32, vp, vp, i32, vp, vp, sz, vp]),
+    "lb_redal_point_scores": (i32, [vp, i64, i32, vp, flt, flt, vp, vp]),
+    "lb_region_mean_f32": (i32, [vp, vp, vp, i32, vp, vp]),
+    "lb_region_feat_mean": (i32, [vp, i64, i32, vp, vp, i32, vp, vp]),
     "lb_tta_softmax_mean_argmax": (i32, [vp, i64, i32, vp, i32, i64, vp, vp, vp]),
     "lb_frame_grid_bytes": (sz, [i64]),
     "lb_frame_grid_ws_bytes": (sz, [i64]),

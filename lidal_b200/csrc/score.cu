@@ -10,6 +10,7 @@
 //   interd accumulates in double; sum_prob in float, neighbours in nei_ids order.
 // One warp owns one query point: lanes 0..26 probe the 27 surrounding cells, then lane c owns class c.
 #include "common.cuh"
+#include "np_sum.cuh"
 
 namespace lb {
 
@@ -119,27 +120,6 @@ __global__ void grid_fill_kernel(const double* __restrict__ xyz, const uint64_t*
   }
 }
 
-// numpy float32 pairwise sum over n <= 32 lane-resident values (lane j holds a[j]); result valid on lane 0.
-__device__ __forceinline__ float np_pairwise_sum32(float a, int n, int lane) {
-  const unsigned full = 0xffffffffu;
-  if (n < 8) {
-    float res = 0.f;
-    for (int j = 0; j < n; ++j) res = __fadd_rn(res, __shfl_sync(full, a, j));
-    return res;
-  }
-  float r = a;                                    // lanes 0..7 hold r[j]
-  const int body = n - (n % 8);
-  for (int i = 8; i < body; i += 8) {
-    float t = __shfl_sync(full, a, (lane & 7) + i);
-    r = __fadd_rn(r, t);
-  }
-  float s1 = __fadd_rn(r, __shfl_down_sync(full, r, 1));      // valid on even lanes: r[j] + r[j+1]
-  float s2 = __fadd_rn(s1, __shfl_down_sync(full, s1, 2));    // valid on lanes 0,4
-  float res = __fadd_rn(s2, __shfl_down_sync(full, s2, 4));   // valid on lane 0
-  for (int i = body; i < n; ++i) res = __fadd_rn(res, __shfl_sync(full, a, i));
-  return res;
-}
-
 constexpr int MAX_NBR = 32;
 struct FrameRef {
   const void* grid;
@@ -247,41 +227,49 @@ interframe_kernel(const float* __restrict__ q_prob, int64_t nq, int n_cls, const
   }
 }
 
-// One block per region: fixed-order double reductions => deterministic results.
-__global__ void __launch_bounds__(256)
+// One block per region.  sv_interds = interd_points[p_ids].mean() (float64) and sv_interes = intere_points[p_ids].mean()
+// (float32) follow numpy's pairwise order exactly (np_sum.cuh) -- the selection compares these values, so the last bit
+// matters; the centre is a fixed-order float64 tree (numpy adds the rows of query_points[p_ids] sequentially in float64:
+// the two differ far below float32 resolution of the stored centre).  Deterministic.
+__global__ void __launch_bounds__(NP_BLOCK_THREADS)
 region_reduce_kernel(const double* __restrict__ interd, const float* __restrict__ intere, const double* __restrict__ xyz,
                      const int* __restrict__ ptr, const int* __restrict__ pts, float* __restrict__ sv_d,
                      float* __restrict__ sv_e, int64_t* __restrict__ sv_n, float* __restrict__ sv_c) {
-  __shared__ double sh[5][256];
+  __shared__ NpLeafLayout L;
+  __shared__ double sums[NP_MAX_LEAVES];
+  __shared__ double sh[3][NP_BLOCK_THREADS];
   const int r = blockIdx.x;
   const int b = ptr[r], e = ptr[r + 1];
-  double a[5] = {0, 0, 0, 0, 0};
-  for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
-    int p = __ldg(&pts[i]);
-    a[0] += interd[p];
-    a[1] += (double)intere[p];
-    a[2] += xyz[3 * (int64_t)p];
-    a[3] += xyz[3 * (int64_t)p + 1];
-    a[4] += xyz[3 * (int64_t)p + 2];
-  }
+  np_build_leaves(e - b, L);
+  const double sd = np_sum_leaves<double>(interd, pts + b, L, sums);
+  const float se = np_sum_leaves<float>(intere, pts + b, L, reinterpret_cast<float*>(sums));
+  if (sv_c) {
+    double a[3] = {0, 0, 0};
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+      const int p = __ldg(&pts[i]);
+      a[0] += xyz[3 * (int64_t)p];
+      a[1] += xyz[3 * (int64_t)p + 1];
+      a[2] += xyz[3 * (int64_t)p + 2];
+    }
 #pragma unroll
-  for (int v = 0; v < 5; ++v) sh[v][threadIdx.x] = a[v];
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s)
-#pragma unroll
-      for (int v = 0; v < 5; ++v) sh[v][threadIdx.x] += sh[v][threadIdx.x + s];
+    for (int v = 0; v < 3; ++v) sh[v][threadIdx.x] = a[v];
     __syncthreads();
+    for (int s = NP_BLOCK_THREADS / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) sh[v][threadIdx.x] += sh[v][threadIdx.x + s];
+      __syncthreads();
+    }
   }
   if (threadIdx.x == 0) {
     const double n = (double)(e - b);
-    sv_d[r] = (float)(sh[0][0] / n);
-    sv_e[r] = (float)(sh[1][0] / n);
+    sv_d[r] = (float)__ddiv_rn(sd, n);                  // float64 mean stored into a float32 array (LiDAL.py:88,97)
+    sv_e[r] = __fdiv_rn(se, (float)(e - b));            // float32 mean (LiDAL.py:89,98)
     if (sv_n) sv_n[r] = e - b;
     if (sv_c) {
-      sv_c[3 * r] = (float)(sh[2][0] / n);
-      sv_c[3 * r + 1] = (float)(sh[3][0] / n);
-      sv_c[3 * r + 2] = (float)(sh[4][0] / n);
+      sv_c[3 * r] = (float)(sh[0][0] / n);
+      sv_c[3 * r + 1] = (float)(sh[1][0] / n);
+      sv_c[3 * r + 2] = (float)(sh[2][0] / n);
     }
   }
 }
@@ -397,7 +385,7 @@ extern "C" int lb_region_reduce(const double* interd, const float* intere, const
   LB_CHECK_ARG(n_regions >= 0, "n_regions < 0");
   if (n_regions == 0) return LB_OK;
   LB_CHECK_ARG(interd && intere && xyz && region_ptr && region_pts && sv_d && sv_e, "null pointer");
-  region_reduce_kernel<<<n_regions, 256, 0, as_stream(stream)>>>(interd, intere, xyz, region_ptr, region_pts, sv_d, sv_e,
+  region_reduce_kernel<<<n_regions, NP_BLOCK_THREADS, 0, as_stream(stream)>>>(interd, intere, xyz, region_ptr, region_pts, sv_d, sv_e,
                                                                  sv_n, sv_c); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
