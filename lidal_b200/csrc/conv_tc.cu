@@ -63,9 +63,19 @@ struct TcParams {
   int stg_bufs;            // staging buffers per epilogue warp (2: the stores of one sub-tile drain while the next is built)
   int n_acc;               // TMEM accumulator sets (2 = epilogue overlaps the next tile, 1 when 2*T*c_out > 512)
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
+  int dbg;                 // LIDAL_DBG knock-out bits for bottleneck hunting (results are WRONG when set): 1 = no gather copies,
+                           // 2 = no MMA issue, 4 = no output stores
+  int prod_warps;          // prod_mode 1: warps that own stages = min(8, stages) -- a warp's consecutive stages must be at most
+                           // one ring lap apart, or its parity wait on the empty barrier could be satisfied by an older phase
+  int prod_mode;           // 0: all producer warps fill every stage in lock-step; 1: each producer warp owns whole stages
+                           // (stage q belongs to warp q % prod_warps), so eight dependent fill chains run side by side
   unsigned* sched;         // dynamic tile scheduler: [0] next ticket, [1] retired CTAs (both zero between launches);
                            // nullptr = static round-robin
 };
+
+// LIDAL_DBG & 128: cycle accounting of CTA 0 (lane 0 of one warp per role) into the scheduler cell, printed by the host
+#define DBG_ON ((p.dbg & 128) && p.sched && blockIdx.x == 0)
+#define DBG_ADD(slot, val) atomicAdd(reinterpret_cast<unsigned long long*>(p.sched + 16) + (slot), (unsigned long long)(val))
 
 template <typename T> __device__ __forceinline__ float cvt_in(uint16_t raw);
 template <> __device__ __forceinline__ float cvt_in<__nv_bfloat16>(uint16_t raw) { return __uint_as_float((uint32_t)raw << 16); }
@@ -139,7 +149,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], NUM_PROD_THREADS + 1);   // 128 gather threads + 1 expect_tx arrive for the TMA tile
+      // every gather thread of the stage posts one asynchronous arrival + 1 expect_tx arrive for the TMA weight tile
+      mbar_init(&full_bar[s], (p.prod_mode == 1 ? 32 : NUM_PROD_THREADS) + 1);
       mbar_init(&empty_bar[s], 1);                     // released by tcgen05.commit
     }
     for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
@@ -167,17 +178,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     // runs once per stage in each of the 8 producer warps, so it is kept minimal: running stage address, precomputed
     // per-thread smem offsets, no per-stage bookkeeping beyond the flag word.
     int cur_word = 0;                                     // tile being issued | its stage count << 24 (published with its first stage)
+    const int pw = warp - NUM_EPI_THREADS / 32;           // producer warp 0..7
+    int seq = 0;                                          // (stages issued so far) % prod_warps -- prod_mode 1: owner of the open stage
     constexpr int PASSES = TILE_M / ROWS_PER_PASS;
     const uint32_t ring_u32 = smem_u32(ring);
     uint32_t st_u32 = ring_u32;                           // smem address of the open stage
     const int64_t ld_in_b = p.ld_in * 2;
     const char* in_col = p.in + (p.pack8 ? 0 : chunk * 16);
     auto issue = [&](const int (&nbv)[T][PASSES], int cb, int b_col, int b_row, uint32_t first_last) {
+      const long long dbg_w = (DBG_ON && t == 0) ? clock64() : 0;
       mbar_wait(&empty_bar[stage], ph ^ 1);               // slot free (first lap passes immediately)
+      if (DBG_ON && t == 0) DBG_ADD(5, clock64() - dbg_w);
       if (t == 0) {
         if (first_last & 1u) s_stage_tile[stage] = cur_word;     // tile id | stage count << 24, read once per tile
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
-        tma_load_2d(st_u32 + a_blk, &w_map, b_col, b_row, &full_bar[stage]);
+        if (p.dbg & 16) mbar_arrive(&full_bar[stage]);
+        else {
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+          tma_load_2d(st_u32 + a_blk, &w_map, b_col, b_row, &full_bar[stage]);
+        }
       }
       const char* in_cb = in_col + (p.pack8 ? 0 : cb * (BK * 2));
 #pragma unroll
@@ -189,7 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           // pack8: 16 bytes = the 8 (padded) channels of one offset; otherwise channels [cb*BK + chunk*8, +8) of the row
           const char* src = in_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b;
           const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
-          cp_async16(st_u32 + sub * A_BYTES + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
+          if (!(p.dbg & 1)) cp_async16(st_u32 + sub * A_BYTES + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
         }
       }
       cp_async_arrive_noinc(&full_bar[stage]);            // asynchronous: fires when this thread's copies have landed
@@ -213,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         const int64_t o = o0 + (q % R4) * 4;
         int4 v = make_int4(-1, -1, -1, -1);
         if (k < KMAX && k < p.k_vol && o < n_out) {
-          if (!p.nbr) {
+          if (!p.nbr || (p.dbg & 64)) {
             v.x = (int)o;
             if (o + 1 < n_out) v.y = (int)o + 1;
             if (o + 2 < n_out) v.z = (int)o + 2;
@@ -240,10 +258,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     unsigned ahead = 0;                                   // thread 0: ticket drawn one tile ahead (its latency is hidden)
     if (t == 0 && p.sched && cur < num_tiles) ahead = atomicAdd(&p.sched[0], 1u);
     uint32_t par = 0;
+    const bool dbg_me = DBG_ON && t == 0;
+    const long long dbg_p0 = dbg_me ? clock64() : 0;
     for (; cur < num_tiles; par ^= 1) {
       const int64_t tile = tile_of(cur);
       // (A) every producer has finished reading s_idx / s_mask[par^1] of the previous tile
+      long long dbg_t = dbg_me ? clock64() : 0;
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      if (dbg_me) { DBG_ADD(6, clock64() - dbg_t); DBG_ADD(8, 1); }
       uint32_t my_bits = 0;
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
@@ -267,7 +289,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         if (p.sched && nx < num_tiles) ahead = atomicAdd(&p.sched[0], 1u);
       }
       // (B) indices and mask of this tile are complete
+      dbg_t = dbg_me ? clock64() : 0;
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      if (dbg_me) DBG_ADD(7, clock64() - dbg_t);
       uint32_t mask = __reduce_or_sync(0xffffffffu, s_mask[par]);   // same value in every lane; REDUX makes it provably uniform
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
       const int nx = (int)__reduce_or_sync(0xffffffffu, (uint32_t)s_next[0]);   // stable until barrier (A) of the next tile
@@ -285,6 +309,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
               nbv[sub][i] = kk < p.k_vol ? s_idx[kk * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS] : -1;
           issue(nbv, kb, kb * BK, 0, (kb == 0 ? 1u : 0u) | (kb == nkb - 1 ? 2u : 0u));
         }
+      } else if (p.prod_mode == 1) {
+        // Per-warp stage ownership: the CTA's stages are numbered in issue order and stage q is filled entirely by
+        // producer warp q % prod_warps (lane = 16-byte chunk of a row x a group of consecutive rows, four row indices per LDS.128).
+        // Every warp walks the same (offset, channel block) sequence and skips the stages it does not own, so eight
+        // fill chains -- slot wait, index loads, address arithmetic, cp.async issue -- overlap instead of one.
+        int remaining = __popc(mask) * kc_blocks;
+        cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
+        bool first = true;
+        constexpr int G = 32 / CHUNKS;                     // row groups per warp instruction: 4 (BK=64) or 8 (BK=32)
+        constexpr int RPL = TM / G;                        // consecutive rows owned by a lane
+        const int lchunk = lane % CHUNKS, lgrp = lane / CHUNKS;
+        const uint32_t lane_dst = (uint32_t)((lgrp * RPL) / TILE_M) * A_BYTES + (uint32_t)((lgrp * RPL) % TILE_M) * ROW_BYTES;
+        const char* lane_src = p.in + lchunk * 16;
+        for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
+          if (!((mask >> k) & 1)) continue;
+          for (int cb = 0; cb < kc_blocks; ++cb, --remaining, first = false) {
+            if (seq == pw) {
+              const long long dbg_w = dbg_me ? clock64() : 0;
+              mbar_wait(&empty_bar[stage], ph ^ 1);
+              if (dbg_me) DBG_ADD(5, clock64() - dbg_w);
+              if (lane == 0) {
+                if (first) s_stage_tile[stage] = cur_word;
+                if (p.dbg & 16) mbar_arrive(&full_bar[stage]);
+                else {
+                  mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+                  tma_load_2d(st_u32 + a_blk, &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
+                }
+              }
+              const char* src_cb = lane_src + cb * (BK * 2);
+              const int4* idx4 = reinterpret_cast<const int4*>(&s_idx[k * TM + lgrp * RPL]);
+              const uint32_t dst0 = st_u32 + lane_dst;
+#pragma unroll 4
+              for (int j4 = 0; j4 < RPL / 4; ++j4) {
+                const int4 v = idx4[j4];
+                const int nb4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int j = j4 * 4 + u;                // row within the lane's group; (lgrp * RPL) % 8 == 0
+                  const uint32_t sw = (BK == 64) ? (uint32_t)(lchunk ^ (j & 7)) : (uint32_t)(lchunk ^ ((j >> 1) & 3));
+                  const int nb = nb4[u];
+                  if (!(p.dbg & 1)) cp_async16(dst0 + (uint32_t)j * ROW_BYTES + sw * 16, src_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b, nb >= 0 ? 16u : 0u);
+                }
+              }
+              cp_async_arrive_noinc(&full_bar[stage]);
+            }
+            if (++seq == p.prod_warps) seq = 0;
+            st_u32 += stage_bytes;
+            if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+          }
+        }
       } else {
         int remaining = __popc(mask) * kc_blocks;
         cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
@@ -301,13 +375,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
       cur = nx >= 0 ? nx : num_tiles;
     }
+    if (dbg_me) DBG_ADD(4, clock64() - dbg_p0);
     // sentinel stage: no data, tile word -1 tells the MMA warp (and through it the epilogue) that this CTA is out of work
-    mbar_wait(&empty_bar[stage], ph ^ 1);
-    if (t == 0) {
-      s_stage_tile[stage] = -1;
-      mbar_arrive(&full_bar[stage]);                      // stands in for the expect_tx arrival of a normal stage
+    if (p.prod_mode == 1) {
+      if (seq == pw) {
+        mbar_wait(&empty_bar[stage], ph ^ 1);
+        if (lane == 0) {
+          s_stage_tile[stage] = -1;
+          mbar_arrive(&full_bar[stage]);                    // stands in for the expect_tx arrival of a normal stage
+        }
+        mbar_arrive(&full_bar[stage]);
+      }
+    } else {
+      mbar_wait(&empty_bar[stage], ph ^ 1);
+      if (t == 0) {
+        s_stage_tile[stage] = -1;
+        mbar_arrive(&full_bar[stage]);                      // stands in for the expect_tx arrival of a normal stage
+      }
+      mbar_arrive(&full_bar[stage]);
     }
-    mbar_arrive(&full_bar[stage]);
     cp_async_wait<0>();                                   // nothing of ours may still be in flight at teardown
   } else if (warp == MMA_WARP) {
     // =============================================================== MMA ISSUER
@@ -320,20 +406,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     constexpr uint32_t A_UNITS = A_BYTES >> 4;
     int stage = 0;
     uint32_t ph = 0, st_lo = ring_lo;
+    const bool dbg_me = DBG_ON && lane == 0;
+    const long long dbg_m0 = dbg_me ? clock64() : 0;
     for (int64_t tcount = 0;; ++tcount) {
       const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
       const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
+      long long dbg_t = dbg_me ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_ph ^ 1);            // epilogue drained this accumulator set
+      if (dbg_me) DBG_ADD(2, clock64() - dbg_t);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * p.c_out);
       // first stage of the tile: its slot carries the tile word (tile id | stage count << 24; -1 = this CTA is done)
+      dbg_t = dbg_me ? clock64() : 0;
       mbar_wait(&full_bar[stage], ph);
+      if (dbg_me) DBG_ADD(1, clock64() - dbg_t);
       const uint32_t word = __reduce_or_sync(0xffffffffu, (uint32_t)s_stage_tile[stage]);   // uniform for the compiler
       if (word == 0xffffffffu) {
         if (lane == 0) {
           s_acc_tile[acc] = -1;
           mbar_arrive(&tstart_bar[acc]);
         }
+        if (dbg_me) DBG_ADD(0, clock64() - dbg_m0);
         break;
       }
       const int n_st = (int)(word >> 24);
@@ -341,9 +434,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         s_acc_tile[acc] = (int)(word & 0xffffffu);               // the epilogue learns its tile before the MMAs finish
         mbar_arrive(&tstart_bar[acc]);
       }
+      if (dbg_me) DBG_ADD(3, n_st);
       for (int e = 0; e < n_st; ++e) {
-        if (e) mbar_wait(&full_bar[stage], ph);
-        fence_proxy_async();                              // gathered rows were written through the generic proxy (cp.async)
+        if (e) {
+          dbg_t = dbg_me ? clock64() : 0;
+          mbar_wait(&full_bar[stage], ph);
+          if (dbg_me) DBG_ADD(1, clock64() - dbg_t);
+        }
+        if (!(p.dbg & 8)) fence_proxy_async();            // gathered rows were written through the generic proxy (cp.async)
         tc_fence_after();
         if (elect_one()) {
           const uint32_t b_lo = st_lo + b_units;
@@ -351,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           for (int sub = 0; sub < T; ++sub) {             // every sub-tile reuses the same weight tile
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
-              umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), st_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
+              if (!(p.dbg & 2)) umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), st_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
                             b_lo + (uint32_t)kk * 2u, desc_hi, idesc, (kk == 0 && e == 0) ? 0u : 1u);   // first MMA overwrites
           }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
@@ -450,7 +548,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           fence_proxy_async();                              // generic-proxy smem writes -> visible to the copy engine
           __syncwarp();
           if (lane == 0) {
-            if (any_live)
+            if (any_live && !(p.dbg & 4))
               for (int g = 0; g < groups; ++g) tma_store_2d(&out_map, g * 32, (int)row0, smem_u32(sbuf + g * 2048));
             bulk_commit();
           }
@@ -469,12 +567,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       const uint32_t row_bytes = (uint32_t)p.c_out * 2;
       uint32_t res_ph = 0;
       int64_t tcount = 0;
+      const bool dbg_me = DBG_ON && threadIdx.x == 0;
+      const long long dbg_e0 = dbg_me ? clock64() : 0;
       for (;; ++tcount) {
         const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
         const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
+        const long long dbg_t = dbg_me ? clock64() : 0;
         mbar_wait(&tstart_bar[acc], acc_ph);              // the MMA warp has published this accumulator's tile
+        if (dbg_me) DBG_ADD(10, clock64() - dbg_t);
         const int64_t tile = s_acc_tile[acc];
-        if (tile < 0) break;
+        if (tile < 0) { if (dbg_me) DBG_ADD(9, clock64() - dbg_e0); break; }
+        if (p.dbg & 32) { mbar_wait(&tfull_bar[acc], acc_ph); tc_fence_after(); }
+        else
         for (int sub = 0; sub < T; ++sub) {
           const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
           const bool live = o < n_out;
@@ -490,7 +594,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             if (live) bulk_load(smem_u32(my_row), p.residual + orow * p.ld_res * 2, row_bytes, &res_bar[warp]);
           }
           if (sub == 0) {
+            const long long dbg_f = dbg_me ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], acc_ph);
+            if (dbg_me) DBG_ADD(11, clock64() - dbg_f);
             tc_fence_after();
           }
           if (p.residual) {
@@ -540,7 +646,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             }
           }
           fence_proxy_async();                            // my generic-proxy smem writes -> visible to the bulk-copy engine
-          if (live) bulk_store(p.out + orow * p.ld_out * 2, smem_u32(my_row), row_bytes);
+          if (live && !(p.dbg & 4)) bulk_store(p.out + orow * p.ld_out * 2, smem_u32(my_row), row_bytes);
           bulk_commit();
         }   // sub-tiles
         tc_fence_before();
@@ -800,6 +906,11 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.stages = stages;
   p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
+  static const int prod_mode_env = getenv("LIDAL_PROD_MODE") ? atoi(getenv("LIDAL_PROD_MODE")) : 0;   // A/B switch
+  static const int dbg_env = getenv("LIDAL_DBG") ? atoi(getenv("LIDAL_DBG")) : 0;
+  p.dbg = dbg_env;
+  p.prod_mode = pack8 ? 0 : prod_mode_env;
+  p.prod_warps = stages < NUM_PROD_THREADS / 32 ? stages : NUM_PROD_THREADS / 32;
   static const bool static_tiles = getenv("LIDAL_STATIC_TILES") != nullptr;   // A/B switch
   p.sched = static_tiles ? nullptr : sched_cell(st);
   const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + (p.staged ? staging_bytes(a.c_out, p.stg_bufs) : 0) + 1024;
@@ -825,6 +936,14 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
 #undef LB_TC_LAUNCH_K
 #undef LB_TC_LAUNCH
   LB_LAUNCH_CHECK();
+  if ((p.dbg & 128) && p.sched) {
+    unsigned long long h[12];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.sched + 16, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaMemset(p.sched + 16, 0, sizeof(h));
+    fprintf(stderr, "[conv dbg] k=%d cin=%d cout=%d n=%lld T=%d stages=%d | mma: total %llu wait_full %llu wait_tempty %llu stages %llu | prod0: total %llu wait_empty %llu barA %llu barB %llu tiles %llu | epi0: total %llu wait_tstart %llu wait_tfull %llu\n",
+            a.k_vol, a.c_in, a.c_out, (long long)a.n_out, T, stages, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+  }
   return LB_OK;
 }
 

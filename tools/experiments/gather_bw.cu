@@ -27,11 +27,11 @@ static __device__ __forceinline__ void gather4(uint32_t dst, const CUtensorMap* 
                ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
-constexpr int STAGES = 8;
+constexpr int STAGES = 12;
 
 template <int MODE, int ROW_BYTES>
-__global__ void __launch_bounds__(32 * 9, 1)
-bench_kernel(const __grid_constant__ CUtensorMap map, const char* __restrict__ in, const int* __restrict__ idx, int tiles_per_cta, int W) {
+__global__ void __launch_bounds__(1024, 1)
+bench_kernel(const __grid_constant__ CUtensorMap map, const char* __restrict__ in, const int* __restrict__ idx, int tiles_per_cta, int W, int WPS) {
   extern __shared__ uint8_t raw[];
   uint8_t* ring = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
@@ -40,7 +40,7 @@ bench_kernel(const __grid_constant__ CUtensorMap map, const char* __restrict__ i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], MODE == 0 ? 1 : (MODE == 1 ? W * 32 : 32));
+      mbar_init(&full[s], MODE == 0 ? 1 : (MODE == 1 ? W * 32 : 32 * WPS));   // modes 2-4: the owning warp's 32 lanes
       mbar_init(&empty[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -77,9 +77,51 @@ bench_kernel(const __grid_constant__ CUtensorMap map, const char* __restrict__ i
         }
         cp_arrive_noinc(&full[s]);
       }
+    } else if (MODE == 3) {
+      // register-staged: LDG.128 x8 in flight, then STS.128 (generic-proxy writes; consumer would need a proxy fence)
+      const int sub = warp % WPS, grp = warp / WPS, ngrp = W / WPS;
+      const int chunk = lane % CHUNKS, row0 = sub * (32 / CHUNKS) + lane / CHUNKS, rpp = WPS * 32 / CHUNKS;
+      for (int t = grp; t < tiles_per_cta; t += ngrp) {
+        const int s = t % STAGES;
+        mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
+        for (int rb = row0; rb < 128; rb += rpp * 8) {
+          uint4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = rb + u * rpp;
+            const int row = __ldg(my_idx + (size_t)t * 128 + r);
+            v[u] = row >= 0 ? __ldg((const uint4*)(in + (size_t)row * ROW_BYTES + chunk * 16)) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = rb + u * rpp;
+            const uint32_t sw = ROW_BYTES == 128 ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
+            *(uint4*)(ring + s * STAGE_BYTES + r * ROW_BYTES + sw * 16) = v[u];
+          }
+        }
+        mbar_arrive(&full[s]);
+      }
+    } else if (MODE == 4) {
+      // cp.async only for present rows; absent rows get an STS.128 of zeros
+      const int sub = warp % WPS, grp = warp / WPS, ngrp = W / WPS;
+      const int chunk = lane % CHUNKS, row0 = sub * (32 / CHUNKS) + lane / CHUNKS, rpp = WPS * 32 / CHUNKS;
+      for (int t = grp; t < tiles_per_cta; t += ngrp) {
+        const int s = t % STAGES;
+        mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
+#pragma unroll 8
+        for (int r = row0; r < 128; r += rpp) {
+          const int row = __ldg(my_idx + (size_t)t * 128 + r);
+          const uint32_t sw = ROW_BYTES == 128 ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
+          uint8_t* dst = ring + s * STAGE_BYTES + r * ROW_BYTES + sw * 16;
+          if (row >= 0) cp_async16(smem_u32(dst), in + (size_t)row * ROW_BYTES + chunk * 16, 16u);
+          else *(uint4*)dst = make_uint4(0, 0, 0, 0);
+        }
+        cp_arrive_noinc(&full[s]);
+      }
     } else {
-      const int chunk = lane % CHUNKS, row0 = lane / CHUNKS, rpp = 32 / CHUNKS;
-      for (int t = warp; t < tiles_per_cta; t += W) {
+      const int sub = warp % WPS, grp = warp / WPS, ngrp = W / WPS;
+      const int chunk = lane % CHUNKS, row0 = sub * (32 / CHUNKS) + lane / CHUNKS, rpp = WPS * 32 / CHUNKS;
+      for (int t = grp; t < tiles_per_cta; t += ngrp) {
         const int s = t % STAGES;
         mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
 #pragma unroll 8
@@ -100,7 +142,7 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 template <int MODE, int ROW_BYTES>
-static void run(EncodeFn enc, char* d_in, int n_rows, const int* d_idx, int tiles_per_cta, int W, double miss, const char* label) {
+static void run(EncodeFn enc, char* d_in, int n_rows, const int* d_idx, int tiles_per_cta, int W, double miss, const char* label, int WPS = 1) {
   CUtensorMap map;
   cuuint64_t gdim[2] = {(cuuint64_t)(ROW_BYTES / 2), (cuuint64_t)n_rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ROW_BYTES};
@@ -117,7 +159,7 @@ static void run(EncodeFn enc, char* d_in, int n_rows, const int* d_idx, int tile
   float best = 1e9f;
   for (int it = 0; it < 4; ++it) {
     cudaEventRecord(e0);
-    bench_kernel<MODE, ROW_BYTES><<<148, 32 * (W + 1), smem>>>(map, d_in, d_idx, tiles_per_cta, W);
+    bench_kernel<MODE, ROW_BYTES><<<148, 32 * (W + 1), smem>>>(map, d_in, d_idx, tiles_per_cta, W, WPS);
     cudaEventRecord(e1);
     cudaError_t e = cudaEventSynchronize(e1);
     if (e != cudaSuccess) { printf("%s: %s\n", label, cudaGetErrorString(e)); exit(2); }
@@ -126,7 +168,7 @@ static void run(EncodeFn enc, char* d_in, int n_rows, const int* d_idx, int tile
   }
   const double bytes = 148.0 * tiles_per_cta * 128 * ROW_BYTES * (1.0 - miss);
   const double stage_cyc = best * 1e-3 * 1.9e9 / tiles_per_cta;
-  printf("%-22s rowB=%3d W=%d rows=%8d miss=%.2f : %7.3f ms  %7.1f GB/s gathered  %6.0f cyc/stage(128 rows)\n", label, ROW_BYTES, W, n_rows, miss, best,
+  printf("%-24s rowB=%3d W=%2d rows=%8d miss=%.2f : %7.3f ms  %7.1f GB/s gathered  %6.0f cyc/stage(128 rows)\n", label, ROW_BYTES, W, n_rows, miss, best,
          bytes / best * 1e-6, stage_cyc);
 }
 
@@ -136,7 +178,7 @@ int main() {
   EncodeFn enc = (EncodeFn)fn;
   const int tiles_per_cta = 2000;
   const size_t n_idx = (size_t)148 * tiles_per_cta * 128;
-  for (int n_rows : {200000, 1000000}) {
+  for (int n_rows : {1000000}) {
     char* d_in; cudaMalloc(&d_in, (size_t)n_rows * 128); cudaMemset(d_in, 1, (size_t)n_rows * 128);
     for (double miss : {0.0, 0.75}) {
       std::vector<int> h(n_idx);
@@ -150,12 +192,14 @@ int main() {
         h[i] = m ? -1 : (int)r;
       }
       int* d_idx; cudaMalloc(&d_idx, n_idx * 4); cudaMemcpy(d_idx, h.data(), n_idx * 4, cudaMemcpyHostToDevice);
-      for (int W : {1, 2, 4, 8}) run<0, 128>(enc, d_in, n_rows, d_idx, tiles_per_cta, W, miss, "tma gather4");
-      for (int W : {1, 2, 4, 8}) run<0, 64>(enc, d_in, n_rows * 2, d_idx, tiles_per_cta, W, miss, "tma gather4");
-      for (int W : {4, 8}) run<1, 128>(enc, d_in, n_rows, d_idx, tiles_per_cta, W, miss, "cp.async lock-step");
-      for (int W : {4, 8}) run<1, 64>(enc, d_in, n_rows * 2, d_idx, tiles_per_cta, W, miss, "cp.async lock-step");
-      for (int W : {4, 8}) run<2, 128>(enc, d_in, n_rows, d_idx, tiles_per_cta, W, miss, "cp.async per-warp stage");
-      for (int W : {4, 8}) run<2, 64>(enc, d_in, n_rows * 2, d_idx, tiles_per_cta, W, miss, "cp.async per-warp stage");
+      for (int W : {8, 12}) run<0, 128>(enc, d_in, n_rows, d_idx, tiles_per_cta, W, miss, "tma gather4");
+      for (int W : {8, 12}) run<0, 64>(enc, d_in, n_rows * 2, d_idx, tiles_per_cta, W, miss, "tma gather4");
+      for (int W : {8, 12, 16, 24}) run<2, 128>(enc, d_in, n_rows, d_idx, tiles_per_cta, W, miss, W > 12 ? "cp.async 2 warps/stage" : "cp.async 1 warp/stage", W > 12 ? 2 : 1);
+      for (int W : {8, 12, 16, 24}) run<2, 64>(enc, d_in, n_rows * 2, d_idx, tiles_per_cta, W, miss, W > 12 ? "cp.async 2 warps/stage" : "cp.async 1 warp/stage", W > 12 ? 2 : 1);
+      for (int W : {8, 16, 24}) run<3, 128>(enc, d_in, n_rows, d_idx, tiles_per_cta, W, miss, W > 12 ? "ldg+sts 2 warps/stage" : "ldg+sts 1 warp/stage", W > 12 ? 2 : 1);
+      for (int W : {8, 16, 24}) run<3, 64>(enc, d_in, n_rows * 2, d_idx, tiles_per_cta, W, miss, W > 12 ? "ldg+sts 2 warps/stage" : "ldg+sts 1 warp/stage", W > 12 ? 2 : 1);
+      for (int W : {8, 16, 24}) run<4, 128>(enc, d_in, n_rows, d_idx, tiles_per_cta, W, miss, W > 12 ? "cp.async+sts0 2w/stage" : "cp.async+sts0 1w/stage", W > 12 ? 2 : 1);
+      for (int W : {8, 16, 24}) run<4, 64>(enc, d_in, n_rows * 2, d_idx, tiles_per_cta, W, miss, W > 12 ? "cp.async+sts0 2w/stage" : "cp.async+sts0 1w/stage", W > 12 ? 2 : 1);
       cudaFree(d_idx);
     }
     cudaFree(d_in);
