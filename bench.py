@@ -151,15 +151,68 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "scans/sec", "value": v, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.model, "cpu"),
+        "config": workload_config(args.model, "cpu"), "path": "cpu (oracle port of the reference's torchsparse path)",
         "cpu_baseline": {"value": v, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def workload_config(model, path):
     return {"workload": f"{model}_inference_{KIND}_batch{BATCH}", "model_family": model, "batch_scans": BATCH,
-            "points_per_scan": "~131k (64-beam ray cast)" if KIND == "SK" else "~33k (32-beam ray cast)", "voxel_m": 0.05, "classes": N_CLS, "path": path,
+            "points_per_scan": "~131k (64-beam ray cast)" if KIND == "SK" else "~33k (32-beam ray cast)", "voxel_m": 0.05, "classes": N_CLS,
             "cache": "3 distinct batches rotated; per-step working set (activations ~0.7M voxels x up to 384 ch) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ config 3: LiDAL frames/s
+TRAIN_POINT_NUM = {"SK": 2349559532, "NU": 976677792}          # score/sv_level/LiDAL.py:130,135
+
+
+def run_lidal(eng, dev, rank, world, n_frames, kind, n_cls, barrier, seed=11):
+    """BASELINE configs[2]: prob_inference (8 TTA views) + inter-frame divergence / entropy scoring + region means over ONE
+    synthetic ``n_frames`` sequence, frames sharded over the ranks as dataset/sk_dataloader.py:196-198 (strong scaling), halo
+    prob maps by P2P, one all_gather of the region scores, then the global selection (replicated).  Raw scans wait in pinned
+    host memory; their H2D copies are inside the timed region."""
+    import torch.distributed as dist
+    from lidal_b200 import pipeline, synth
+    own = pipeline.frame_shard(n_frames, world, rank)
+    seq = synth.GpuSequence(n_frames, kind, seed=seed, device=dev)
+    frames = {}
+    for fid in own:                                             # synthesise this rank's frames (untimed), park them on the host
+        raw, pose, sv_id, (ptr, pts) = seq.frame(fid)
+        frames[fid] = (raw.cpu().pin_memory(), pose, sv_id, (ptr, pts))
+    n_regions_total = n_frames * seq.n_regions
+    flags0 = np.zeros(n_regions_total, int)                     # round 0: 1 % of the frames fully labelled (sk_dataloader.py:99-118)
+    lab = np.random.default_rng(5).choice(n_frames, max(1, n_frames // 100), replace=False)
+    flags0.reshape(n_frames, seq.n_regions)[lab] = 1
+    src = lambda fid: frames[fid]                               # noqa: E731
+    # warm-up: a short sequence through the same code (allocator, tensor maps, NCCL channels for the P2P pattern)
+    warm = synth.GpuSequence(min(n_frames, 26 * max(world, 1)), kind, seed=seed + 1, device=dev)
+    pipeline.run_sequence_sharded(eng, warm.frame, warm.n_frames, n_cls, warm.n_frames * warm.n_regions, device=dev)
+    barrier()
+    t0 = time.perf_counter()
+    d, e, pn, c, flags, tm = pipeline.run_sequence_sharded(eng, src, n_frames, n_cls, n_regions_total, seed=seed, device=dev,
+                                                           select_with=(flags0, TRAIN_POINT_NUM[kind]))
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    total = torch.tensor([tm["device_total_ms"] + tm.get("selection_ms", 0.0), wall_ms, tm["prob_inference_ms"], tm["halo_ms"],
+                          tm["scoring_ms"], tm["gather_ms"], tm.get("selection_ms", 0.0)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    total = total.tolist()
+    pts = float(np.mean([frames[f][0].shape[0] for f in own])) if len(own) else 0.0
+    return {
+        "metric": "LiDAL scored frames/sec", "value": n_frames / (total[0] / 1e3), "unit": "frames/s", "scaling": "strong",
+        "frames": n_frames, "n_gpus": world, "ms_total": total[0], "wall_ms_max": total[1],
+        "workload": f"prob_inference(8 TTA views, SPVCNN) + inter-frame scoring + region means + selection, one {n_frames}-frame {kind}-shaped sequence",
+        "timing": "CUDA events over inference + halo + scoring + all_gather, plus host time of the selection; max over ranks",
+        "phases_ms_max_over_ranks": {"prob_inference": total[2], "halo_exchange": total[3], "interframe_scoring": total[4],
+                                     "region_all_gather": total[5], "selection": total[6]},
+        "collective": {"halo_ms": total[3], "halo_bytes_received_rank0": tm.get("halo_bytes_received", 0),
+                       "halo_frames_received_rank0": tm.get("halo_frames_received", 0), "all_gather_ms": tm.get("all_gather_ms", 0.0),
+                       "all_gather_bytes_per_rank": tm.get("all_gather_bytes_per_rank", 0)},
+        "points_per_frame": pts, "regions": n_regions_total, "h2d_bytes_per_frame": int(pts * 16),
+        "selected": {"labelled": int((flags == 1).sum()), "pseudo": int((flags == 2).sum())},
+        "checks": {"sv_interds_sum": float(d.astype(np.float64).sum()), "sv_interes_sum": float(e.astype(np.float64).sum())},
+    }
 
 
 # ------------------------------------------------------------------------------------------ main
@@ -174,6 +227,8 @@ def main():
     ap.add_argument("--kind", default="SK", choices=["SK", "NU"], help="scan shape: SemanticKITTI-like (19 classes) or nuScenes-like (16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-lidal", action="store_true", help="skip the LiDAL scored-frames/s workload (BASELINE configs[2])")
+    ap.add_argument("--lidal-frames", type=int, default=1000)
     args = ap.parse_args()
     global KIND, N_CLS
     KIND, N_CLS = args.kind, (19 if args.kind == "SK" else 16)
@@ -273,12 +328,24 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 operands, f32 accumulate", "data": "synthetic",
-        "config": workload_config(args.model, path),
+        "config": workload_config(args.model, path), "path": path,
         "e2e": {"value": world * args.steps * BATCH / (ms_e2e / 1e3), "unit": "scans/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clk.summary(),
         "voxels_per_step": int(np.mean(n_vox)),
     }
+
+    lidal = None
+    if eng is not None and not args.no_lidal and args.model == "spvcnn":
+        try:
+            lidal = run_lidal(eng, dev, rank, world, args.lidal_frames, KIND, N_CLS, barrier)
+        except Exception as e:          # noqa: BLE001
+            import traceback
+            lidal = {"error": repr(e), "trace": traceback.format_exc()[-600:]}
+    if lidal is not None:
+        result["lidal"] = lidal
+        result["lidal_frames_per_sec"] = lidal.get("value")
+        result["collective"] = lidal.get("collective")
 
     if rank == 0:
         # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events around every launch
@@ -298,11 +365,17 @@ def main():
             torch.set_num_threads(cores)
             c, f = one_scan(batches[0])
             cpu_reference_step(args.model, c, f)
-            ts_ = [cpu_reference_step(args.model, c, f)[0] for _ in range(2)]
-            t = sum(ts_) / len(ts_)
+            runs = [cpu_reference_step(args.model, c, f) for _ in range(2)]
+            t = sum(r[0] for r in runs) / len(runs)
+            want = runs[-1][1].double()
+            got = run(torch.from_numpy(c).to(dev), torch.from_numpy(f).to(dev)).double().cpu()       # same scan through the CUDA path
+            rel_l2 = float((got - want).norm() / want.norm())
+            agree = float((got.argmax(1) == want.argmax(1)).double().mean())
             result["cpu_baseline"] = {"value": 1.0 / t, "unit": "scans/s", "cores": cores, "kind": "port",
                                       "sample": f"1 of the {BATCH} scans ({c.shape[0]} voxels), mean of 2 after 1 warm-up; "
-                                                "oracle restatement of torchsparse-CPU (the real package cannot be installed offline)"}
+                                                "oracle restatement of torchsparse-CPU (the real package cannot be installed offline)",
+                                      "logits_rel_l2_gpu_vs_oracle": rel_l2, "argmax_agreement": agree,
+                                      "tolerance": "1e-2 relative (bf16 operands, f32 accumulate vs the fp32 oracle)"}
         print(json.dumps(result))
     if world > 1:
         dist.barrier()

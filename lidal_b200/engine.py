@@ -140,6 +140,11 @@ class _HostCounters:
         self.ev.synchronize()
         return int(self.buf[i])
 
+    def pinned_copy(self, dev_scalar: torch.Tensor, i: int):
+        """Queue a copy of a device int32 scalar into slot i; the returned callable reads it after the next ``read``."""
+        self.buf[i:i + 1].copy_(dev_scalar.reshape(1), non_blocking=True)
+        return lambda: int(self.buf[i])
+
 
 _COUNTERS = {}
 
@@ -270,9 +275,12 @@ class InferenceEngine:
         return [torch.empty((m.n[3 - i], widths[i]), dtype=dt, device=dev) for i in range(4)]
 
     @torch.no_grad()
-    def __call__(self, coords, feats):
+    def __call__(self, coords, feats, return_feat: bool = False):
+        """logits f32 [N, n_cls]; with ``return_feat`` also the model's second output (network/minkunet.py:122 ``y4.F``,
+        network/spvcnn.py:155 ``z3.F``): the 96-channel features in the engine's 16-bit activation type."""
         L.require_cuda(coords, feats)
-        return self._spvcnn(coords, feats) if self.is_spvcnn else self._minkunet(coords, feats)
+        logits, feat = self._spvcnn(coords, feats) if self.is_spvcnn else self._minkunet(coords, feats)
+        return (logits, feat) if return_feat else logits
 
     def _minkunet(self, coords, feats):
         m = Maps(coords.contiguous())
@@ -285,7 +293,7 @@ class InferenceEngine:
         for i in range(1, 5):
             y = self._decode(y, m, i, cats[i - 1])
         logits = self.classifier(y, None, m.n[0], out_dtype=torch.float32)
-        return logits[:, : self.n_cls]
+        return logits[:, : self.n_cls], y
 
     # ---- SPVCNN point branch
     def _table_of(self, m, lvl):
@@ -373,7 +381,7 @@ class InferenceEngine:
         y = self._decode(y, m, 4, cats[3])
         z3 = self.mlp[2](z2, None, z2.shape[0], residual=self._devox(y, iq0, w0), relu_first=True)   # [Np, 96]
         logits = self.classifier(z3, None, z3.shape[0], out_dtype=torch.float32)
-        return logits[:, : self.n_cls]
+        return logits[:, : self.n_cls], z3
 
 
 class HostPipeline:

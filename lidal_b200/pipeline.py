@@ -78,30 +78,40 @@ def exchange_halo(local: dict, n_points: Sequence[int], n_cls: int, n_frames: in
     return out
 
 
-def gather_region_scores(sv_id, sv_d, sv_e, sv_n, sv_c, n_regions_total: int, device="cpu"):
+def gather_region_scores(sv_id, sv_d, sv_e, sv_n, sv_c, n_regions_total: int, device="cpu", timings: dict | None = None):
     """The one collective of the path: every rank contributes the regions of its frames; all ranks obtain the global
-    arrays indexed by sv_id (LiDAL.py:208-218).  Payload: 8 + 4 + 4 + 8 + 12 bytes per region."""
+    arrays indexed by sv_id (LiDAL.py:208-218).  Payload: 9 float64 per region (id, d, e, pnum, centre, padded to a common
+    row count); inputs may be numpy arrays or tensors already on ``device`` (then nothing touches the host before the
+    all_gather).  float32 / int values below 2^53 survive the float64 packing exactly."""
     world = dist.get_world_size() if dist.is_initialized() else 1
-    pack = torch.zeros((len(sv_id), 6), dtype=torch.float64, device=device)
-    pack[:, 0] = torch.as_tensor(np.asarray(sv_id), dtype=torch.float64)
-    pack[:, 1] = torch.as_tensor(np.asarray(sv_d), dtype=torch.float64)
-    pack[:, 2] = torch.as_tensor(np.asarray(sv_e), dtype=torch.float64)
-    pack[:, 3] = torch.as_tensor(np.asarray(sv_n), dtype=torch.float64)
-    centres = torch.as_tensor(np.asarray(sv_c), dtype=torch.float64).reshape(-1, 3)
+    as_t = lambda x: (x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))).to(device=device, dtype=torch.float64)  # noqa: E731
+    n_loc = len(sv_id)
+    pack = torch.zeros((n_loc, 9), dtype=torch.float64, device=device)
+    if n_loc:
+        pack[:, 0], pack[:, 1], pack[:, 2], pack[:, 3] = as_t(sv_id), as_t(sv_d), as_t(sv_e), as_t(sv_n)
+        pack[:, 6:] = as_t(sv_c).reshape(-1, 3)
     if world > 1:
+        ev0 = ev1 = None
+        if timings is not None and pack.is_cuda:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         counts = torch.zeros(world, dtype=torch.int64, device=device)
-        counts[dist.get_rank()] = len(sv_id)
+        counts[dist.get_rank()] = n_loc
         dist.all_reduce(counts)
+        counts = counts.cpu()
         cap = int(counts.max().item())
         buf = torch.zeros((cap, 9), dtype=torch.float64, device=device)
-        buf[: len(sv_id), :6] = pack
-        buf[: len(sv_id), 6:] = centres
+        buf[:n_loc] = pack
         parts = [torch.empty((cap, 9), dtype=torch.float64, device=device) for _ in range(world)]
         dist.all_gather(parts, buf)
+        if ev0 is not None:
+            ev1.record()
+            torch.cuda.synchronize()
+            timings["all_gather_ms"] = ev0.elapsed_time(ev1)
+            timings["all_gather_bytes_per_rank"] = cap * 9 * 8
         rows = torch.cat([parts[r][: int(counts[r])] for r in range(world)]).cpu().numpy()
     else:
-        rows = torch.cat([pack, torch.zeros((len(sv_id), 0), dtype=torch.float64, device=device)], 1).cpu().numpy()
-        rows = np.concatenate([rows[:, :6], centres.cpu().numpy()], 1)
+        rows = pack.cpu().numpy()
     ids = rows[:, 0].astype(np.int64)
     sv_interds = np.zeros(n_regions_total, np.float32)
     sv_interes = np.zeros(n_regions_total, np.float32)
@@ -142,13 +152,88 @@ def cuda_score_frame(n_frames: int, nei_num=24, dis_thresh=0.1, device="cuda"):
     return score
 
 
+def prob_inference_frame(engine, raw_dev, seed, inf_reps=8, want_feat=False):
+    """score/prob_inference.py:91-118 for ONE frame, everything on device: the ``inf_reps`` TTA views (voxelizer, F1) ->
+    network (engine) -> softmax / mean / argmax (tta_tail).  Returns (prob f32 [Np,C], pred i64 [Np][, out_feat f32 [Np,96]])."""
+    from . import score, voxelizer
+    coords, feats, inverse = voxelizer.tta_batch_gpu(raw_dev, seed=seed, inf_reps=inf_reps)
+    if want_feat:
+        logits, feat = engine(coords, feats, return_feat=True)
+        return score.tta_tail(logits, inverse, inf_reps, out_feat=feat)
+    return score.tta_tail(engine(coords, feats), inverse, inf_reps)
+
+
+def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: int, n_regions_total: int, seed=0, inf_reps=8,
+                         nei_num=24, dis_thresh=0.1, device="cuda", select_with=None, keep_scorer=False):
+    """BASELINE config 3 / 5 for ONE sequence on the ranks of the default process group (or one GPU):
+
+      frames shard as dataset/sk_dataloader.py:196-198 -> per own frame: H2D of the raw scan, pose registration (F2), 8-view
+      prob_inference, resident prob map + hash grid  ->  halo: the +-12 frame windows a rank does not own arrive by P2P
+      (xyz f64 + prob f32 per frame)  ->  inter-frame scoring + per-region means of the own frames  ->  ONE all_gather of
+      the region scores  ->  (optional) the global selection, replicated on every rank (it is sequential and tiny).
+
+    frame_source(fid) -> (raw f32 [Np,4] host (pinned) or device, pose 4x4 float64, sv_id int64 [R], regions) with regions the
+    reference's ``sv2point`` lists or a device CSR pair.  select_with = (sv_flags, train_point_num) runs ``select_regions``.
+    Returns (sv_interds, sv_interes, sv_pnums, sv_centers, flags or None, timings dict [ms, device events; host for selection])."""
+    import time
+    from . import score
+    dev = torch.device(device)
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+    own = frame_shard(n_frames, world, rank)
+    ev = lambda: torch.cuda.Event(enable_timing=True)          # noqa: E731
+    t = [ev() for _ in range(5)]
+    scorer = score.SequenceScorer(dev, nei_num, dis_thresh, n_total=n_frames)
+    timings: dict = {"frames_total": n_frames, "frames_own": len(own), "world": world}
+    t[0].record()
+    for fid in own:
+        raw, pose, sv_id, regions = frame_source(fid)
+        raw_dev = torch.as_tensor(raw).to(dev, non_blocking=True)
+        xyz = score.register_points(raw_dev, pose)
+        prob, _pred = prob_inference_frame(engine, raw_dev, seed + fid, inf_reps)
+        scorer.add_frame(xyz, prob, sv_id, regions, fid=fid)
+    t[1].record()
+    # ---- halo: neighbour-window frames owned by other ranks
+    if world > 1:
+        split = int(math.ceil(n_frames / world))
+        mine = torch.zeros(split, dtype=torch.int64, device=dev)
+        for j, fid in enumerate(own):
+            mine[j] = scorer.frames[fid].n
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)                              # point counts of every frame (sizes of the halo messages)
+        n_points = torch.cat(allc).cpu().tolist()[:n_frames]
+        local = {fid: (scorer.frames[fid].xyz, scorer.frames[fid].prob) for fid in own}
+        held = exchange_halo(local, n_points, n_cls, n_frames, nei_num, dev)
+        halo_bytes = 0
+        for fid, (xyz, prob) in held.items():
+            if fid not in scorer.frames:
+                scorer.add_frame(xyz, prob, fid=fid)
+                halo_bytes += xyz.numel() * 8 + prob.numel() * 4
+        timings["halo_frames_received"] = len(held) - len(own)
+        timings["halo_bytes_received"] = halo_bytes
+    t[2].record()
+    ids, d, e, pn, c = scorer.score_frames_device(list(own))
+    t[3].record()
+    out = gather_region_scores(ids, d, e, pn, c, n_regions_total, dev, timings)
+    t[4].record()
+    torch.cuda.synchronize(dev)
+    timings.update(prob_inference_ms=t[0].elapsed_time(t[1]), halo_ms=t[1].elapsed_time(t[2]), scoring_ms=t[2].elapsed_time(t[3]),
+                   gather_ms=t[3].elapsed_time(t[4]), device_total_ms=t[0].elapsed_time(t[4]))
+    flags = None
+    if select_with is not None:
+        h0 = time.perf_counter()
+        flags = score.select_regions(select_with[0], out[0], out[1], out[2], out[3], select_with[1], device=dev)
+        timings["selection_ms"] = (time.perf_counter() - h0) * 1e3
+    if keep_scorer:
+        timings["scorer"] = scorer
+    return out + (flags, timings)
+
+
 def infer_and_score_sequence(engine, raws, xyz, regions, seed=0, inf_reps=8, nei_num=24, dis_thresh=0.1, device="cuda"):
-    """The whole LiDAL chain for one sequence on ONE GPU, nothing leaves the device between stages:
-    raw scan -> 8 TTA views (voxelizer, F1) -> network (engine) -> softmax / mean / argmax (tta_tail) -> resident prob map
-    -> inter-frame divergence / entropy against the +-12 frame window -> per-region means.
+    """The whole LiDAL chain for one sequence on ONE GPU with caller-registered coordinates (kept for callers that hold
+    KD-tree pickles): raw scan -> 8 TTA views -> network -> tail -> resident prob map -> inter-frame scoring -> region means.
     raws: per-frame float32 [Np,4] sensor-frame points (host or device); xyz: per-frame float64 [Np,3] registered coordinates;
     regions: per-frame (sv_id, sv2point).  Returns (per-frame worker_func tuples, timings dict in ms)."""
-    from . import score, voxelizer
+    from . import score
     dev = torch.device(device)
     ev = lambda: torch.cuda.Event(enable_timing=True)          # noqa: E731
     t0, t1, t2 = ev(), ev(), ev()
@@ -156,9 +241,7 @@ def infer_and_score_sequence(engine, raws, xyz, regions, seed=0, inf_reps=8, nei
     t0.record()
     for i, raw in enumerate(raws):
         raw_dev = torch.as_tensor(raw).to(dev)
-        coords, feats, inverse = voxelizer.tta_batch_gpu(raw_dev, seed=seed + i, inf_reps=inf_reps)
-        logits = engine(coords, feats)
-        prob, _pred = score.tta_tail(logits, inverse, inf_reps)
+        prob, _pred = prob_inference_frame(engine, raw_dev, seed + i, inf_reps)
         scorer.add_frame(xyz[i], prob, *regions[i])
     t1.record()
     out = [scorer.score_frame(i) for i in range(len(raws))]

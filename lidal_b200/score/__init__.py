@@ -29,10 +29,11 @@ def _ws(nbytes, device):
 
 
 # ------------------------------------------------------------------------------------------- prob_inference tail
-def tta_tail(logits: torch.Tensor, inverse_indices: torch.Tensor, inf_reps: int):
+def tta_tail(logits: torch.Tensor, inverse_indices: torch.Tensor, inf_reps: int, out_feat: torch.Tensor | None = None):
     """logits f32 [Nv, C] (all views stacked), inverse_indices int64 [inf_reps * Np]
-    -> (prob_map_mean f32 [Np, C], pred int64 [Np]), both on device."""
-    L.require_cuda(logits, inverse_indices)
+    -> (prob_map_mean f32 [Np, C], pred int64 [Np]), both on device.  With ``out_feat`` (the model's second output,
+    [Nv, 96], any float type) also its per-point mean over the views, f32 [Np, 96] (score/prob_inference.py:103-105,116-118)."""
+    L.require_cuda(logits, inverse_indices, out_feat)
     logits = logits.contiguous().float()
     inv = inverse_indices.contiguous().long()
     assert inv.numel() % inf_reps == 0
@@ -41,7 +42,36 @@ def tta_tail(logits: torch.Tensor, inverse_indices: torch.Tensor, inf_reps: int)
     pred = torch.empty(n_pts, dtype=torch.int64, device=logits.device)
     L.check(L.lib().lb_tta_softmax_mean_argmax(L.ptr(logits), logits.shape[0], n_cls, L.ptr(inv), inf_reps, n_pts,
                                                L.ptr(prob), L.ptr(pred), L.stream()))
-    return prob, pred
+    if out_feat is None:
+        return prob, pred
+    assert out_feat.shape[0] == logits.shape[0] and out_feat.stride(1) == 1
+    c = out_feat.shape[1]
+    feat = torch.empty((n_pts, c), dtype=torch.float32, device=logits.device)
+    L.check(L.lib().lb_tta_feat_mean(L.ptr(out_feat), L.DT_OF[out_feat.dtype], out_feat.stride(0), out_feat.shape[0], L.ptr(inv),
+                                     inf_reps, n_pts, c, L.ptr(feat), L.stream()))
+    return prob, pred, feat
+
+
+def register_points(raw: torch.Tensor, pose) -> torch.Tensor:
+    """dataset/prepare_kdtree_sk.py:76-80 on device: raw f32 [Np, >=3] sensor-frame points, pose 4x4 float64 (sensor -> world)
+    -> registered float64 [Np, 3], bit-equal to the numpy expression."""
+    L.require_cuda(raw)
+    raw = raw.float()
+    if raw.stride(1) != 1:
+        raw = raw.contiguous()
+    n = raw.shape[0]
+    xyz = torch.empty((n, 3), dtype=torch.float64, device=raw.device)
+    pose = np.ascontiguousarray(np.asarray(pose, dtype=np.float64)).reshape(16)
+    L.check(L.lib().lb_register_points(L.ptr(raw), raw.stride(0), n, (C.c_double * 16)(*pose.tolist()), L.ptr(xyz), L.stream()))
+    return xyz
+
+
+def regions_to_csr(sv2point, device):
+    """The reference's ragged ``sv2point`` lists -> (region_ptr int32 [R+1], region_pts int32 [sum]) on device."""
+    ptr = np.zeros(len(sv2point) + 1, np.int32)
+    ptr[1:] = np.cumsum([len(p) for p in sv2point])
+    pts = np.concatenate([np.asarray(p, np.int32) for p in sv2point]) if len(sv2point) else np.zeros(0, np.int32)
+    return torch.from_numpy(ptr).to(device), torch.from_numpy(pts.astype(np.int32)).to(device)
 
 
 # ------------------------------------------------------------------------------------------- per-frame scoring
@@ -91,11 +121,11 @@ class SequenceScorer:
         return f
 
     def set_regions(self, f: Frame, sv_id, sv2point):
-        ptr = np.zeros(len(sv2point) + 1, np.int32)
-        ptr[1:] = np.cumsum([len(p) for p in sv2point])
-        pts = np.concatenate([np.asarray(p, np.int32) for p in sv2point]) if len(sv2point) else np.zeros(0, np.int32)
-        f.region_ptr = torch.from_numpy(ptr).to(self.device)
-        f.region_pts = torch.from_numpy(pts.astype(np.int32)).to(self.device)
+        """sv2point: the reference's list of index arrays, or an already built device CSR pair (region_ptr, region_pts)."""
+        if isinstance(sv2point, tuple) and len(sv2point) == 2 and torch.is_tensor(sv2point[0]):
+            f.region_ptr, f.region_pts = (t.to(self.device, torch.int32).contiguous() for t in sv2point)
+        else:
+            f.region_ptr, f.region_pts = regions_to_csr(sv2point, self.device)
         f.sv_id = np.asarray(sv_id)
 
     def score_points(self, fid: int, want_nn=False):
@@ -128,6 +158,14 @@ class SequenceScorer:
                                          L.ptr(q.region_pts), r, L.ptr(sv_d), L.ptr(sv_e), L.ptr(sv_n), L.ptr(sv_c),
                                          L.stream()))
         return sv_d, sv_e, sv_n, sv_c
+
+    def score_frames_device(self, fids):
+        """``score_frame_device`` for several frames; results concatenated on device in ``fids`` order, plus the matching
+        sv_id vector (host int64).  No host synchronisation."""
+        outs = [self.score_frame_device(f) for f in fids]
+        cat = lambda i, shape, dt: (torch.cat([o[i] for o in outs]) if outs else torch.zeros(shape, dtype=dt, device=self.device))  # noqa: E731
+        ids = np.concatenate([np.asarray(self.frames[f].sv_id, np.int64) for f in fids]) if len(fids) else np.zeros(0, np.int64)
+        return ids, cat(0, 0, torch.float32), cat(1, 0, torch.float32), cat(2, 0, torch.int64), cat(3, (0, 3), torch.float32)
 
     def score_frame(self, fid: int, sv_pre=False):
         """The reference's ``worker_func`` return tuple (numpy, dtypes int64 / f32 / f32 / int64 / f32)."""
@@ -180,6 +218,82 @@ def frame_level_scores(prob: torch.Tensor):
     return ent, mar, conf
 
 
+def segment_entropy(pred: torch.Tensor, sv2point, n_cls: int) -> float:
+    """score/frame_level/segment_entropy.py:41-48 for one frame: pred int64 [Np] on device, regions as the reference's
+    ``sv2point`` lists or a device CSR pair."""
+    L.require_cuda(pred)
+    pred = pred.contiguous().long()
+    ptr, pts = sv2point if (isinstance(sv2point, tuple) and torch.is_tensor(sv2point[0])) else regions_to_csr(sv2point, pred.device)
+    r = ptr.numel() - 1
+    out = torch.empty(1, dtype=torch.float64, device=pred.device)
+    ws = _ws(max(r, 1) * 8, pred.device)
+    L.check(L.lib().lb_segment_entropy(L.ptr(pred), pred.numel(), n_cls, L.ptr(ptr), L.ptr(pts), r, L.ptr(out), L.ptr(ws), ws.numel(),
+                                       L.stream()))
+    return float(out.item())
+
+
+REDAL_ALPHA, REDAL_GAMMA, REDAL_FT_DIM = 1.0, 0.05, 96          # score/sv_level/ReDAL.py:15-21
+
+
+def redal_region_scores(prob: torch.Tensor, outfeat: torch.Tensor, curvature, sv_id, sv2point, sv_pre: bool = False):
+    """score/sv_level/ReDAL.py:37-84 (``worker_func``) for one frame on device: prob f32 [Np, C], outfeat f32 [Np, 96] (the
+    TTA-mean out_feat of ``tta_tail``), curvature f32 [Np] or None.  Returns the reference's tuple
+    (sv_id, sv_scores f32 [R], sv_feats f32 [R, 96][, sv_pnums int [R]]) as numpy."""
+    L.require_cuda(prob, outfeat)
+    dev = prob.device
+    prob = prob.contiguous().float()
+    outfeat = outfeat.contiguous().float()
+    n, n_cls = prob.shape
+    assert outfeat.shape[0] == n and outfeat.shape[1] == REDAL_FT_DIM
+    curv = None if curvature is None else torch.as_tensor(curvature).to(dev, torch.float32).contiguous()
+    ptr, pts = sv2point if (isinstance(sv2point, tuple) and torch.is_tensor(sv2point[0])) else regions_to_csr(sv2point, dev)
+    r = ptr.numel() - 1
+    point_score = torch.empty(n, dtype=torch.float32, device=dev)
+    L.check(L.lib().lb_redal_point_scores(L.ptr(prob), n, n_cls, L.ptr(curv), REDAL_ALPHA, REDAL_GAMMA, L.ptr(point_score), L.stream()))
+    sv_scores = torch.empty(r, dtype=torch.float32, device=dev)
+    sv_feats = torch.empty((r, REDAL_FT_DIM), dtype=torch.float32, device=dev)
+    L.check(L.lib().lb_region_mean_f32(L.ptr(point_score), L.ptr(ptr), L.ptr(pts), r, L.ptr(sv_scores), L.stream()))
+    L.check(L.lib().lb_region_feat_mean(L.ptr(outfeat), outfeat.stride(0), REDAL_FT_DIM, L.ptr(ptr), L.ptr(pts), r, L.ptr(sv_feats),
+                                        L.stream()))
+    out = (np.asarray(sv_id), sv_scores.cpu().numpy(), sv_feats.cpu().numpy())
+    if sv_pre:
+        return out
+    return out + ((ptr[1:] - ptr[:-1]).cpu().numpy().astype(int),)
+
+
+# ------------------------------------------------------------------------------------------- multi-sequence driver
+def score_dataset(sequences, nei_num=24, dis_thresh=0.1, n_regions_total=None, sv_pnums=None, sv_centers=None, device="cuda"):
+    """score/sv_level/LiDAL.py:163-222: every sequence is scored on its own (no connections between sequences) and the
+    per-region values are scattered into the global arrays by ``sv_id``.  ``sequences`` is a list of
+    (prob_files, kdtree_files, sv_info_files) triples in ``train_split`` order -- file paths in the reference's formats or
+    in-memory arrays, as for ``init_worker``.  If ``sv_pnums`` / ``sv_centers`` are given (the reference's cached
+    sv_pnums.npy / sv_centers.npy, LiDAL.py:171-175) they are reused (``sv_pre``); otherwise they are computed, with
+    ``idx * 1000.0`` added to the centres of sequence idx (LiDAL.py:218).
+    Returns (sv_interds f32, sv_interes f32, sv_pnums int, sv_centers f32 [.,3], sv_pre)."""
+    sv_pre = sv_pnums is not None and sv_centers is not None
+    results = []
+    for idx, (prob_files, kdtree_files, sv_info_files) in enumerate(sequences):
+        assert len(prob_files) == len(kdtree_files) == len(sv_info_files)                          # :199-200
+        init_worker(sv_pre, nei_num, dis_thresh, idx, prob_files, kdtree_files, sv_info_files, device=device)
+        scorer = var_dict["scorer"]
+        results.append((idx, scorer.score_frames_device(list(range(len(prob_files))))))
+        scorer.frames.clear()                                                                      # free the sequence's HBM
+    if n_regions_total is None:
+        n_regions_total = 1 + max((int(ids.max()) for _, (ids, *_r) in results if len(ids)), default=-1)
+    sv_interds = np.zeros(n_regions_total, np.float32)                                             # :164-166
+    sv_interes = np.zeros(n_regions_total, np.float32)
+    if not sv_pre:
+        sv_pnums = np.zeros(n_regions_total, int)                                                  # :178-180
+        sv_centers = np.zeros((n_regions_total, 3), np.float32)
+    for idx, (ids, d, e, pn, c) in results:
+        sv_interds[ids] = d.cpu().numpy()                                                          # :208-216
+        sv_interes[ids] = e.cpu().numpy()
+        if not sv_pre:
+            sv_pnums[ids] = pn.cpu().numpy().astype(int)
+            sv_centers[ids] = c.cpu().numpy() + idx * 1000.0                                       # :218 (float32 + python float -> float32)
+    return sv_interds, sv_interes, sv_pnums, sv_centers, sv_pre
+
+
 # ------------------------------------------------------------------------------------------- selection
 def argsort_f32(keys: torch.Tensor) -> torch.Tensor:
     L.require_cuda(keys)
@@ -193,7 +307,8 @@ def argsort_f32(keys: torch.Tensor) -> torch.Tensor:
 
 
 def region_pairs(centers: torch.Tensor, radius: float):
-    """CSR (row_ptr int64 [n+1], idx int32 [nnz]) of regions with float32 distance < radius (LiDAL.py:252-254)."""
+    """CSR (row_ptr int64 [n+1], idx int32 [nnz]) of regions with float32 distance < radius (LiDAL.py:252-254).  Kept as a
+    device utility (all-pairs lists); ``select_regions`` no longer needs it -- it indexes only the regions added so far."""
     L.require_cuda(centers)
     centers = centers.contiguous().float()
     n = centers.shape[0]
@@ -203,23 +318,82 @@ def region_pairs(centers: torch.Tensor, radius: float):
     L.check(L.lib().lb_region_pairs(L.ptr(centers), n, float(radius), L.ptr(counts), None, L.ptr(ws), nbytes, L.stream()))
     row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=centers.device)
     row_ptr[1:] = torch.cumsum(counts, 0)
+    nnz = int(row_ptr[-1].item())
+    if nnz >= 2 ** 31:
+        raise L.LidalError(f"region_pairs: {nnz} pairs exceed the int32 offsets of lb_region_pairs; build the lists in chunks")
     offs = row_ptr[:-1].to(torch.int32).contiguous()
-    idx = torch.empty(max(int(row_ptr[-1].item()), 1), dtype=torch.int32, device=centers.device)
+    idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=centers.device)
     L.check(L.lib().lb_region_pairs(L.ptr(centers), n, float(radius), L.ptr(offs), L.ptr(idx), L.ptr(ws), nbytes, L.stream()))
-    return row_ptr, idx[: int(row_ptr[-1].item())]
+    return row_ptr, idx[:nnz]
 
 
-def _greedy_walk(order, cand_ids, interds, interes, pnums, row_ptr, nbr_idx, flags, flag_value, point_limit,
-                 prefer_higher_entropy, skip_zero):
-    """Host replay of LiDAL.py:242-270 / 293-325.  The reference scans a CPython ``set`` and stops at the FIRST
-    member within 5 m; which member that is depends on the set's iteration order, so the same add / remove
-    sequence is fed to a real ``set`` and its order is consulted only when two or more members are in range."""
+_CELL_BIAS = 1 << 20
+_CELL_NBRS = [(dx << 42) + (dy << 21) + dz for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)]
+
+
+def region_cells(centers: np.ndarray, radius: float):
+    """One integer key per region: its cell in a grid of ``radius``-sized cells (anything closer than ``radius`` lies in
+    the 27 surrounding cells).  Python ints so that dict lookups in the greedy walk stay cheap."""
+    c = np.floor(np.asarray(centers, np.float64) / float(radius)).astype(np.int64) + _CELL_BIAS
+    return ((c[:, 0] << 42) | (c[:, 1] << 21) | c[:, 2]).tolist()
+
+
+class _GridIndex:
+    """The regions added so far, indexed by 5 m cells (cost independent of the dataset size); distances are the
+    reference's float32 expression ``np.sqrt(np.square(a - b).sum())`` (LiDAL.py:252)."""
+
+    def __init__(self, centers, cells, radius):
+        self.centers, self.cells, self.thr, self.grid = centers, cells, np.float32(radius), {}
+
+    def near(self, sv):
+        key = self.cells[sv]
+        pool = []
+        for dk in _CELL_NBRS:
+            lst = self.grid.get(key + dk)
+            if lst:
+                pool.extend(lst)
+        if not pool:
+            return pool
+        arr = np.asarray(pool, dtype=np.int64)
+        dist = np.sqrt(np.square(self.centers[sv] - self.centers[arr]).sum(1))     # float32, same operation order
+        return arr[dist < self.thr].tolist()
+
+    def add(self, sv):
+        self.grid.setdefault(self.cells[sv], []).append(sv)
+
+    def remove(self, sv):
+        self.grid[self.cells[sv]].remove(sv)
+
+
+class _CsrIndex:
+    """All in-range pairs precomputed on device (``region_pairs``): a candidate's lookups are set-membership tests only."""
+
+    def __init__(self, row_ptr, nbr_idx):
+        self.row_ptr, self.nbr_idx, self.members = row_ptr, nbr_idx, set()
+
+    def near(self, sv):
+        m = self.members
+        return [j for j in self.nbr_idx[self.row_ptr[sv]:self.row_ptr[sv + 1]] if j in m]
+
+    def add(self, sv):
+        self.members.add(sv)
+
+    def remove(self, sv):
+        self.members.discard(sv)
+
+
+def _greedy_walk(order, cand_ids, interds, interes, pnums, index, flags, flag_value, point_limit, prefer_higher_entropy, skip_zero):
+    """Host replay of LiDAL.py:242-270 / 293-325.  The reference scans a CPython ``set`` of the regions added so far and
+    stops at the FIRST member within 5 m; which member that is depends on the set's iteration order, so the same add /
+    remove sequence is fed to a real ``set`` and its order is consulted only when two or more members are in range.
+    ``index`` answers "which added regions lie within 5 m of this candidate" (_GridIndex or _CsrIndex)."""
     added = set()
-    for idx in order:
-        if skip_zero and interds[cand_ids[idx]] == 0:
+    cand_list = cand_ids.tolist()
+    for idx in order.tolist():
+        sv = cand_list[idx]                                  # hash(int) == hash(np.int64): same set order as the reference
+        if skip_zero and interds[sv] == 0:
             continue
-        sv = cand_ids[idx]                                   # np.int64, hashed like the reference's elements
-        near = [j for j in nbr_idx[row_ptr[sv]:row_ptr[sv + 1]] if j in added]
+        near = index.near(sv)
         if near:
             hit = near[0]
             if len(near) > 1:
@@ -231,6 +405,8 @@ def _greedy_walk(order, cand_ids, interds, interes, pnums, row_ptr, nbr_idx, fla
                 flags[hit] = 0
                 added.add(sv)
                 added.remove(hit)
+                index.remove(hit)
+                index.add(sv)
                 point_limit = point_limit + pnums[hit] - pnums[sv]
             continue
         point_limit -= pnums[sv]
@@ -238,30 +414,57 @@ def _greedy_walk(order, cand_ids, interds, interes, pnums, row_ptr, nbr_idx, fla
             break
         flags[sv] = flag_value
         added.add(sv)
+        index.add(sv)
     return flags
 
 
+CSR_MAX_PAIRS = 1 << 27          # above this the all-pairs lists are not built (memory); the grid index is used instead
+
+
 def select_regions(sv_flags, sv_interds, sv_interes, sv_pnums, sv_centers, train_point_num, sv_dis_thresh=5.0,
-                   device="cuda"):
-    """LiDAL.py:230-325.  Inputs are the global per-region arrays (numpy); returns int flags (0 / 1 labelled / 2 pseudo)."""
+                   device="cuda", method="auto"):
+    """LiDAL.py:230-325.  Inputs are the global per-region arrays (numpy); returns int flags (0 / 1 labelled / 2 pseudo).
+
+    The two sorts run on device (radix argsort of the unlabelled regions' divergence, LiDAL.py:235,283) and so does the
+    5 m neighbourhood search (``region_pairs``, a hash grid over all centres) unless the pair lists would be too large
+    (``method="grid"``: only the added regions are indexed, on the host).  The greedy walk is inherently sequential and
+    is replayed on the host.  Ties: the reference's ``np.argsort`` is an unstable introsort, so the visiting order of EQUAL
+    keys is only defined by numpy itself -- when the device sort sees equal keys it falls back to ``np.argsort`` for
+    that pass, so the selected ids stay identical to the reference's in every case."""
     dev = torch.device(device)
     flags = np.asarray(sv_flags).astype(int)
-    d_dev = torch.as_tensor(np.asarray(sv_interds, np.float32)).to(dev)
-    row_ptr, nbr_idx = region_pairs(torch.as_tensor(np.asarray(sv_centers, np.float32)).to(dev), sv_dis_thresh)
-    row_ptr, nbr_idx = row_ptr.cpu().numpy(), nbr_idx.cpu().numpy().astype(np.int64)
     interds, interes = np.asarray(sv_interds), np.asarray(sv_interes)
     pnums = np.asarray(sv_pnums)
+    centers = np.ascontiguousarray(np.asarray(sv_centers, np.float32))
+    d_dev = torch.as_tensor(np.asarray(sv_interds, np.float32)).to(dev)
+    csr = None
+    if method in ("auto", "csr"):
+        c_dev = torch.from_numpy(centers).to(dev)
+        counts = torch.zeros(centers.shape[0], dtype=torch.int32, device=dev)
+        nbytes = L.lib().lb_region_pairs_ws_bytes(centers.shape[0])
+        L.check(L.lib().lb_region_pairs(L.ptr(c_dev), centers.shape[0], float(sv_dis_thresh), L.ptr(counts), None,
+                                        L.ptr(_ws(nbytes, dev)), nbytes, L.stream()))
+        if method == "csr" or int(counts.sum(dtype=torch.int64).item()) <= CSR_MAX_PAIRS:
+            row_ptr, nbr_idx = region_pairs(c_dev, sv_dis_thresh)
+            csr = (row_ptr.cpu().tolist(), nbr_idx.cpu().tolist())
+    cells = None if csr is not None else region_cells(centers, sv_dis_thresh)
+
+    def new_index():
+        return _CsrIndex(*csr) if csr is not None else _GridIndex(centers, cells, sv_dis_thresh)
 
     def sorted_candidates():
         ids = np.where(flags == 0)[0]
-        ids_dev = torch.from_numpy(ids).to(dev)
-        order = argsort_f32(d_dev[ids_dev]).cpu().numpy()
+        keys = d_dev[torch.from_numpy(ids).to(dev)]
+        order_dev = argsort_f32(keys)
+        sk = keys[order_dev.long()]
+        has_ties = bool((sk[1:] == sk[:-1]).any().item()) if ids.size > 1 else False
+        order = np.argsort(interds[ids]) if has_ties else order_dev.cpu().numpy()
         return ids, order
 
     ids, order = sorted_candidates()                                           # :232-235
     limit = round(0.01 * train_point_num)                                      # :240
-    _greedy_walk(order[::-1], ids, interds, interes, pnums, row_ptr, nbr_idx, flags, 1, limit, True, False)
+    _greedy_walk(order[::-1], ids, interds, interes, pnums, new_index(), flags, 1, limit, True, False)
     ids, order = sorted_candidates()                                           # :281-283 (before the reset)
     flags[flags == 2] = 0                                                      # :286
-    _greedy_walk(order, ids, interds, interes, pnums, row_ptr, nbr_idx, flags, 2, limit, False, True)
+    _greedy_walk(order, ids, interds, interes, pnums, new_index(), flags, 2, limit, False, True)
     return flags

@@ -199,3 +199,95 @@ def synthetic_probs(xyz: np.ndarray, n_cls: int, seed: int, noise: float = 0.6) 
     logits -= logits.max(1, keepdims=True)
     e = np.exp(logits)
     return (e / e.sum(1, keepdims=True)).astype(np.float32)
+
+
+def region_table(n_frames: int, seed: int = 0, regions_per_frame: int = 20, labelled_frac: float = 0.01):
+    """Per-region arrays shaped like a scored driving sequence (inputs of the global selection, LiDAL.py:230-325):
+    ``regions_per_frame`` azimuth sectors around an ego that advances 1 m per frame, so regions of nearby frames overlap
+    within the 5 m rule.  Returns (sv_flags int, sv_interds f32, sv_interes f32, sv_pnums int, sv_centers f32 [.,3]);
+    ``labelled_frac`` of the frames start fully labelled (dataset/sk_dataloader.py:99-118)."""
+    rng = np.random.default_rng(seed)
+    n = n_frames * regions_per_frame
+    frame = np.repeat(np.arange(n_frames), regions_per_frame)
+    sector = np.tile(np.arange(regions_per_frame), n_frames)
+    ang = (sector + 0.5) / regions_per_frame * 2 * math.pi
+    rad = rng.uniform(4.0, 18.0, n)
+    centers = np.stack([frame * 1.0 + rad * np.cos(ang), rad * np.sin(ang), rng.uniform(-0.5, 1.5, n)], 1).astype(np.float32)
+    interds = rng.gamma(2.0, 0.05, n).astype(np.float32)
+    interds[rng.random(n) < 0.01] = 0.0                      # regions without a single matched point
+    interes = rng.uniform(0.1, 2.5, n).astype(np.float32)
+    pnums = rng.integers(6200, 6900, n)
+    flags = np.zeros(n, int)
+    lab = rng.choice(n_frames, max(1, int(round(labelled_frac * n_frames))), replace=False)
+    flags[np.isin(frame, lab)] = 1
+    return flags, interds, interes, pnums.astype(int), centers
+
+
+# ------------------------------------------------------------------------------------------- device-side generator
+def raycast_scan_gpu(seed: int, kind: str, pose: np.ndarray, device):
+    """``raycast_scan`` with torch ops on ``device`` (same world, same sensor model; the noise stream is torch's, so the
+    points differ from the numpy version in the last digits).  Used to synthesise long sequences for the benchmark without
+    minutes of host ray casting.  Returns float32 [Np, 4] on device."""
+    import torch
+    beams, top, bot, steps, height, rmin, rmax, _ = SENSORS[kind]
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    f64 = torch.float64
+    elev = torch.deg2rad(torch.linspace(top, bot, beams, dtype=f64, device=device))
+    az0 = float(torch.rand(1, generator=g, device=device, dtype=f64).item()) * 2 * math.pi / steps
+    azim = torch.arange(steps, dtype=f64, device=device) * (2 * math.pi / steps) - math.pi + az0
+    el, az = torch.meshgrid(elev, azim, indexing="ij")
+    d_s = torch.stack([torch.cos(el) * torch.cos(az), torch.cos(el) * torch.sin(az), torch.sin(el)], -1).reshape(-1, 3)
+    rot = torch.as_tensor(pose[:3, :3], dtype=f64, device=device)
+    org = [float(v) for v in pose[:3, 3]]
+    d_w = d_s @ rot.T
+    inf = torch.full((d_w.shape[0],), float("inf"), dtype=f64, device=device)
+    t_best = torch.where(d_w[:, 2] < -1e-6, -org[2] / d_w[:, 2], inf)
+
+    def wall(x, side):
+        return side * (12.0 + 3.0 * torch.sin(x / 15.0 + (0.7 if side > 0 else 2.1)) + 1.0 * torch.sin(x / 4.0 + 1.3 * side))
+
+    for side in (1.0, -1.0):
+        ok = d_w[:, 1] * side > 1e-3
+        x0 = torch.full_like(t_best, org[0])
+        t = torch.where(ok, (wall(x0, side) - org[1]) / d_w[:, 1], inf)
+        for _ in range(6):
+            xw = org[0] + torch.where(torch.isfinite(t), t, torch.zeros_like(t)) * d_w[:, 0]
+            t = torch.where(ok, (wall(xw, side) - org[1]) / d_w[:, 1], inf)
+        zw = org[2] + torch.where(torch.isfinite(t), t, torch.zeros_like(t)) * d_w[:, 2]
+        t = torch.where((zw >= 0.0) & (zw <= WALL_HEIGHT) & (t > 0), t, inf)
+        t_best = torch.minimum(t_best, t)
+    r = t_best + torch.randn(t_best.shape, generator=g, device=device, dtype=f64) * 0.02
+    keep = torch.isfinite(t_best) & (r > rmin) & (r < rmax)
+    pts = d_s[keep] * r[keep, None]
+    inten = torch.rand(pts.shape[0], generator=g, device=device, dtype=f64)
+    return torch.cat([pts, inten[:, None]], 1).float().contiguous()
+
+
+def balanced_regions_gpu(raw, n_regions: int = 20):
+    """``balanced_regions`` on device: equal-count azimuth sectors as a CSR pair (region_ptr int32 [R+1], region_pts int32 [Np],
+    point ids ascending inside a region -- the order ``np.where(label == r)[0]`` gives)."""
+    import torch
+    n = raw.shape[0]
+    order = torch.sort(torch.atan2(raw[:, 1], raw[:, 0]), stable=True).indices
+    bounds = torch.linspace(0, n, n_regions + 1, dtype=torch.float64).to(torch.int64)
+    label = torch.empty(n, dtype=torch.int64, device=raw.device)
+    sizes = (bounds[1:] - bounds[:-1]).to(raw.device)
+    label[order] = torch.repeat_interleave(torch.arange(n_regions, device=raw.device), sizes)
+    pts = torch.sort(label, stable=True).indices.to(torch.int32)
+    return bounds.to(torch.int32).to(raw.device), pts.contiguous()
+
+
+class GpuSequence:
+    """A synthetic driving sequence generated on device, frame by frame: ``frame(fid)`` -> (raw f32 [Np,4] on device,
+    pose float64 4x4, sv_id int64 [R], (region_ptr, region_pts) device CSR).  ``sv_id`` numbers regions globally across the
+    sequence (dataset/prepare_supervoxel_kmeans_sk.py:67-69)."""
+
+    def __init__(self, n_frames: int, kind: str = "SK", seed: int = 0, device="cuda", n_regions: int = 20, sv_id_start: int = 0):
+        self.n_frames, self.kind, self.seed, self.device, self.n_regions, self.sv_id_start = n_frames, kind, seed, device, n_regions, sv_id_start
+
+    def frame(self, fid: int):
+        pose = make_pose(fid, SENSORS[self.kind][4])
+        raw = raycast_scan_gpu(self.seed * 100003 + fid, self.kind, pose, self.device)
+        sv_id = np.arange(self.n_regions, dtype=np.int64) + self.sv_id_start + fid * self.n_regions
+        return raw, pose, sv_id, balanced_regions_gpu(raw, self.n_regions)

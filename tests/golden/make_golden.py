@@ -9,6 +9,12 @@ What it pins:
                  oracle torchsparse restatement: logits slices + checksums, kernel-map sizes/checksums.
   hash.npz       sphash known answers from an independent pure-Python-int FNV-1a.
 
+  voxelizer.npz  the reference's own ``dataset.sk_dataset.SK_Dataset`` ('score' mode, ``__getitem__`` x 8 + ``collate_fn``) on a
+                 synthetic .bin file under ``np.random.seed`` == oracle.lidal_extra.score_batch == lidal_b200.synth.tta_batch.
+  extra.npz      the reference's own ``dataset.prepare_kdtree_sk.process_frame`` (registered coordinates read back from the
+                 KD-tree pickle), ``score.frame_level.segment_entropy.worker_func`` and ``score.sv_level.ReDAL.worker_func``
+                 on synthetic files == oracle.lidal_extra.{register_points, segment_entropy, redal_worker} (exact).
+
 Run:  python tests/golden/make_golden.py
 """
 import hashlib
@@ -187,7 +193,88 @@ def gen_nets():
     np.savez_compressed(f"{OUT}/nets.npz", **out)
 
 
+def gen_voxelizer():
+    import lidal_extra as ox
+    from dataset.sk_dataset import SK_Dataset            # the reference's dataset class, unmodified
+    raw = synth.raycast_scan(21, "NU")[::3]
+    seed, reps = 3, 8
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(f"{d}/Processing_files/SK")
+        os.makedirs(f"{d}/sequences/00/velodyne")
+        path = f"{d}/sequences/00/velodyne/000000.bin"
+        raw.tofile(path)
+        os.chdir(d)
+        try:
+            ds = SK_Dataset("score", [path] * reps)
+            np.random.seed(seed)
+            batch = ds.collate_fn([ds[i] for i in range(reps)])
+        finally:
+            os.chdir(cwd)
+    coords, feats, inv = batch["coords_v_b"].numpy(), batch["feats_v_b"].numpy(), batch["inverse_indices_b"].numpy()
+    for name, fn in (("oracle.lidal_extra.score_batch", ox.score_batch), ("lidal_b200.synth.tta_batch", synth.tta_batch)):
+        c2, f2, i2 = fn(raw, seed, reps)
+        assert c2.dtype == coords.dtype and np.array_equal(c2, coords), name
+        assert f2.dtype == feats.dtype and np.array_equal(f2, feats), name
+        assert np.array_equal(i2, inv), name
+    np.savez_compressed(f"{OUT}/voxelizer.npz", scan_seed=21, stride=3, seed=seed, reps=reps, n_vox=coords.shape[0],
+                        coords_sha=sha(coords), feats_sha=sha(feats), inverse_sha=sha(inv.astype(np.int64)),
+                        coords_head=coords[:256], feats_head=feats[:256], inverse_head=inv[:512])
+    print(f"voxelizer.npz: reference SK_Dataset('score') + collate_fn == oracle == synth on {raw.shape[0]} points, {coords.shape[0]} voxels")
+
+
+def gen_extra():
+    import lidal_extra as ox
+    import dataset.prepare_kdtree_sk as ref_kd
+    import score.frame_level.segment_entropy as ref_se
+    import score.sv_level.ReDAL as ref_redal
+    rng = np.random.default_rng(17)
+    seq = synth.make_sequence(2, "NU", seed=4, max_points=6000)
+    raw, pose = seq.raw[1], seq.poses[1]
+    sv_id, sv2point = seq.sv_id[1], seq.sv2point[1]
+    n, n_cls = raw.shape[0], 16
+    prob = synth.synthetic_probs(seq.xyz[1], n_cls, 9)
+    pred = np.argmax(prob, 1)
+    outfeat = rng.normal(0, 1, (n, 96)).astype(np.float32)
+    curvature = rng.random(n)                                  # float64 on disk; ReDAL.py:57 casts to float32
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(f"{d}/Processing_files/SK/kdtree/00")
+        os.makedirs(f"{d}/sequences/00/velodyne")
+        path = f"{d}/sequences/00/velodyne/000001.bin"
+        raw.tofile(path)
+        os.chdir(d)
+        try:
+            with redirect_stdout(io.StringIO()):
+                ref_kd.process_frame(0, [path], [pose])
+            with open("Processing_files/SK/kdtree/00/000001.pickle", "rb") as f:
+                xyz_ref = np.asarray(pickle.load(f).data)
+        finally:
+            os.chdir(cwd)
+        np.save(f"{d}/prob.npy", prob); np.save(f"{d}/pred.npy", pred); np.save(f"{d}/feat.npy", outfeat); np.save(f"{d}/curv.npy", curvature)
+        with open(f"{d}/sv.pickle", "wb") as f:
+            pickle.dump((sv_id, sv2point), f)
+        ref_se.init_worker(n_cls, "00", [f"{d}/pred.npy"], [f"{d}/sv.pickle"])
+        with redirect_stdout(io.StringIO()):
+            sege_ref = ref_se.worker_func(0)
+        ref_redal.init_worker(False, "00", [f"{d}/prob.npy"], [f"{d}/feat.npy"], [f"{d}/curv.npy"], [f"{d}/sv.pickle"])
+        with redirect_stdout(io.StringIO()):
+            redal_ref = ref_redal.worker_func(0)
+    xyz = ox.register_points(raw, pose)
+    assert xyz.dtype == xyz_ref.dtype and np.array_equal(xyz, xyz_ref), "register_points"
+    assert np.array_equal(xyz, seq.xyz[1]), "synth.make_sequence registration"
+    sege = ox.segment_entropy(pred, sv2point, n_cls)
+    assert sege == sege_ref, "segment_entropy"
+    mine = ox.redal_worker(prob, outfeat, curvature.astype(np.float32), sv_id, sv2point, False)
+    for a, b in zip(redal_ref, mine):
+        assert a.dtype == b.dtype and np.array_equal(a, b), "redal_worker"
+    np.savez_compressed(f"{OUT}/extra.npz", seq_seed=4, frame=1, max_points=6000, n_cls=n_cls, pose=pose, xyz_sha=sha(xyz_ref),
+                        xyz_head=xyz_ref[:64], segment_entropy=sege_ref, outfeat_seed=17, curvature=curvature,
+                        redal_scores=redal_ref[1], redal_feats=redal_ref[2], redal_pnums=redal_ref[3])
+    print(f"extra.npz: reference process_frame / segment_entropy / ReDAL worker == oracle on {n} points; sege={sege_ref:.6f}")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets"]
+    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets", "voxelizer", "extra"]
     for w in which:
         globals()[f"gen_{w}"]()

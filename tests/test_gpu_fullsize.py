@@ -82,3 +82,71 @@ def test_gpu_voxelizer_full_size_roundtrip(sk_batch):
     assert bool((key[1:] > key[:-1]).all())                                  # lexicographic (b, x, y, z), unique
     assert bool((c[:, :3] >= 0).all()) and bool((c[:, :3] < 8192).all())
     assert torch.unique(inv).numel() == c.shape[0]                           # every voxel is hit by at least one point
+
+
+# ------------------------------------------------------------------------------------------ oracle parity AT BASELINE size
+@pytest.mark.parametrize("name", ["minkunet", "spvcnn"])
+def test_engine_logits_vs_oracle_full_sk_scan(name, oracle_ts):
+    """One full SemanticKITTI-shaped scan (~100k voxels, BASELINE configs[0] shape) through the fused engine vs the reference's
+    network on the CPU oracle (a few seconds of host time): logits within 1e-2 relative, as north_star states for
+    bf16 operands / f32 accumulate vs the fp32 reference."""
+    import lidal_b200.compat as ts
+    from lidal_b200 import synth
+    from lidal_b200.engine import InferenceEngine
+    from lidal_b200.network import MinkUNet, SPVCNN, seeded_state_dict
+    raw = synth.raycast_scan(123, "SK")
+    coords, feats, _ = synth.tta_batch(raw, seed=3, inf_reps=1)
+    assert coords.shape[0] > 80_000
+    cls = MinkUNet if name == "minkunet" else SPVCNN
+    ref = cls(19, oracle_ts)
+    sd = seeded_state_dict(ref.state_dict())
+    ref.load_state_dict(sd); ref.eval()
+    torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
+    with torch.no_grad():
+        want, want_feat = ref(oracle_ts.SparseTensor(torch.from_numpy(feats), torch.from_numpy(coords)))
+    dev = cls(19, ts); dev.load_state_dict(sd); dev = dev.cuda().eval()
+    got, got_feat = InferenceEngine(dev)(torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda(), return_feat=True)
+    err = float((got.cpu().double() - want.double()).norm() / want.double().norm())
+    err_f = float((got_feat.float().cpu().double() - want_feat.double()).norm() / want_feat.double().norm())
+    agree = float((got.cpu().argmax(1) == want.argmax(1)).double().mean())
+    print(f"{name}: {coords.shape[0]} voxels, logits rel-L2 {err:.3e}, out_feat rel-L2 {err_f:.3e}, argmax agreement {agree:.4f}")
+    assert err < 1e-2 and err_f < 1e-2 and agree > 0.98
+
+
+def test_score_points_vs_oracle_full_sk_frame():
+    """One SK-sized query frame (~130k points) against its 24-frame window vs oracle.lidal_scoring.score_points (the
+    reference's KD-tree loop, LiDAL.py:59-81; about a minute of host time): match counts bit-exact, D / H within 1e-5."""
+    import lidal_scoring as orc
+    from lidal_b200 import score, synth
+    n_frames, fid = 25, 12
+    seq = synth.make_sequence(n_frames, "SK", seed=3)
+    probs = [synth.synthetic_probs(seq.xyz[i], 19, 900 + i) for i in range(n_frames)]
+    sc = score.SequenceScorer()
+    for i in range(n_frames):
+        sc.add_frame(seq.xyz[i], probs[i], seq.sv_id[i], seq.sv2point[i])
+    d, e, cnt = sc.score_points(fid)
+    nids = orc.neighbour_ids(fid, n_frames)
+    trees = orc.build_trees([seq.xyz[n] for n in nids])
+    want_d, want_e, want_c = orc.score_points(probs[fid], seq.xyz[fid], [probs[n] for n in nids], trees)
+    assert seq.xyz[fid].shape[0] > 120_000 and want_c.sum() > 1_000_000
+    assert np.array_equal(cnt.cpu().numpy(), want_c.astype(np.int32))
+    np.testing.assert_allclose(d.cpu().numpy(), want_d, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(e.cpu().numpy(), want_e, rtol=1e-5)
+    sv = sc.score_frame(fid)
+    want_sv = orc.reduce_regions(want_d, want_e, seq.xyz[fid], seq.sv_id[fid], seq.sv2point[fid])
+    assert np.array_equal(sv[0], want_sv[0]) and np.array_equal(sv[3], want_sv[3])
+    np.testing.assert_allclose(sv[1], want_sv[1], rtol=1e-5)
+    np.testing.assert_allclose(sv[2], want_sv[2], rtol=1e-5)
+
+
+def test_select_regions_vs_oracle_20k_regions():
+    """The global selection at config-3 size (1000 frames x 20 regions, budget of LiDAL.py:130) == oracle, both index paths."""
+    import lidal_scoring as orc
+    from lidal_b200 import score, synth
+    flags, d, e, pn, c = synth.region_table(1000, seed=1)
+    tpn = 2349559532
+    want = orc.select_regions(flags.astype(np.float64), d, e, pn, c, tpn)
+    for method in ("csr", "grid"):
+        got = score.select_regions(flags.copy(), d, e, pn, c, tpn, method=method)
+        assert np.array_equal(got, want), method
+    assert (want == 1).sum() > 500 and (want == 2).sum() > 500

@@ -123,3 +123,64 @@ def test_frame_level_baselines_vs_reference_formulas():
         np.testing.assert_allclose(ent, np.mean(entropy(prob, axis=1)), rtol=1e-5)
         np.testing.assert_allclose(mar, np.mean(srt[:, -1] - srt[:, -2]), rtol=1e-5)
         np.testing.assert_allclose(conf, np.mean(srt[:, -1]), rtol=1e-5)
+
+
+def _write_reference_files(d, seq, probs, sv_id_offset=0):
+    """The reference's on-disk ABI between prob_inference / pre-processing and scoring: prob .npy (score/prob_inference.py:129),
+    sklearn KDTree .pickle (dataset/prepare_kdtree_sk.py:83-88), (sv_id, sv2point) .pickle (prepare_supervoxel_kmeans_sk.py:60-74)."""
+    import pickle
+    from sklearn.neighbors import KDTree
+    pf, kf, sf = [], [], []
+    for i in range(seq.n_frames):
+        pf.append(f"{d}/p{i:06d}.npy"); np.save(pf[-1], probs[i])
+        kf.append(f"{d}/k{i:06d}.pickle")
+        with open(kf[-1], "wb") as f:
+            pickle.dump(KDTree(seq.xyz[i]), f)
+        sf.append(f"{d}/s{i:06d}.pickle")
+        with open(sf[-1], "wb") as f:
+            pickle.dump((seq.sv_id[i] + sv_id_offset, seq.sv2point[i]), f)
+    return pf, kf, sf
+
+
+def test_init_worker_from_reference_files(golden, tmp_path):
+    """B2 through the file-path branch: the same calls score/sv_level/LiDAL.py:204-206 makes, on files in the reference's formats."""
+    from make_golden import build_scoring_inputs, scoring_case
+    from lidal_b200 import score
+    seq, probs = build_scoring_inputs(scoring_case())
+    pf, kf, sf = _write_reference_files(str(tmp_path), seq, probs)
+    g = golden["scoring"]
+    for sv_pre in (False, True):
+        score.init_worker(sv_pre, 24, 0.1, "00", pf, kf, sf)
+        for i in (0, 7, 13, 25):
+            out = score.worker_func(i)
+            assert len(out) == (3 if sv_pre else 5)
+            assert np.array_equal(out[0], g["sv_id"][i]) and out[0].dtype == np.int64
+            np.testing.assert_allclose(out[1], g["sv_interds"][i], rtol=1e-5, atol=1e-9)
+            np.testing.assert_allclose(out[2], g["sv_interes"][i], rtol=1e-5)
+            if not sv_pre:
+                assert np.array_equal(out[3], g["sv_pnums"][i])
+                np.testing.assert_allclose(out[4], g["sv_centers"][i], rtol=1e-6, atol=1e-6)
+
+
+def test_score_dataset_multi_sequence(golden, tmp_path):
+    """LiDAL.py:185-222: per-sequence scoring scattered into the global arrays; centres of sequence idx shifted by idx * 1000
+    (:218); with cached sv_pnums / sv_centers (sv_pre, :171-175) only the two score arrays are filled."""
+    from make_golden import build_scoring_inputs, scoring_case
+    from lidal_b200 import score
+    seq, probs = build_scoring_inputs(scoring_case())
+    g = golden["scoring"]
+    n_seq_regions = int(g["sv_id"].max()) + 1
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    seq_a = _write_reference_files(str(tmp_path / "a"), seq, probs)
+    seq_b = _write_reference_files(str(tmp_path / "b"), seq, probs, sv_id_offset=n_seq_regions)
+    d, e, pn, c, sv_pre = score.score_dataset([seq_a, seq_b])
+    assert not sv_pre and d.shape[0] == 2 * n_seq_regions and d.dtype == np.float32 and c.dtype == np.float32
+    ids = g["sv_id"].reshape(-1)
+    for k, off in enumerate((0, n_seq_regions)):
+        np.testing.assert_allclose(d[ids + off], g["sv_interds"].reshape(-1), rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(e[ids + off], g["sv_interes"].reshape(-1), rtol=1e-5)
+        assert np.array_equal(pn[ids + off], g["sv_pnums"].reshape(-1))
+        np.testing.assert_allclose(c[ids + off], g["sv_centers"].reshape(-1, 3) + np.float32(k * 1000.0), rtol=1e-6, atol=1e-4)
+    assert np.array_equal(d[:n_seq_regions], d[n_seq_regions:])                 # same inputs, same bits
+    d2, e2, pn2, c2, sv_pre2 = score.score_dataset([seq_a, seq_b], sv_pnums=pn, sv_centers=c)
+    assert sv_pre2 and pn2 is pn and c2 is c and np.array_equal(d2, d) and np.array_equal(e2, e)

@@ -14,29 +14,49 @@ def test_neighbour_ids_match_oracle():
 def _cpu_pairs(centers, radius):
     rows, ptr = [], [0]
     for i in range(len(centers)):
-        d = np.sqrt(np.square(centers[i] - centers).sum(1, dtype=np.float32))
+        d = np.sqrt(np.square(centers[i] - centers).sum(1))
         near = np.where((d < radius) & (np.arange(len(centers)) != i))[0]
         rows.append(near)
         ptr.append(ptr[-1] + len(near))
-    return np.array(ptr), np.concatenate(rows).astype(np.int64)
+    return ptr, np.concatenate(rows).tolist()
+
+
+def _walk_both_passes(flags, d, e, pn, c, tpn, argsort, index="grid"):
+    cells = score.region_cells(c, 5.0)
+    csr = _cpu_pairs(c, np.float32(5.0)) if index == "csr" else None
+    new_index = (lambda: score._CsrIndex(*csr)) if csr else (lambda: score._GridIndex(c, cells, 5.0))
+    limit = round(0.01 * int(tpn))
+    ids = np.where(flags == 0)[0]
+    order = argsort(d[ids])
+    score._greedy_walk(order[::-1], ids, d, e, pn, new_index(), flags, 1, limit, True, False)
+    ids = np.where(flags == 0)[0]
+    order = argsort(d[ids])
+    flags[flags == 2] = 0
+    score._greedy_walk(order, ids, d, e, pn, new_index(), flags, 2, limit, False, True)
+    return flags
 
 
 def test_greedy_walk_replays_reference_selection(golden):
-    """The host replay (set-iteration-order exact) fed with CPU-built neighbour lists == reference golden flags."""
+    """The host replay (set-iteration-order exact, added regions indexed by a 5 m grid) == reference golden flags."""
     g = golden["selection"]
     for d_key, tpn_key, out_key in (("sv_interds", "tight_tpn", "tight_out"), ("loose_interds", "loose_tpn", "loose_out")):
-        flags = g["sv_flags"].astype(int)
-        d, e, pn, c = g[d_key], g["sv_interes"], g["sv_pnums"], g["sv_centers"]
-        ptr, idx = _cpu_pairs(c, np.float32(5.0))
-        limit = round(0.01 * int(g[tpn_key]))
-        ids = np.where(flags == 0)[0]
-        order = np.argsort(d[ids], kind="stable")
-        score._greedy_walk(order[::-1], ids, d, e, pn, ptr, idx, flags, 1, limit, True, False)
-        ids = np.where(flags == 0)[0]
-        order = np.argsort(d[ids], kind="stable")
-        flags[flags == 2] = 0
-        score._greedy_walk(order, ids, d, e, pn, ptr, idx, flags, 2, limit, False, True)
+        flags = _walk_both_passes(g["sv_flags"].astype(int), g[d_key], g["sv_interes"], g["sv_pnums"],
+                                  np.ascontiguousarray(g["sv_centers"], dtype=np.float32), g[tpn_key], np.argsort)
         assert np.array_equal(flags, g[out_key]), d_key
+
+
+def test_greedy_walk_vs_oracle_on_a_sequence_shaped_region_set():
+    """2,000 regions laid out like a driving sequence (20 sectors per frame, ego moving 1 m / frame): many candidates have
+    several added regions within 5 m, so the set-order rule and the swap branch are exercised; == oracle selection."""
+    import lidal_scoring as orc
+    sv_flags, d, e, pn, c = synth.region_table(100, seed=3)
+    tpn = int(pn.sum()) * 20            # budget = 20 % of the points: binds in both passes
+    want = orc.select_regions(sv_flags.copy(), d, e, pn, c, tpn)
+    got = _walk_both_passes(sv_flags.astype(int), d, e, pn, c, tpn, np.argsort)
+    assert np.array_equal(got, want)
+    got = _walk_both_passes(sv_flags.astype(int), d, e, pn, c, tpn, np.argsort, index="csr")
+    assert np.array_equal(got, want)
+    assert (got == 1).sum() > 20 and (got == 2).sum() > 20
 
 
 def test_synthetic_shapes():
