@@ -354,10 +354,21 @@ def main():
             result["roofline"] = conv_roofline(run, resident, steps=min(args.steps, 5))
         except Exception as e:      # noqa: BLE001
             result["roofline"] = {"error": repr(e)}
+        if eng is not None:
+            try:
+                from lidal_b200.profiling import stage_rooflines
+                result["roofline_by_stage"] = stage_rooflines(run, resident, steps=3)
+            except Exception as e:  # noqa: BLE001
+                result["roofline_by_stage"] = {"error": repr(e)}
         if not args.no_extras:
             try:
                 from lidal_b200.profiling import scoring_extras
                 result["extra"] = scoring_extras(result["ms_per_step"], dev, n_cls=N_CLS, engine=eng, kind=KIND)
+                rbs = result.get("roofline_by_stage")
+                if isinstance(rbs, dict) and "error" not in rbs:
+                    rbs["tta_tail"] = result["extra"]["tta_roofline"]
+                    rbs["interframe_scoring"] = result["extra"]["score_roofline"]
+                    rbs["frame_grid_build"] = result["extra"]["grid_roofline"]
             except Exception as e:  # noqa: BLE001
                 result["extra"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:

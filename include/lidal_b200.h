@@ -9,8 +9,10 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is DEVICE memory unless marked [host].
  *   - the caller owns all memory including workspaces (`*_bytes` helpers size them);
- *     no allocation, no host synchronisation and no global state inside a call
- *     (the exceptions are marked "syncs").
+ *     no device allocation and no host synchronisation inside a call (the exceptions are marked "syncs");
+ *     host-side state is limited to per-process caches (SM count, the driver's tensor-map encoder entry point,
+ *     the one-time shared-memory opt-in of each kernel) and the thread-local error text, so every call is
+ *     stream-capturable.
  *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
  *   - return value: LB_OK or a negative LB_E* code; `lb_last_error()` has the text.
  *   - there is NO CPU fallback: without a CUDA device every compute entry returns LB_ECUDA.
@@ -31,7 +33,7 @@ extern "C" {
 #define LB_ECAP (-2)   /* capacity / workspace too small                          */
 #define LB_ECUDA (-3)  /* CUDA runtime error or no device                         */
 
-#define LB_ABI_VERSION 1
+#define LB_ABI_VERSION 2
 
 int lb_abi_version(void);
 const char* lb_last_error(void); /* [host] thread-local text of the last failure */
@@ -169,7 +171,12 @@ typedef struct lb_conv_args {
   int act_dtype;           /* LB_DT_BF16 | LB_DT_F16                                         */
   int out_dtype;           /* LB_DT_BF16 | LB_DT_F16 | LB_DT_F32                             */
   int flags;
+  void* sched_ws;          /* optional device scratch of lb_conv_sched_ws_bytes() bytes, zeroed ONCE by the caller and
+                              private to one stream (launches on it are ordered; the kernel leaves it zeroed): enables
+                              the dynamic tile scheduler.  NULL = static round-robin tiles.                          */
 } lb_conv_args;
+
+size_t lb_conv_sched_ws_bytes(void);
 
 /* fp32 [k_vol, c_in, c_out] (the `kernel` parameter layout of spnn.Conv3d) -> 16-bit [k_vol, c_out, c_in]. */
 int lb_conv_pack_weight(const float* kernel, int k_vol, int c_in, int c_out, int act_dtype, void* packed,
@@ -286,11 +293,14 @@ typedef struct lb_frame_ref { /* one neighbouring frame, all device pointers */
  * intere = entropy(sum_prob / count) and interd /= (count-1) where > 0.
  * q_grid: the QUERY frame's own grid (its points are walked in cell-sorted order); q_prob in original row order.
  * nbrs: [host] array of n_nbr (<= 32) frames.  Outputs: interd f64 [nq], intere f32 [nq]; optional count int32 [nq]
- * (= matches).  nn int32 [nq, n_nbr] is REQUIRED scratch/output: phase 1 (one thread per point) stores the matched
- * neighbour row (or -1) per neighbour frame, phase 2 (one warp per point, lane = class) consumes it. */
+ * (= matches) and nn int32 [nq, n_nbr] (matched neighbour row or -1 per neighbour frame).  ws: scratch of
+ * lb_interframe_score_ws_bytes(nq, n_nbr) bytes -- phase 1 (one thread per (point, frame) pair: float32 screening on
+ * cell-relative coordinates, survivors in exact float64) stores its result there frame-major, phase 2 (one warp per
+ * point, lane = class) consumes it. */
+size_t lb_interframe_score_ws_bytes(int64_t nq, int n_nbr);
 int lb_interframe_score(const void* q_grid, const float* q_prob, int64_t nq, int n_cls, const lb_frame_ref* nbrs,
                         int n_nbr, double dis_thresh, double cell, double* interd, float* intere, int32_t* count,
-                        int32_t* nn, void* stream);
+                        int32_t* nn, void* ws, size_t ws_bytes, void* stream);
 
 /* LiDAL.py:87-98: per-region means over the ragged `sv2point` lists given in CSR form:
  * region_ptr int32 [r+1], region_pts int32 [region_ptr[r]].  Outs: d,e f32 [r]; optional pnums i64 [r],

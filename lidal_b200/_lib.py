@@ -25,7 +25,7 @@ class ConvArgs(C.Structure):
     _fields_ = [("inp", vp), ("n_in", i64), ("ld_in", i64), ("out", vp), ("n_out", i64), ("ld_out", i64),
                 ("n_out_dev", vp), ("nbr", vp), ("nbr_ld", i64), ("out_rows", vp), ("weight", vp),
                 ("k_vol", i32), ("c_in", i32), ("c_out", i32), ("scale", vp), ("shift", vp), ("residual", vp),
-                ("ld_res", i64), ("act_dtype", i32), ("out_dtype", i32), ("flags", i32)]
+                ("ld_res", i64), ("act_dtype", i32), ("out_dtype", i32), ("flags", i32), ("sched_ws", vp)]
 
 
 class FrameRef(C.Structure):
@@ -65,6 +65,7 @@ SIGNATURES = {
     "lb_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
     "lb_conv_wgrad": (i32, [vp, i64, i64, vp, i64, i64, vp, C.POINTER(i32), i32, i32, i32, i32, vp, vp]),
     "lb_conv_uses_tensor_cores": (i32, [i32, i32, i32, i32]),
+    "lb_conv_sched_ws_bytes": (sz, []),
     "lb_cast": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, vp]),
     "lb_count": (i32, [vp, i64, vp, i64, vp]),
     "lb_voxelize_fwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
@@ -91,7 +92,8 @@ SIGNATURES = {
     "lb_frame_grid_bytes": (sz, [i64]),
     "lb_frame_grid_ws_bytes": (sz, [i64]),
     "lb_frame_grid_build": (i32, [vp, i64, dbl, vp, sz, vp, sz, vp]),
-    "lb_interframe_score": (i32, [vp, vp, i64, i32, C.POINTER(FrameRef), i32, dbl, dbl, vp, vp, vp, vp, vp]),
+    "lb_interframe_score_ws_bytes": (sz, [i64, i32]),
+    "lb_interframe_score": (i32, [vp, vp, i64, i32, C.POINTER(FrameRef), i32, dbl, dbl, vp, vp, vp, vp, vp, sz, vp]),
     "lb_frame_level_ws_bytes": (sz, []),
     "lb_frame_level_scores": (i32, [vp, i64, i32, vp, vp, sz, vp]),
     "lb_region_reduce": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
@@ -135,6 +137,22 @@ def ptr(t: torch.Tensor | None):
 
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_SCHED_CELLS: dict = {}
+
+
+def conv_sched_ws():
+    """The tile-scheduler scratch of lb_conv_fwd for the current (device, stream): allocated and zeroed once, then reused
+    (the kernel leaves it zeroed; launches on one stream are ordered).  Returns a raw device pointer."""
+    dev = torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    cell = _SCHED_CELLS.get(key)
+    if cell is None:
+        cell = torch.zeros(lib().lb_conv_sched_ws_bytes() // 4, dtype=torch.int32, device=f"cuda:{dev}")
+        torch.cuda.current_stream().synchronize()         # zeroing is ordered on this stream anyway; once per stream
+        _SCHED_CELLS[key] = cell
+    return cell.data_ptr()
 
 
 def require_cuda(*tensors):

@@ -280,6 +280,7 @@ def conv_forward(feats16, packed_w, nbr, n_out, *, scale=None, shift=None, resid
     a.residual, a.ld_res = (residual.data_ptr(), residual.stride(0)) if residual is not None else (None, 0)
     a.act_dtype, a.out_dtype = L.DT_OF[feats16.dtype], L.DT_OF[out.dtype]
     a.flags = (L.LB_CONV_RELU if relu else 0) | (L.LB_CONV_FORCE_SIMT if force_simt else 0) | extra_flags
+    a.sched_ws = L.conv_sched_ws()
     if CONV_TRACE is None:
         L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
         return out

@@ -151,6 +151,7 @@ extern "C" int lb_conv_pack_weight(const float* kernel, int k, int cin, int cout
   return LB_OK;
 }
 
+extern "C" size_t lb_conv_sched_ws_bytes(void) { return 256; }
 extern "C" int lb_conv_uses_tensor_cores(int k_vol, int c_in, int c_out, int act_dtype) {
   return conv_tc_supported(k_vol, c_in, c_out, act_dtype);
 }

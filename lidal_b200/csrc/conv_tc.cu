@@ -22,9 +22,6 @@
 // Measured on B200 (ncu, round 1): the kernel is bound by instructions per ring stage in the producer warps and in
 // the single issuing warp, not by DRAM, L2 or the tensor pipe on the 32/96-channel layers -- hence the care taken to
 // keep both per-stage paths short (running addresses, uniform control flow through REDUX, elect.sync issue).
-#include <map>
-#include <mutex>
-#include <utility>
 #include "tc_ptx.cuh"
 
 namespace lb {
@@ -776,22 +773,6 @@ static size_t tail_bytes(int T) {
 }
 static size_t staging_bytes(int c_out, int bufs = 1) { return (size_t)bufs * 4 * 32 * (c_out * 2 + 16); }
 
-// One 2-word scheduler cell per (device, stream): launches on a stream are ordered, and the kernel leaves the cell zeroed.
-static unsigned* sched_cell(cudaStream_t st) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, unsigned*> cells;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cells.find({dev, st});
-  if (it != cells.end()) return it->second;
-  unsigned* cell = nullptr;
-  if (cudaMalloc(&cell, 256) != cudaSuccess) return nullptr;
-  if (cudaMemset(cell, 0, 256) != cudaSuccess) { cudaFree(cell); return nullptr; }
-  cells[{dev, st}] = cell;
-  return cell;
-}
-
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const bool pack8 = (a.flags & LB_CONV_PACK8) != 0;
   const int bk = pack8 ? 64 : block_k_for(a.c_in);
@@ -912,14 +893,22 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.prod_mode = pack8 ? 0 : prod_mode_env;
   p.prod_warps = stages < NUM_PROD_THREADS / 32 ? stages : NUM_PROD_THREADS / 32;
   static const bool static_tiles = getenv("LIDAL_STATIC_TILES") != nullptr;   // A/B switch
-  p.sched = static_tiles ? nullptr : sched_cell(st);
+  p.sched = static_tiles ? nullptr : (unsigned*)a.sched_ws;   // caller-owned, zeroed once, private to this stream
   const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + (p.staged ? staging_bytes(a.c_out, p.stg_bufs) : 0) + 1024;
   int64_t tiles = (a.n_out + (int64_t)T * TILE_M - 1) / ((int64_t)T * TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
 #define LB_TC_LAUNCH(BKV, TV, KV)                                                                                     \
   do {                                                                                                                \
-    LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BKV, TV, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    {                                                                                                                 \
+      static bool opted[64] = {};                /* per device: raise the dynamic shared memory limit once */          \
+      int dev_ = 0;                                                                                                   \
+      cudaGetDevice(&dev_);                                                                                           \
+      if (dev_ < 0 || dev_ >= 64 || !opted[dev_]) {                                                                   \
+        LB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BKV, TV, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+        if (dev_ >= 0 && dev_ < 64) opted[dev_] = true;                                                               \
+      }                                                                                                               \
+    }                                                                                                                 \
     conv_tc_kernel<BKV, TV, KV><<<grid, NUM_THREADS, smem, st>>>(map, out_map, res_map, p);                              \
     LB_LAUNCHED(1);                                                                                                   \
   } while (0)

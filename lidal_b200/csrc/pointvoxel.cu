@@ -427,6 +427,50 @@ __global__ void voxelize_ex_vec4_kernel(const TI* __restrict__ feats, int64_t ld
     }
   }
 }
+template <typename T> __device__ __forceinline__ float lo16_to_f32(uint32_t w);
+template <typename T> __device__ __forceinline__ float hi16_to_f32(uint32_t w);
+// 16-bit features (engine path): same run-length scheme, 8-byte loads of 4 channels, the run is summed first and scaled
+// once by 1 / count at the flush (the reference adds f / count per point in atomic order -- neither order is canonical).
+template <typename TI>
+__global__ void voxelize16_vec4_kernel(const TI* __restrict__ feats, int64_t ld_f_, const int* __restrict__ idx,
+                                       const int* __restrict__ counts, int64_t n, int64_t m, int c, float* __restrict__ out) {
+  constexpr int VOX_RUN = 16;
+  const int cpr = c >> 2;
+  const int64_t chunks = (n + VOX_RUN - 1) / VOX_RUN;
+  const int64_t total = chunks * cpr;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ch = t / cpr;
+    const int j = (int)(t - ch * cpr) * 4;
+    const int64_t i0 = ch * VOX_RUN, i1 = (i0 + VOX_RUN < n) ? i0 + VOX_RUN : n;
+    int cur = -1, cnt = 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush = [&]() {
+      if (cur >= 0 && cnt > 0) {
+        const float r = __frcp_rn((float)cnt);
+        const float4 v = make_float4(acc.x * r, acc.y * r, acc.z * r, acc.w * r);
+        float4* dst = (float4*)&out[(int64_t)cur * c + j];
+        if (cnt == 1) *dst = v;                        // single-point voxel: no other writer exists for this row
+        else atomicAdd(dst, v);
+      }
+    };
+    for (int64_t i = i0; i < i1; ++i) {
+      const int v = __ldg(&idx[i]);
+      if (v < 0 || v >= m) continue;
+      if (v != cur) {
+        flush();
+        cur = v;
+        cnt = __ldg(&counts[v]);
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (cnt > 0) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(&feats[i * ld_f_ + j]));
+        acc.x += lo16_to_f32<TI>(w.x); acc.y += hi16_to_f32<TI>(w.x);
+        acc.z += lo16_to_f32<TI>(w.y); acc.w += hi16_to_f32<TI>(w.y);
+      }
+    }
+    flush();
+  }
+}
 template <typename TI, typename TO>
 __global__ void devoxelize_ex_kernel(const TI* __restrict__ feats, int64_t ld_f_, const int* __restrict__ idx,
                                      const float* __restrict__ w, int64_t n, int64_t m, int c, TO* __restrict__ out,
@@ -464,6 +508,21 @@ namespace lb {
 // 16-bit in / 16-bit out, c % 8 == 0: one thread per (point, 8-channel chunk), 16-byte loads and stores, fp32 math in
 // the same corner order.  Corners with weight exactly 0 are not fetched (LiDAL's points sit on voxel corners, so at
 // stride 1 seven of the eight weights are 0); the result is identical for finite features.
+template <typename T> __device__ __forceinline__ float lo16_to_f32(uint32_t w);
+template <typename T> __device__ __forceinline__ float hi16_to_f32(uint32_t w);
+template <> __device__ __forceinline__ float lo16_to_f32<__nv_bfloat16>(uint32_t w) { return __uint_as_float(w << 16); }
+template <> __device__ __forceinline__ float hi16_to_f32<__nv_bfloat16>(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+template <> __device__ __forceinline__ float lo16_to_f32<__half>(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+template <> __device__ __forceinline__ float hi16_to_f32<__half>(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+template <typename T> __device__ __forceinline__ uint32_t pack16x2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack16x2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack16x2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 template <typename T>
 __global__ void devoxelize16_kernel(const T* __restrict__ feats, int64_t ld_f_, const int* __restrict__ idx,
                                     const float* __restrict__ w, int64_t n, int64_t m, int c, T* __restrict__ out,
@@ -487,15 +546,17 @@ __global__ void devoxelize16_kernel(const T* __restrict__ feats, int64_t ld_f_, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (ik[k] >= 0 && ik[k] < m && wk[k] != 0.f) {
-        const T* e = reinterpret_cast<const T*>(&v[k]);
+        const uint32_t wd[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(wk[k], ld_f<T>(&e[j])));
+        for (int j = 0; j < 4; ++j) {                 // two 16-bit elements per word; fp32 multiply then add, corner order
+          acc[2 * j] = __fadd_rn(acc[2 * j], __fmul_rn(wk[k], lo16_to_f32<T>(wd[j])));
+          acc[2 * j + 1] = __fadd_rn(acc[2 * j + 1], __fmul_rn(wk[k], hi16_to_f32<T>(wd[j])));
+        }
       }
     }
     uint4 o;
-    T* oe = reinterpret_cast<T*>(&o);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) st_f<T>(&oe[j], acc[j]);
+    o.x = pack16x2<T>(acc[0], acc[1]); o.y = pack16x2<T>(acc[2], acc[3]);
+    o.z = pack16x2<T>(acc[4], acc[5]); o.w = pack16x2<T>(acc[6], acc[7]);
     *(uint4*)&out[p * ld_o + ch * 8] = o;
   }
 }
@@ -536,6 +597,8 @@ extern "C" int lb_voxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld
     const int64_t total = ((n + 15) / 16) * (c / 4), blocks = (total + 255) / 256, cap = (int64_t)sm_count() * 32;
     const int g4 = (int)(blocks > cap ? cap : blocks);
     if (feats_dtype == LB_DT_F32) { voxelize_ex_vec4_kernel<float><<<g4, 256, 0, st>>>((const float*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+    else if (feats_dtype == LB_DT_BF16 && ld_f % 4 == 0 && (((uintptr_t)feats) & 7) == 0) { voxelize16_vec4_kernel<__nv_bfloat16><<<g4, 256, 0, st>>>((const __nv_bfloat16*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
+    else if (feats_dtype == LB_DT_F16 && ld_f % 4 == 0 && (((uintptr_t)feats) & 7) == 0) { voxelize16_vec4_kernel<__half><<<g4, 256, 0, st>>>((const __half*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
     else if (feats_dtype == LB_DT_BF16) { voxelize_ex_vec4_kernel<__nv_bfloat16><<<g4, 256, 0, st>>>((const __nv_bfloat16*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
     else if (feats_dtype == LB_DT_F16) { voxelize_ex_vec4_kernel<__half><<<g4, 256, 0, st>>>((const __half*)feats, ld_f, idx, counts, n, m, c, out); LB_LAUNCHED(1); }
     else { set_error("lb_voxelize_fwd_ex: bad dtype"); return LB_EINVAL; }

@@ -16,6 +16,7 @@ namespace lb {
 
 // Per-frame uniform grid, cell-sorted:
 //   header | slots[cap] {key, start, count} (open addressing on the packed cell key) | xyz_sorted f64 [n,3] | orig i32 [n]
+//          | rel f32 [n,3] (coordinates relative to the point's own cell origin: |rel| < cell, so float32 keeps ~1e-8 m)
 // Points are radix-sorted by cell key, so the candidates of a cell are one contiguous run and consecutive points are
 // spatial neighbours (probes of consecutive query points hit the same cache lines).
 struct GridHeader {
@@ -36,10 +37,11 @@ struct GridView {
   const GridSlot* slots;
   const double* xyz;     // cell-sorted coordinates
   const int* orig;       // cell-sorted position -> original row
+  const float* rel;      // cell-sorted coordinates minus their cell origin, float32 (prefilter operand)
 };
 __host__ __device__ inline size_t grid_bytes_for(int64_t n) {
   uint64_t cap = table_capacity(n);
-  return sizeof(GridHeader) + cap * sizeof(GridSlot) + (size_t)(n > 0 ? n : 1) * 28 + 64;
+  return sizeof(GridHeader) + cap * sizeof(GridSlot) + (size_t)(n > 0 ? n : 1) * 40 + 64;
 }
 __host__ __device__ __forceinline__ GridView grid_view(const void* g) {
   const GridHeader* h = (const GridHeader*)g;
@@ -50,6 +52,7 @@ __host__ __device__ __forceinline__ GridView grid_view(const void* g) {
   v.slots = (const GridSlot*)((const char*)g + sizeof(GridHeader));
   v.xyz = (const double*)(v.slots + h->cap);
   v.orig = (const int*)(v.xyz + 3 * (h->n > 0 ? h->n : 1));
+  v.rel = (const float*)(v.orig + (h->n > 0 ? h->n : 1));
   return v;
 }
 constexpr long long CELL_BIAS = 1 << 20;
@@ -101,6 +104,8 @@ __global__ void grid_fill_kernel(const double* __restrict__ xyz, const uint64_t*
   GridSlot* slots = (GridSlot*)((char*)grid + sizeof(GridHeader));
   double* sx = (double*)(slots + cap);
   int* orig = (int*)(sx + 3 * n);
+  float* rel = (float*)(orig + n);
+  const double cell = ((const GridHeader*)grid)->cell;
   const uint64_t mask = cap - 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t o = vals[i];
@@ -108,6 +113,11 @@ __global__ void grid_fill_kernel(const double* __restrict__ xyz, const uint64_t*
     sx[3 * i + 1] = xyz[3 * (int64_t)o + 1];
     sx[3 * i + 2] = xyz[3 * (int64_t)o + 2];
     orig[i] = (int)o;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v = xyz[3 * (int64_t)o + a];
+      rel[3 * i + a] = (float)(v - (double)cell_of(v, cell) * cell);
+    }
     const uint64_t key = keys[i];
     if (i == 0 || keys[i - 1] != key) {                  // run start: claim the slot (keys are unique per run)
       int64_t e = i + 1;
@@ -132,79 +142,106 @@ struct ScoreParams {
   int n_nbr;
 };
 
-// Phase 1 -- nearest-neighbour search, one THREAD per cell-sorted query point, all neighbour frames in turn.
-// Consecutive threads are spatial neighbours, so their 27-cell probes and candidate reads coalesce in L1/L2.
-// nn[p * n_nbr + f] = original row of the exact float64 nearest neighbour in frame f if sqrt(d2) <= thresh, else -1.
+// Phase 1 -- nearest-neighbour search, one THREAD per (cell-sorted query point, neighbour frame): blockIdx.y = frame.
+// Consecutive threads are spatial neighbours, so their cell probes and candidate reads coalesce in L1/L2; every
+// (point, frame) pair is independent, so a frame's search exposes 24x the parallelism of a per-point loop.
+// Candidates are screened in float32 on cell-relative coordinates (error ~1e-7 m, screening radius inflated by 1e-5 m so a
+// true match can never be dropped) and only survivors are evaluated in the reference's arithmetic: float64, no FMA
+// contraction (sklearn's rdist), ties to the smaller original row.  Result: the exact nearest neighbour if it lies within
+// the threshold, else -1 -- identical to the KD-tree query + `dists <= dis_thresh` of LiDAL.py:66-69.
+// nn_fm[f * nq + sp] (frame-major, by SORTED position): coalesced writes; phase 2 reads it back by sorted position.
 __global__ void __launch_bounds__(128)
 nn_search_kernel(const void* __restrict__ q_grid, int64_t nq, const __grid_constant__ ScoreParams P, double thresh,
-                 int* __restrict__ nn) {
+                 int* __restrict__ nn_fm) {
   const GridView qg = grid_view(q_grid);
-  const double t2 = thresh * thresh * (1.0 + 1e-6) + 1e-12;   // inflated: pruning must never drop a true match
+  const int f = blockIdx.y;
+  const GridView g = grid_view(P.nbr[f].grid);
+  const float tf = (float)thresh + 1e-5f;                    // inflated screening radius: must never drop a true match
+  const float t2f = tf * tf;
   for (int64_t sp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; sp < nq; sp += (int64_t)gridDim.x * blockDim.x) {
     const double qx = __ldg(&qg.xyz[3 * sp]), qy = __ldg(&qg.xyz[3 * sp + 1]), qz = __ldg(&qg.xyz[3 * sp + 2]);
-    const int64_t p = __ldg(&qg.orig[sp]);
-    for (int f = 0; f < P.n_nbr; ++f) {
-      const GridView g = grid_view(P.nbr[f].grid);
-      const long long cx = cell_of(qx, g.cell), cy = cell_of(qy, g.cell), cz = cell_of(qz, g.cell);
-      // distance from the query to the lower / upper face of its own cell per axis: a neighbouring cell can hold a match
-      // only if its box is within the (slightly inflated) match radius -- exact pruning, typically ~6 of 27 cells remain
-      const double lx = fmax(qx - (double)cx * g.cell, 0.0), hx = fmax((double)(cx + 1) * g.cell - qx, 0.0);
-      const double ly = fmax(qy - (double)cy * g.cell, 0.0), hy = fmax((double)(cy + 1) * g.cell - qy, 0.0);
-      const double lz = fmax(qz - (double)cz * g.cell, 0.0), hz = fmax((double)(cz + 1) * g.cell - qz, 0.0);
-      double best = INFINITY;
-      int bi = 0x7fffffff;
-#pragma unroll 1
-      for (int c = 0; c < 27; ++c) {
-        const int ox = c / 9 - 1, oy = (c / 3) % 3 - 1, oz = c % 3 - 1;
-        const double gx = ox == 0 ? 0.0 : (ox < 0 ? lx : hx), gy = oy == 0 ? 0.0 : (oy < 0 ? ly : hy),
-                     gz = oz == 0 ? 0.0 : (oz < 0 ? lz : hz);
-        if (gx * gx + gy * gy + gz * gz > t2) continue;
-        const int2 run = grid_find(g, cell_key(cx + ox, cy + oy, cz + oz));
-        for (int j = run.x; j < run.x + run.y; ++j) {
-          // sklearn euclidean rdist: d = 0; d += t*t per axis, no FMA contraction
-          const double tx = __dsub_rn(qx, __ldg(&g.xyz[3 * (int64_t)j]));
-          const double ty = __dsub_rn(qy, __ldg(&g.xyz[3 * (int64_t)j + 1]));
-          const double tz = __dsub_rn(qz, __ldg(&g.xyz[3 * (int64_t)j + 2]));
-          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
-          const int oj = __ldg(&g.orig[j]);
-          if (d2 < best || (d2 == best && oj < bi)) { best = d2; bi = oj; }
+    const long long cx = cell_of(qx, g.cell), cy = cell_of(qy, g.cell), cz = cell_of(qz, g.cell);
+    // query relative to its own cell origin; a neighbouring cell's origin differs by exactly (ox, oy, oz) * cell
+    const double rx = qx - (double)cx * g.cell, ry = qy - (double)cy * g.cell, rz = qz - (double)cz * g.cell;
+    // Distance from the query to the lower / upper face of its own cell per axis: a neighbouring cell can hold a match only
+    // if its box lies within the match radius.  The pruning runs in float32 against the inflated screening radius (the
+    // gaps are < cell, so their float32 error is ~1e-8 m -- far inside the 1e-5 m inflation): conservative, so no cell that
+    // could hold a match is skipped; typically ~6 of 27 cells remain.
+    const float cellf = (float)g.cell;
+    const float rxf = (float)rx, ryf = (float)ry, rzf = (float)rz;
+    const float gap2x[3] = {rxf * rxf, 0.f, (cellf - rxf) * (cellf - rxf)};
+    const float gap2y[3] = {ryf * ryf, 0.f, (cellf - ryf) * (cellf - ryf)};
+    const float gap2z[3] = {rzf * rzf, 0.f, (cellf - rzf) * (cellf - rzf)};
+    double best = INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int ix = 0; ix < 3; ++ix) {
+      if (gap2x[ix] > t2f) continue;
+#pragma unroll
+      for (int iy = 0; iy < 3; ++iy) {
+        const float gxy = gap2x[ix] + gap2y[iy];
+        if (gxy > t2f) continue;
+#pragma unroll
+        for (int iz = 0; iz < 3; ++iz) {
+          if (gxy + gap2z[iz] > t2f) continue;
+          const int ox = ix - 1, oy = iy - 1, oz = iz - 1;
+          const int2 run = grid_find(g, cell_key(cx + ox, cy + oy, cz + oz));
+          if (run.y == 0) continue;
+          const float fx = rxf - (float)ox * cellf, fy = ryf - (float)oy * cellf, fz = rzf - (float)oz * cellf;
+          for (int j = run.x; j < run.x + run.y; ++j) {
+            const float ex = fx - __ldg(&g.rel[3 * (int64_t)j]), ey = fy - __ldg(&g.rel[3 * (int64_t)j + 1]),
+                        ez = fz - __ldg(&g.rel[3 * (int64_t)j + 2]);
+            if (ex * ex + ey * ey + ez * ez > t2f) continue;
+            // sklearn euclidean rdist: d = 0; d += t*t per axis, no FMA contraction
+            const double tx = __dsub_rn(qx, __ldg(&g.xyz[3 * (int64_t)j]));
+            const double ty = __dsub_rn(qy, __ldg(&g.xyz[3 * (int64_t)j + 1]));
+            const double tz = __dsub_rn(qz, __ldg(&g.xyz[3 * (int64_t)j + 2]));
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+            const int oj = __ldg(&g.orig[j]);
+            if (d2 < best || (d2 == best && oj < bi)) { best = d2; bi = oj; }
+          }
         }
       }
-      nn[p * P.n_nbr + f] = (bi != 0x7fffffff && __dsqrt_rn(best) <= thresh) ? bi : -1;
     }
+    nn_fm[(int64_t)f * nq + sp] = (bi != 0x7fffffff && __dsqrt_rn(best) <= thresh) ? bi : -1;
   }
 }
 
-// Phase 2 -- one WARP per query point, lane = class: accumulate over the matched neighbours in nei_ids order.
+// Phase 2 -- one WARP per query point (walked by sorted position; results land at the point's original row), lane = class:
+// accumulate over the matched neighbours in nei_ids order.
 __global__ void __launch_bounds__(256)
-interframe_kernel(const float* __restrict__ q_prob, int64_t nq, int n_cls, const __grid_constant__ ScoreParams P,
-                  const int* __restrict__ nn, double* __restrict__ interd_out, float* __restrict__ intere_out,
-                  int* __restrict__ count_out) {
+interframe_kernel(const void* __restrict__ q_grid, const float* __restrict__ q_prob, int64_t nq, int n_cls,
+                  const __grid_constant__ ScoreParams P, const int* __restrict__ nn_fm, double* __restrict__ interd_out,
+                  float* __restrict__ intere_out, int* __restrict__ count_out, int* __restrict__ nn_out) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const float eps = 0.00001f;
-  for (int64_t p = warp; p < nq; p += nwarps) {
+  const int* __restrict__ q_orig = grid_view(q_grid).orig;
+  for (int64_t sp = warp; sp < nq; sp += nwarps) {
+    const int64_t p = __ldg(&q_orig[sp]);
     const float q = lane < n_cls ? __ldg(&q_prob[p * n_cls + lane]) : 0.f;
-    const int my_nn = lane < P.n_nbr ? __ldg(&nn[p * P.n_nbr + lane]) : -1;
+    const int my_nn = lane < P.n_nbr ? __ldg(&nn_fm[(int64_t)lane * nq + sp]) : -1;
+    if (nn_out && lane < P.n_nbr) nn_out[p * P.n_nbr + lane] = my_nn;
     float sum = q;
     double interd = 0.0;
     int cnt = 1;
-    for (int f = 0; f < P.n_nbr; ++f) {
+    unsigned hits = __ballot_sync(full, my_nn >= 0);
+    while (hits) {                                        // matched neighbour frames only, in nei_ids order
+      const int f = __ffs(hits) - 1;
+      hits &= hits - 1;
       const int bi = __shfl_sync(full, my_nn, f);
-      if (bi >= 0) {
-        const float pn = lane < n_cls ? __ldg(&P.nbr[f].prob[(int64_t)bi * n_cls + lane]) : 0.f;
-        sum = __fadd_rn(sum, pn);
-        float kl = 0.f;
-        if (lane < n_cls) {
-          const double x = (double)__fadd_rn(q, eps), y = (double)__fadd_rn(pn, eps);
-          kl = (float)__dadd_rn(__dsub_rn(__dmul_rn(x, log(__ddiv_rn(x, y))), x), y);
-        }
-        const float ks = np_pairwise_sum32(kl, n_cls, lane);
-        interd += (double)ks;      // only lane 0's value is meaningful
-        cnt += 1;
+      const float pn = lane < n_cls ? __ldg(&P.nbr[f].prob[(int64_t)bi * n_cls + lane]) : 0.f;
+      sum = __fadd_rn(sum, pn);
+      float kl = 0.f;
+      if (lane < n_cls) {
+        const double x = (double)__fadd_rn(q, eps), y = (double)__fadd_rn(pn, eps);
+        kl = (float)__dadd_rn(__dsub_rn(__dmul_rn(x, log(__ddiv_rn(x, y))), x), y);
       }
+      const float ks = np_pairwise_sum32(kl, n_cls, lane);
+      interd += (double)ks;      // only lane 0's value is meaningful
+      cnt += 1;
     }
     // LiDAL.py:75-76  sum_prob /= map_count (f32 / f64 -> f32);  entropy(pk) renormalises, natural log
     const float pm = lane < n_cls ? (float)__ddiv_rn((double)sum, (double)cnt) : 0.f;
@@ -354,14 +391,19 @@ extern "C" int lb_frame_grid_build(const double* xyz, int64_t n, double cell, vo
   return LB_OK;
 }
 
+extern "C" size_t lb_interframe_score_ws_bytes(int64_t nq, int n_nbr) {
+  return (size_t)(nq > 0 ? nq : 1) * (size_t)(n_nbr > 0 ? n_nbr : 1) * 4 + 256;
+}
 extern "C" int lb_interframe_score(const void* q_grid, const float* q_prob, int64_t nq, int n_cls,
                                    const lb_frame_ref* nbrs, int n_nbr, double dis_thresh, double cell,
-                                   double* interd, float* intere, int32_t* count, int32_t* nn, void* stream) {
+                                   double* interd, float* intere, int32_t* count, int32_t* nn, void* ws, size_t ws_bytes,
+                                   void* stream) {
   LB_CHECK_ARG(nq >= 0 && n_cls > 0 && n_cls <= 32, "n_cls must be in [1,32]");
   LB_CHECK_ARG(n_nbr >= 0 && n_nbr <= MAX_NBR, "at most 32 neighbour frames");
   LB_CHECK_ARG(cell >= dis_thresh * 1.001, "grid cell must exceed dis_thresh (27-cell probe exactness)");
   if (nq == 0) return LB_OK;
-  LB_CHECK_ARG(q_grid && q_prob && interd && intere && nn && (nbrs || n_nbr == 0), "null pointer");
+  LB_CHECK_ARG(q_grid && q_prob && interd && intere && ws && (nbrs || n_nbr == 0), "null pointer");
+  if (ws_bytes < lb_interframe_score_ws_bytes(nq, n_nbr)) { set_error("lb_interframe_score: workspace too small"); return LB_ECAP; }
   ScoreParams P;
   P.n_nbr = n_nbr;
   for (int i = 0; i < n_nbr; ++i) {
@@ -369,12 +411,13 @@ extern "C" int lb_interframe_score(const void* q_grid, const float* q_prob, int6
     P.nbr[i].grid = nbrs[i].grid; P.nbr[i].xyz = nbrs[i].xyz; P.nbr[i].prob = nbrs[i].prob; P.nbr[i].n = nbrs[i].n;
   }
   cudaStream_t st = as_stream(stream);
+  int* nn_fm = (int*)ws;
   if (n_nbr > 0) {
-    int64_t b1 = (nq + 127) / 128, cap1 = (int64_t)sm_count() * 16;
-    nn_search_kernel<<<(int)(b1 > cap1 ? cap1 : b1), 128, 0, st>>>(q_grid, nq, P, dis_thresh, nn); LB_LAUNCHED(1);
+    int64_t b1 = (nq + 127) / 128, cap1 = (int64_t)sm_count() * 32;
+    nn_search_kernel<<<dim3((unsigned)(b1 > cap1 ? cap1 : b1), (unsigned)n_nbr), 128, 0, st>>>(q_grid, nq, P, dis_thresh, nn_fm); LB_LAUNCHED(1);
   }
   int64_t blocks = (nq + 7) / 8, cap = (int64_t)sm_count() * 8;
-  interframe_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(q_prob, nq, n_cls, P, nn, interd, intere, count); LB_LAUNCHED(1);
+  interframe_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(q_grid, q_prob, nq, n_cls, P, nn_fm, interd, intere, count, nn); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -86,6 +86,7 @@ class _Conv:
         a.flags = ((L.LB_CONV_RELU if self.relu else 0) | (L.LB_CONV_RELU_FIRST if relu_first else 0)
                    | (L.LB_CONV_PACK8 if self.pack8 else 0) | (L.LB_CONV_TILE128 if FORCE_TILE128 else 0)
                    | (L.LB_CONV_NO_STAGED if NO_STAGED else 0))
+        a.sched_ws = L.conv_sched_ws()
         trace = F.CONV_TRACE
         ev = trace.begin() if trace is not None else None
         L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
@@ -144,6 +145,48 @@ class _HostCounters:
         """Queue a copy of a device int32 scalar into slot i; the returned callable reads it after the next ``read``."""
         self.buf[i:i + 1].copy_(dev_scalar.reshape(1), non_blocking=True)
         return lambda: int(self.buf[i])
+
+
+class StageTrace:
+    """Optional per-stage device timing for bench.py's ``roofline_by_stage``: CUDA events on the launching stream around
+    each non-conv stage of a step, with the stage's ALGORITHMIC bytes (SURVEY.md section 8d formulas)."""
+
+    def __init__(self):
+        self.records = []          # (name, ev0, ev1, bytes)
+
+    def summarise(self):
+        torch.cuda.synchronize()
+        out: dict = {}
+        for name, e0, e1, nbytes in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "bytes": 0, "calls": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+            d["calls"] += 1
+        return out
+
+
+STAGE_TRACE: StageTrace | None = None
+
+
+class _stage:
+    """``with _stage(name, bytes):`` -- free when tracing is off."""
+    __slots__ = ("name", "nbytes", "ev")
+
+    def __init__(self, name, nbytes):
+        self.name, self.nbytes, self.ev = name, nbytes, None
+
+    def __enter__(self):
+        if STAGE_TRACE is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None and STAGE_TRACE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            STAGE_TRACE.records.append((self.name, self.ev, e1, int(self.nbytes() if callable(self.nbytes) else self.nbytes)))
+        return False
 
 
 _COUNTERS = {}
@@ -206,6 +249,19 @@ class Maps:
             self.n.append(cn.shape[0])
             self.nbr_dn.append(_mask_sorted(dn) if SORT_MAPS else dn)
             self.nbr_up.append(_mask_sorted(up) if SORT_MAPS else up)
+
+
+def _maps_algorithmic_bytes(self):
+    total = 0
+    for lvl in range(5):
+        n = self.n[lvl]
+        total += 16 * n + 16 * n + 4 * 27 * n + 24 * n                 # submanifold k3 map + its hash table
+        if lvl < 4:
+            total += 16 * n + 16 * self.n[lvl + 1] + 2 * 4 * 8 * n        # k2s2 map pair (down + transposed)
+    return total
+
+
+Maps.algorithmic_bytes = _maps_algorithmic_bytes
 
 
 class InferenceEngine:
@@ -282,8 +338,16 @@ class InferenceEngine:
         logits, feat = self._spvcnn(coords, feats) if self.is_spvcnn else self._minkunet(coords, feats)
         return (logits, feat) if return_feat else logits
 
+    @staticmethod
+    def _maps(coords):
+        """All 9 kernel maps of a batch.  SURVEY 8d per map: 16 * N_ref + 16 * N_out + 4 * K * N_out (+ tables 24 * N_ref)."""
+        box = {}
+        with _stage("map_build", lambda: box["m"].algorithmic_bytes()):
+            box["m"] = Maps(coords)
+        return box["m"]
+
     def _minkunet(self, coords, feats):
-        m = Maps(coords.contiguous())
+        m = self._maps(coords.contiguous())
         cats = self._cat_buffers(m)
         x = self._stem(self._pad8(feats), m, cats[3])
         for lvl in range(1, 5):
@@ -304,8 +368,9 @@ class InferenceEngine:
         idx = torch.empty((n, 8), dtype=torch.int, device=pts.device)
         w = torch.empty((n, 8), dtype=torch.float32, device=pts.device)
         t = m.tables[lvl]
-        L.check(L.lib().lb_point_corner_query(L.ptr(pts), pts.stride(0), n, 2 ** lvl, L.ptr(t[0]), t[1], L.ptr(idx),
-                                              L.ptr(w), L.stream()))
+        with _stage("point_query", n * (16 + 64) + 12 * m.n[lvl]):
+            L.check(L.lib().lb_point_corner_query(L.ptr(pts), pts.stride(0), n, 2 ** lvl, L.ptr(t[0]), t[1], L.ptr(idx),
+                                                  L.ptr(w), L.stream()))
         return idx, w
 
     def _cell_query(self, pts, m, lvl):
@@ -320,14 +385,18 @@ class InferenceEngine:
     def _devox(self, x, idx, w, out_dtype=None):
         n, c = idx.shape[0], x.shape[1]
         out = torch.empty((n, c), dtype=out_dtype or self.dtype, device=x.device)
-        L.check(L.lib().lb_devoxelize_fwd_ex(L.ptr(x), L.DT_OF[x.dtype], x.stride(0), L.ptr(idx), L.ptr(w), n, x.shape[0], c,
-                                             L.ptr(out), L.DT_OF[out.dtype], out.stride(0), L.stream()))
+        # devoxelize = Np * (64 + C * e) + Nv * C * e
+        with _stage("devoxelize", n * (64 + c * out.element_size()) + x.shape[0] * c * x.element_size()):
+            L.check(L.lib().lb_devoxelize_fwd_ex(L.ptr(x), L.DT_OF[x.dtype], x.stride(0), L.ptr(idx), L.ptr(w), n, x.shape[0], c,
+                                                 L.ptr(out), L.DT_OF[out.dtype], out.stride(0), L.stream()))
         return out
 
     def _vox(self, f, idx, counts, m_rows):
         acc = torch.empty((m_rows, f.shape[1]), dtype=torch.float32, device=f.device)
-        L.check(L.lib().lb_voxelize_fwd_ex(L.ptr(f), L.DT_OF[f.dtype], f.stride(0), L.ptr(idx), L.ptr(counts), f.shape[0],
-                                           m_rows, f.shape[1], L.ptr(acc), L.stream()))
+        # voxelize = (Np * e_in + Nv * 4) * C + 4 * Np
+        with _stage("voxelize", (f.shape[0] * f.element_size() + m_rows * 4) * f.shape[1] + 4 * f.shape[0]):
+            L.check(L.lib().lb_voxelize_fwd_ex(L.ptr(f), L.DT_OF[f.dtype], f.stride(0), L.ptr(idx), L.ptr(counts), f.shape[0],
+                                               m_rows, f.shape[1], L.ptr(acc), L.stream()))
         return acc
 
     def _initial_voxelize(self, coords, feats):
@@ -357,7 +426,7 @@ class InferenceEngine:
 
     def _spvcnn(self, coords, feats):
         zc, vcoords, vfeats = self._initial_voxelize(coords.contiguous(), feats)
-        m = Maps(vcoords)
+        m = self._maps(vcoords)
         cats = self._cat_buffers(m)
         x0 = self._stem(self._pad8(vfeats), m, cats[3])
         iq0, w0 = self._corner_query(zc, m, 0)

@@ -139,10 +139,12 @@ class SequenceScorer:
         interd = torch.empty(q.n, dtype=torch.float64, device=self.device)
         intere = torch.empty(q.n, dtype=torch.float32, device=self.device)
         count = torch.empty(q.n, dtype=torch.int32, device=self.device)
-        nn = torch.empty((q.n, len(nids)), dtype=torch.int32, device=self.device)
+        nn = torch.empty((q.n, len(nids)), dtype=torch.int32, device=self.device) if want_nn else None
+        nb = L.lib().lb_interframe_score_ws_bytes(q.n, len(nids))
+        ws = _ws(nb, self.device)
         L.check(L.lib().lb_interframe_score(L.ptr(q.grid), L.ptr(q.prob), q.n, q.prob.shape[1], refs, len(nids),
                                             self.dis_thresh, self.cell, L.ptr(interd), L.ptr(intere), L.ptr(count),
-                                            L.ptr(nn), L.stream()))
+                                            L.ptr(nn), L.ptr(ws), nb, L.stream()))
         return (interd, intere, count, nn) if want_nn else (interd, intere, count)
 
     def score_frame_device(self, fid: int):

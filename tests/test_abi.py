@@ -29,12 +29,33 @@ def test_library_exports_every_declared_symbol():
 
 def test_python_binding_covers_header():
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib().lb_abi_version() == 1
+    assert _lib.lib().lb_abi_version() == 2
 
 
-def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.ConvArgs) == 160 or ctypes.sizeof(_lib.ConvArgs) % 8 == 0
-    assert ctypes.sizeof(_lib.FrameRef) == 32
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every field of the two ABI structs, taken from include/lidal_b200.h by the C compiler, equal the
+    ctypes mirrors in lidal_b200/_lib.py (field names differ only for `in`, a Python keyword)."""
+    import subprocess
+    structs = {"lb_conv_args": (_lib.ConvArgs, {"inp": "in"}), "lb_frame_ref": (_lib.FrameRef, {})}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "lidal_b200.h"', 'int main(void) {']
+    for cname, (ct, rename) in structs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {rename.get(fname, fname)}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, fname, val = line.split()
+        got[(cname, fname)] = int(val)
+    for cname, (ct, _) in structs.items():
+        assert got[(cname, "sizeof")] == ctypes.sizeof(ct), cname
+        for fname, _t in ct._fields_:
+            assert got[(cname, fname)] == getattr(ct, fname).offset, (cname, fname)
+    assert got[("lb_conv_args", "sizeof")] == 160 and got[("lb_frame_ref", "sizeof")] == 32
 
 
 def test_no_cpu_fallback():
