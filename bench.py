@@ -215,6 +215,78 @@ def run_lidal(eng, dev, rank, world, n_frames, kind, n_cls, barrier, seed=11):
     }
 
 
+# ------------------------------------------------------------------------------------------ config 4: training step
+def run_train(args, dev, rank, world, local_rank, barrier):
+    """BASELINE configs[3]: MinkUNet training fwd + bwd (+ Adam) on synthetic SemanticKITTI-shaped scans, batch 2 per GPU,
+    through the torchsparse drop-in layer (lidal_b200.compat: tcgen05 fwd / dgrad / wgrad, fp16 operands, fp32 accumulate and
+    fp32 parameters), torch DDP over NCCL when world > 1 (train.py:50-53,128-140).  Weak scaling: every rank trains on its
+    own scans; the only collective is DDP's bucketed gradient all-reduce, overlapped with the backward pass."""
+    import torch.distributed as dist
+    import lidal_b200.compat as ts
+    from lidal_b200 import _lib as L, synth
+    from lidal_b200.network import MinkUNet, seeded_state_dict
+    per_gpu = 2
+    sets = [synth.scan_batch(seed=50 + 10 * rank + s, kind=KIND, batch=per_gpu) for s in range(2)]
+    data = [(torch.from_numpy(c).to(dev), torch.from_numpy(f).to(dev),
+             torch.from_numpy(np.random.default_rng(s).integers(0, N_CLS, c.shape[0])).to(dev)) for s, (c, f, _) in enumerate(sets)]
+    model = MinkUNet(N_CLS, ts)
+    model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
+    model = model.to(dev).train()
+    n_params = sum(p.numel() for p in model.parameters())
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank)
+    opt = torch.optim.Adam(model.parameters())
+
+    def step(i):
+        c, f, y = data[i % len(data)]
+        opt.zero_grad()
+        logits, _ = model(ts.SparseTensor(f, c))
+        loss = torch.nn.functional.cross_entropy(logits, y, ignore_index=255, reduction="mean")
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.lib().lb_launch_count()
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            loss = step(i)
+        e1.record()
+        barrier()
+    launches = int(L.lib().lb_launch_count() - launches0)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    same = True
+    if world > 1:                      # all-reduced updates keep the replicas bit-identical
+        flat = torch.cat([p.detach().flatten() for p in model.parameters()])
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        ok = torch.tensor([float(torch.equal(flat, ref))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = bool(ok.item())
+    if rank == 0:
+        n_vox = int(np.mean([d[0].shape[0] for d in data]))
+        print(json.dumps({
+            "metric": "training scans/sec", "value": world * per_gpu * args.steps / (ms_total / 1e3), "unit": "scans/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 operands (power-of-two scaled gradients), f32 accumulate, f32 parameters / BatchNorm / Adam", "data": "synthetic",
+            "config": {"workload": f"minkunet_train_{KIND}_batch{per_gpu}_per_gpu", "model_family": "minkunet", "batch_scans_per_gpu": per_gpu,
+                       "voxels_per_step_per_gpu": n_vox, "classes": N_CLS, "optimizer": "Adam", "parameters": n_params},
+            "collective": {"kind": "DDP bucketed all-reduce (NCCL), overlapped with backward", "bytes_per_step": n_params * 4 if world > 1 else 0},
+            "replicas_identical": same, "loss": float(loss.detach()), "gpu_launches": launches, "clocks": clk.summary()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -227,6 +299,8 @@ def main():
     ap.add_argument("--kind", default="SK", choices=["SK", "NU"], help="scan shape: SemanticKITTI-like (19 classes) or nuScenes-like (16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer: SPVCNN inference scans/s + LiDAL frames/s (BASELINE configs[1], [2]); train: MinkUNet training step, DDP (configs[3])")
     ap.add_argument("--no-lidal", action="store_true", help="skip the LiDAL scored-frames/s workload (BASELINE configs[2])")
     ap.add_argument("--lidal-frames", type=int, default=1000)
     args = ap.parse_args()
@@ -247,6 +321,13 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "train":
+        def barrier_():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        run_train(args, dev, rank, world, local_rank, barrier_)
+        return
     from lidal_b200 import _lib as L
     path = args.path
     if path == "auto":

@@ -198,6 +198,14 @@ int lb_conv_wgrad(const void* x, int64_t n_x, int64_t ld_x, const void* g, int64
 int lb_cast(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows,
             int64_t cols, void* stream);
 
+/* Training backward (fp16 operands): amax = max |src| over a [rows, cols] fp32 matrix (device float[1], zeroed inside;
+ * NaN / Inf ignored), then dst = fp16/bf16(src * s) with s = 2^floor(log2(target / amax)) computed on device.
+ * scale_out (optional device float[2]) receives {s, 1/s}; inv_vec (optional device float[256]) is filled with 1/s --
+ * pass it as lb_conv_args.scale so the dgrad epilogue removes the scale again (exact: powers of two). */
+int lb_absmax_f32(const float* src, int64_t ld, int64_t rows, int64_t cols, float* amax, void* stream);
+int lb_cast_scaled(const float* src, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows, int64_t cols,
+                   const float* amax, float target, float* scale_out, float* inv_vec, void* stream);
+
 /* ------------------------------------------------------------------ point <-> voxel (SPVCNN)
  * Replaces torchsparse.backend.count_cuda / voxelize_* / devoxelize_* reached from network/utils.py:20-25,49,56,77-95. */
 int lb_count(const int32_t* idx, int64_t n, int32_t* counts, int64_t m, void* stream);

@@ -67,6 +67,8 @@ SIGNATURES = {
     "lb_conv_uses_tensor_cores": (i32, [i32, i32, i32, i32]),
     "lb_conv_sched_ws_bytes": (sz, []),
     "lb_cast": (i32, [vp, i32, i64, vp, i32, i64, i64, i64, vp]),
+    "lb_absmax_f32": (i32, [vp, i64, i64, i64, vp, vp]),
+    "lb_cast_scaled": (i32, [vp, i64, vp, i32, i64, i64, i64, vp, flt, vp, vp, vp]),
     "lb_count": (i32, [vp, i64, vp, i64, vp]),
     "lb_voxelize_fwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),
     "lb_voxelize_bwd": (i32, [vp, vp, vp, i64, i64, i32, vp, vp]),

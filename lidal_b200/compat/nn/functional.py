@@ -18,7 +18,12 @@ from .utils import get_kernel_offsets, make_ntuple
 __all__ = ["sphash", "sphashquery", "spcount", "spvoxelize", "spdevoxelize", "calc_ti_weights", "spdownsample",
            "conv3d", "build_kernel_map"]
 
-ACT_DTYPE = torch.bfloat16          # 16-bit operand type of the tensor-core convolution (fp32 accumulate)
+ACT_DTYPE = torch.bfloat16          # 16-bit operand type of the tensor-core convolution in inference (fp32 accumulate)
+TRAIN_DTYPE = torch.float16         # operand type when gradients are recorded: fp16's 11-bit significand keeps whole-network
+                                    # gradients within cosine 0.99 of the fp32 reference (bf16: ~0.92); output gradients are
+                                    # rescaled per tensor by a power of two before the cast, so they stay in fp16's normal range
+GRAD_TARGET = 8192.0                # max |g * s| aimed for (fp16 max 65504: headroom for the accumulation of many terms is
+                                    # irrelevant -- accumulation is fp32 -- but rounding to fp16 must not overflow)
 CONV_TRACE = None                   # set by lidal_b200.profiling to time every conv launch with CUDA events
 
 
@@ -213,6 +218,20 @@ class KernelMap:
             self._nbr_t = t
         return self._nbr_t
 
+    def wgrad_pairs(self, transposed):
+        """(pairs int32 [M,2] = (x_row, g_row) offset-major, host prefix offsets) for lb_conv_wgrad, cached per map: the
+        offsets need ``nbsizes`` on the host once per map, not once per layer that shares the map."""
+        cache = self.__dict__.setdefault("_wgrad", {})
+        if transposed not in cache:
+            pairs = self.nbmaps
+            if transposed:
+                pairs = pairs[:, [1, 0]]
+            begin = [0]
+            for n in self.nbsizes.tolist():
+                begin.append(begin[-1] + n)
+            cache[transposed] = (pairs.contiguous(), begin)
+        return cache[transposed]
+
     def __getitem__(self, i):
         return (self.nbmaps, self.nbsizes, (self.n_in, self.n_out))[i]
 
@@ -233,21 +252,34 @@ def build_kernel_map(coords, in_stride, kernel_size, stride, dilation) -> Kernel
 _PACKED = {}        # id(Parameter) -> (weakref, version, dtype, packed weight): repack only after an update
 
 
-def packed_weight_cached(kernel, dtype):
-    """Packed weight of an nn.Parameter, re-packed only when the parameter was modified (optimizer step, load_state_dict).
-    Keyed by id() and validated through a weakref (tensor keys cannot be compared with == inside a dict)."""
-    hit = _PACKED.get(id(kernel))
-    if hit is not None and hit[0]() is kernel and hit[1] == kernel._version and hit[2] == dtype and hit[3].device == kernel.device:
+def packed_weight_cached(kernel, dtype, transposed=False):
+    """Packed weight of an nn.Parameter (``transposed``: of W^T per offset, the dgrad operand), re-packed only when the
+    parameter was modified.  Keyed by id() and validated through a weakref, the version counter AND the storage pointer
+    (``p.data = t`` / ``p.data.copy_`` do not bump ``_version``; a new storage is caught by the pointer, an in-place
+    ``.data`` write is not -- call ``invalidate_packed_weights()`` after such surgery)."""
+    key = (id(kernel), bool(transposed))
+    hit = _PACKED.get(key)
+    if hit is not None and hit[0]() is kernel and hit[1] == kernel._version and hit[2] == dtype and hit[3].device == kernel.device \
+            and hit[4] == kernel.data_ptr():
         return hit[3]
-    packed = pack_weight(kernel, dtype)
+    if transposed:
+        w3 = kernel if kernel.dim() == 3 else kernel.unsqueeze(0)
+        packed = pack_weight(w3.transpose(1, 2), dtype)
+    else:
+        packed = pack_weight(kernel, dtype)
     if len(_PACKED) > 4096:
-        for key in [k for k, v in _PACKED.items() if v[0]() is None]:
-            del _PACKED[key]
+        for k_ in [k for k, v in _PACKED.items() if v[0]() is None]:
+            del _PACKED[k_]
     try:
-        _PACKED[id(kernel)] = (weakref.ref(kernel), kernel._version, dtype, packed)
+        _PACKED[key] = (weakref.ref(kernel), kernel._version, dtype, packed, kernel.data_ptr())
     except TypeError:
         pass
     return packed
+
+
+def invalidate_packed_weights():
+    """Forget every cached packed weight (after writing parameters through ``.data``)."""
+    _PACKED.clear()
 
 
 def pack_weight(kernel, dtype):
@@ -301,81 +333,93 @@ def _to16(x, dtype):
     return out
 
 
+def _scaled16(g, dtype):
+    """fp32 gradient -> (16-bit g * s, inv_vec float[256] = 1/s, scale float[2] = {s, 1/s}); s is a power of two chosen on
+    device from max |g| (no host round trip)."""
+    g = g.float()
+    if g.stride(1) != 1:
+        g = g.contiguous()
+    rows, cols = g.shape
+    dev = g.device
+    amax = torch.empty(1, dtype=torch.float32, device=dev)
+    L.check(L.lib().lb_absmax_f32(L.ptr(g), g.stride(0), rows, cols, L.ptr(amax), L.stream()))
+    g16 = torch.empty((rows, cols), dtype=dtype, device=dev)
+    scale = torch.empty(2, dtype=torch.float32, device=dev)
+    inv_vec = torch.empty(256, dtype=torch.float32, device=dev)
+    L.check(L.lib().lb_cast_scaled(L.ptr(g), g.stride(0), L.ptr(g16), L.DT_OF[dtype], cols, rows, cols, L.ptr(amax), GRAD_TARGET,
+                                   L.ptr(scale), L.ptr(inv_vec), L.stream()))
+    return g16, inv_vec, scale
+
+
 class _ConvFunction(torch.autograd.Function):
     """Forward on the implicit-GEMM kernel; dgrad reuses it with swapped map roles and W^T; wgrad is one
-    tcgen05 split-K contraction over the map pairs (lb_conv_wgrad)."""
+    tcgen05 split-K contraction over the map pairs (lb_conv_wgrad).  When gradients are recorded the operands are fp16
+    (TRAIN_DTYPE) and the 16-bit copy of the input is what is saved for wgrad."""
 
     @staticmethod
     def forward(ctx, feats, kernel, nbr, n_out, kmap, transposed):
-        w = packed_weight_cached(kernel, ACT_DTYPE)
-        x16 = _to16(feats.float(), ACT_DTYPE)
+        train = any(ctx.needs_input_grad[:2])
+        dt = TRAIN_DTYPE if train else ACT_DTYPE
+        w = packed_weight_cached(kernel, dt)
+        x16 = _to16(feats.float(), dt)
         out = conv_forward(x16, w, nbr, n_out)
-        ctx.save_for_backward(feats, kernel)
+        ctx.save_for_backward(x16, kernel)
         ctx.kmap, ctx.transposed = kmap, transposed
         return out
 
     @staticmethod
     def backward(ctx, g):
-        feats, kernel = ctx.saved_tensors
+        x16, kernel = ctx.saved_tensors
         kmap, transposed = ctx.kmap, ctx.transposed
+        dt = x16.dtype
         w3 = kernel if kernel.dim() == 3 else kernel.unsqueeze(0)
         gi = gw = None
+        g16, inv_vec, scale = _scaled16(g, dt)
         if ctx.needs_input_grad[0]:
             if kmap is None:
                 nbr_back = None
             else:
                 nbr_back = kmap.nbr if transposed else kmap.nbr_t
-            wt = pack_weight(w3.transpose(1, 2), ACT_DTYPE)                 # packed [K, Cin (as output), Cout (as input)]
-            g16 = _to16(g.float(), ACT_DTYPE)
+            wt = packed_weight_cached(kernel, dt, transposed=True)          # packed [K, Cin (as output), Cout (as input)]
             cin = wt.shape[1]
             if cin <= 256:
-                gi = conv_forward(g16, wt, nbr_back, feats.shape[0])
+                gi = conv_forward(g16, wt, nbr_back, x16.shape[0], scale=inv_vec)
             else:                                                           # MMA N <= 256: produce the input grad in column slices
-                gi = torch.empty((feats.shape[0], cin), dtype=torch.float32, device=g.device)
+                gi = torch.empty((x16.shape[0], cin), dtype=torch.float32, device=g.device)
                 for c0 in range(0, cin, 128):
                     c1 = min(c0 + 128, cin)
-                    conv_forward(g16, wt[:, c0:c1, :].contiguous(), nbr_back, feats.shape[0], out=gi[:, c0:c1])
+                    conv_forward(g16, wt[:, c0:c1, :].contiguous(), nbr_back, x16.shape[0], out=gi[:, c0:c1], scale=inv_vec)
         if ctx.needs_input_grad[1]:
-            gw = _wgrad(feats, g, kmap, transposed, w3.shape).view(kernel.shape)
+            gw = _wgrad(x16, g16, kmap, transposed, w3.shape)
+            gw = (gw * scale[1]).view(kernel.shape)
         return gi, gw, None, None, None, None
 
 
-def _wgrad(feats, g, kmap, transposed, wshape):
-    """grad of the `kernel` parameter [K, Cin, Cout].  Tensor-core kernel (lb_conv_wgrad) whenever Cout % 32 == 0; the
-    input is zero-padded to a multiple of 8 channels if needed.  Other shapes use one gathered GEMM per offset."""
+def _wgrad(x16, g16, kmap, transposed, wshape):
+    """grad of the `kernel` parameter [K, Cin, Cout] from 16-bit operands.  Tensor-core kernel (lb_conv_wgrad) whenever
+    Cout % 32 == 0; the input is zero-padded to a multiple of 8 channels if needed.  Other shapes use one gathered GEMM per offset."""
     k_vol, cin, cout = wshape
-    dev = feats.device
+    dev = x16.device
     if cout % 32 == 0 and cout <= 256 and k_vol <= 27:
         if kmap is None:
-            idx = torch.arange(feats.shape[0], dtype=torch.int, device=dev)
+            idx = torch.arange(x16.shape[0], dtype=torch.int, device=dev)
             pairs = torch.stack([idx, idx], 1).contiguous()
-            begin = [0, feats.shape[0]]
+            begin = [0, x16.shape[0]]
         else:
-            pairs = kmap.nbmaps                                             # (in_idx, out_idx), offset-major
-            if transposed:
-                pairs = pairs[:, [1, 0]]
-            pairs = pairs.contiguous()
-            sizes = kmap.nbsizes.tolist()
-            begin = [0]
-            for n in sizes:
-                begin.append(begin[-1] + n)
+            pairs, begin = kmap.wgrad_pairs(transposed)
         cin_p = (cin + 7) // 8 * 8
-        x16 = torch.zeros((feats.shape[0], cin_p), dtype=ACT_DTYPE, device=dev) if cin_p != cin else None
-        if x16 is None:
-            x16 = _to16(feats.float(), ACT_DTYPE)
-        else:
-            f32 = feats.float().contiguous()
-            L.check(L.lib().lb_cast(L.ptr(f32), L.LB_DT_F32, f32.stride(0), L.ptr(x16), L.DT_OF[ACT_DTYPE], cin_p,
-                                    f32.shape[0], cin, L.stream()))
-        g16 = _to16(g.float(), ACT_DTYPE)
+        if cin_p != cin:
+            xp = torch.zeros((x16.shape[0], cin_p), dtype=x16.dtype, device=dev)
+            xp[:, :cin] = x16
+            x16 = xp
         gw = torch.empty((k_vol, cin_p, cout), dtype=torch.float32, device=dev)
         pb = (C.c_int * len(begin))(*begin)
         L.check(L.lib().lb_conv_wgrad(L.ptr(x16), x16.shape[0], x16.stride(0), L.ptr(g16), g16.shape[0], g16.stride(0),
-                                      L.ptr(pairs), pb, k_vol, cin_p, cout, L.DT_OF[ACT_DTYPE], L.ptr(gw), L.stream()))
+                                      L.ptr(pairs), pb, k_vol, cin_p, cout, L.DT_OF[x16.dtype], L.ptr(gw), L.stream()))
         return gw[:, :cin, :] if cin_p != cin else gw
     gw = torch.zeros(wshape, dtype=torch.float32, device=dev)
     if kmap is None:
-        gw[0] = feats.float().t() @ g.float()
+        gw[0] = x16.float().t() @ g16.float()
         return gw
     nbmaps, nbsizes = kmap.nbmaps.long(), kmap.nbsizes.tolist()
     a, b = (1, 0) if transposed else (0, 1)
@@ -383,7 +427,7 @@ def _wgrad(feats, g, kmap, transposed, wshape):
     for k, n in enumerate(nbsizes):
         if n:
             m = nbmaps[cur:cur + n]
-            gw[k] = feats[m[:, a]].float().t() @ g[m[:, b]].float()
+            gw[k] = x16[m[:, a]].float().t() @ g16[m[:, b]].float()
         cur += n
     return gw
 

@@ -290,6 +290,64 @@ extern "C" int lb_cast(const void* src, int sd, int64_t ld_s, void* dst, int dd,
   return LB_EINVAL;
 }
 
+// ---------------------------------------------------------------------------------------- scaled 16-bit cast (training)
+// Gradients of a mean-reduced loss sit far below fp16's normal range; the backward convolutions therefore cast g * s with
+// s = the power of two that brings max|g| near `target`, and fold 1 / s into the kernel epilogue (exact: powers of two).
+namespace lb {
+__global__ void absmax_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols, unsigned* __restrict__ out) {
+  float m = 0.f;
+  const int64_t total = rows * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / cols;
+    const float v = fabsf(src[r * ld + (t - r * cols)]);
+    m = (v == v && v < INFINITY) ? fmaxf(m, v) : m;                    // NaN / Inf do not steer the scale
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bits
+}
+template <typename D>
+__global__ void cast_scaled_kernel(const float* __restrict__ src, int64_t ld_s, D* __restrict__ dst, int64_t ld_d, int64_t rows,
+                                   int64_t cols, const float* __restrict__ amax, float target, float* __restrict__ scale_out,
+                                   float* __restrict__ inv_vec) {
+  const float a = *amax;
+  const float s = (a > 0.f && a < INFINITY) ? exp2f(floorf(log2f(target / a))) : 1.f;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0 && scale_out) { scale_out[0] = s; scale_out[1] = 1.f / s; }
+    if (inv_vec) inv_vec[threadIdx.x] = 1.f / s;                        // blockDim.x == 256 entries
+  }
+  const int64_t total = rows * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / cols, c = t - r * cols;
+    dst[r * ld_d + c] = (D)(src[r * ld_s + c] * s);           // round-to-nearest conversion constructors
+  }
+}
+}  // namespace lb
+extern "C" int lb_absmax_f32(const float* src, int64_t ld, int64_t rows, int64_t cols, float* amax, void* stream) {
+  LB_CHECK_ARG(rows >= 0 && cols >= 0 && amax, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  LB_CUDA(cudaMemsetAsync(amax, 0, 4, st));
+  if (rows == 0 || cols == 0) return LB_OK;
+  LB_CHECK_ARG(src && ld >= cols, "null pointer or row stride smaller than the column count");
+  int64_t blocks = (rows * cols + 1023) / 1024, cap = (int64_t)sm_count() * 16;
+  absmax_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(src, ld, rows, cols, (unsigned*)amax); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_cast_scaled(const float* src, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst, int64_t rows, int64_t cols,
+                              const float* amax, float target, float* scale_out, float* inv_vec, void* stream) {
+  LB_CHECK_ARG(rows >= 0 && cols >= 0 && amax && target > 0.f, "bad arguments");
+  LB_CHECK_ARG(rows == 0 || cols == 0 || (src && dst && ld_src >= cols && ld_dst >= cols), "null pointer or bad strides");
+  cudaStream_t st = as_stream(stream);
+  int64_t blocks = (rows * cols + 255) / 256, cap = (int64_t)sm_count() * 32;
+  int g = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+  if (dst_dtype == LB_DT_F16) { cast_scaled_kernel<__half><<<g, 256, 0, st>>>(src, ld_src, (__half*)dst, ld_dst, rows, cols, amax, target, scale_out, inv_vec); LB_LAUNCHED(1); }
+  else if (dst_dtype == LB_DT_BF16) { cast_scaled_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, amax, target, scale_out, inv_vec); LB_LAUNCHED(1); }
+  else { set_error("lb_cast_scaled: dst must be a 16-bit type"); return LB_EINVAL; }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
 extern "C" int lb_tta_softmax_mean_argmax(const float* logits, int64_t n_vox, int n_cls, const int64_t* inverse,
                                           int reps, int64_t n_pts, float* prob, int64_t* pred, void* stream) {
   LB_CHECK_ARG(n_cls > 0 && n_cls <= 32, "n_cls must be in [1,32]");

@@ -192,11 +192,13 @@ def test_conv_backward_shapes_vs_oracle(ts, oracle_ts, small_scan, cin, cout, ks
 
 def test_minkunet_training_step_vs_oracle(ts, oracle_ts, small_scan):
     """Config 4 path: one MinkUNet fwd + cross-entropy + bwd through the drop-in layer (train-mode BatchNorm, tcgen05
-    fwd / dgrad / wgrad).  Two checks: (1) against the oracle with operands rounded to bf16 at the same points
-    (oracle EMULATE_16BIT) -- verifies the kernels; (2) against the pure fp32 oracle -- bounds the precision choice
-    (measured: gradient cosine ~0.91-0.93 with bf16 operands, ~0.99 with fp16, on this 5.5k-voxel random-label case)."""
+    fwd / dgrad / wgrad) against the reference network on the fp32 CPU oracle (train.py:134-137 runs in fp32).
+    Training operands are fp16 with per-tensor power-of-two gradient scaling (compat.nn.functional.TRAIN_DTYPE): every
+    conv weight gradient must point the same way as the fp32 one.  Measured on B200 on this 5.5k-voxel random-label case:
+    cosine min 0.990 / median 0.994, gradient rel-L2 median 0.11 (bf16 operands: cosine 0.91-0.93, rel-L2 ~0.3) -- the
+    residual is forward round-off (2^-11 per operand, the same significand as TF32) flipping ReLU gates and moving the
+    train-mode BatchNorm statistics, not a kernel defect: the per-layer fwd / dgrad / wgrad checks above hold 1e-2."""
     from lidal_b200.network import MinkUNet, seeded_state_dict
-    Fo = oracle_ts.nn.functional
     coords, feats, _ = small_scan
     sel = np.arange(coords.shape[0]) % 3 == 0                      # keep the CPU oracle backward quick
     coords, feats = np.ascontiguousarray(coords[sel]), np.ascontiguousarray(feats[sel])
@@ -210,26 +212,39 @@ def test_minkunet_training_step_vs_oracle(ts, oracle_ts, small_scan):
         logits, _ = model(be.SparseTensor(torch.from_numpy(feats).to(dev), torch.from_numpy(coords).to(dev)))
         loss = torch.nn.functional.cross_entropy(logits, labels.to(dev), ignore_index=255)
         loss.backward()
-        return float(loss), {k: p.grad.detach().cpu().double() for k, p in model.named_parameters() if k.endswith("kernel")}
+        return float(loss.detach()), {k: p.grad.detach().cpu().double() for k, p in model.named_parameters() if k.endswith("kernel")}
 
+    assert ts.nn.functional.TRAIN_DTYPE == torch.float16
     loss_g, grad_g = run(ts, "cuda")
     loss_32, grad_32 = run(oracle_ts, "cpu")
-    try:
-        Fo.EMULATE_16BIT = torch.bfloat16
-        loss_16, grad_16 = run(oracle_ts, "cpu")
-    finally:
-        Fo.EMULATE_16BIT = None
-    assert abs(loss_g - loss_16) / abs(loss_16) < 2e-3 and abs(loss_g - loss_32) / abs(loss_32) < 2e-2
-    err16 = {k: float((grad_g[k] - grad_16[k]).norm() / grad_16[k].norm()) for k in grad_16}
-    cos32 = {k: float((grad_g[k] * grad_32[k]).sum() / (grad_g[k].norm() * grad_32[k].norm())) for k in grad_32}
-    print("vs bf16-emulating oracle: median rel-L2 %.3e, worst %.3e" % (np.median(list(err16.values())), max(err16.values())))
-    print("vs fp32 oracle: min cosine %.4f" % min(cos32.values()))
-    # Per-layer fwd/dgrad/wgrad are checked at 1e-2 above.  Through the whole train-mode network two bf16 computations
-    # decorrelate: activations agree to 6e-10 at the first conv and ~1e-2 at the last (rounding flips), and softmax + BN
-    # batch-statistics backward amplify that to 5 % at the last layer's gradient, growing smoothly to ~30 % at depth
-    # (tools/debug_train_grad.py prints the table; no layer type stands out).  Bound the drift, not bit parity.
-    assert np.median(list(err16.values())) < 0.35 and max(err16.values()) < 0.5, sorted(err16.items(), key=lambda kv: -kv[1])[:3]
-    assert min(cos32.values()) > 0.85
+    assert abs(loss_g - loss_32) / abs(loss_32) < 5e-3
+    err = {k: float((grad_g[k] - grad_32[k]).norm() / grad_32[k].norm()) for k in grad_32}
+    cos = {k: float((grad_g[k] * grad_32[k]).sum() / (grad_g[k].norm() * grad_32[k].norm())) for k in grad_32}
+    worst = sorted(cos.items(), key=lambda kv: kv[1])[:3]
+    print("vs fp32 oracle: gradient rel-L2 median %.3e worst %.3e; cosine min %.4f median %.4f; lowest %s"
+          % (np.median(list(err.values())), max(err.values()), min(cos.values()), np.median(list(cos.values())), worst))
+    assert all(np.isfinite(v).all() for v in grad_g.values())
+    assert min(cos.values()) >= 0.985 and np.median(list(cos.values())) >= 0.99, worst
+    assert np.median(list(err.values())) < 0.15
+
+
+def test_scaled_cast_keeps_tiny_gradients():
+    """lb_absmax_f32 + lb_cast_scaled: gradients far below fp16's normal range survive the cast (relative error of a
+    normal fp16 value), the scale is an exact power of two and inv_vec undoes it."""
+    from lidal_b200.compat.nn import functional as F
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(5000, 96, generator=g) * 3e-7).cuda()
+    x[17, 5] = 4.1e-6
+    g16, inv_vec, scale = F._scaled16(x, torch.float16)
+    s, inv = float(scale[0]), float(scale[1])
+    assert s * inv == 1.0 and np.log2(s) == round(np.log2(s)) and 4096.0 <= 4.1e-6 * s <= 8192.0
+    assert bool((inv_vec == inv).all())
+    back = g16.float() * inv
+    rel = ((back - x).abs() / x.abs().clamp_min(1e-30))[x.abs() > 1e-9]
+    assert float(rel.max()) < 2 ** -10                              # fp16 round-off of NORMAL numbers
+    zero = torch.zeros(8, 32, device="cuda")
+    g16, _, scale = F._scaled16(zero, torch.float16)
+    assert float(scale[0]) == 1.0 and float(g16.abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("cin,cout,res", [(32, 256, False), (256, 128, True), (64, 64, True), (128, 96, False)])
