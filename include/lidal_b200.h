@@ -174,6 +174,9 @@ typedef struct lb_conv_args {
   void* sched_ws;          /* optional device scratch of lb_conv_sched_ws_bytes() bytes, zeroed ONCE by the caller and
                               private to one stream (launches on it are ordered; the kernel leaves it zeroed): enables
                               the dynamic tile scheduler.  NULL = static round-robin tiles.                          */
+  int64_t in_pad_rows;     /* 0, or a power of two >= 16: rows [n_in, n_in + in_pad_rows) of `in` exist and are all ZERO.
+                              Enables the TMA gather producer (tile::gather4 cannot skip rows, so missing neighbours are
+                              fetched from this pool); without it the cp.async producer is used.                       */
 } lb_conv_args;
 
 size_t lb_conv_sched_ws_bytes(void);

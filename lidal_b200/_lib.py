@@ -25,7 +25,7 @@ class ConvArgs(C.Structure):
     _fields_ = [("inp", vp), ("n_in", i64), ("ld_in", i64), ("out", vp), ("n_out", i64), ("ld_out", i64),
                 ("n_out_dev", vp), ("nbr", vp), ("nbr_ld", i64), ("out_rows", vp), ("weight", vp),
                 ("k_vol", i32), ("c_in", i32), ("c_out", i32), ("scale", vp), ("shift", vp), ("residual", vp),
-                ("ld_res", i64), ("act_dtype", i32), ("out_dtype", i32), ("flags", i32), ("sched_ws", vp)]
+                ("ld_res", i64), ("act_dtype", i32), ("out_dtype", i32), ("flags", i32), ("sched_ws", vp), ("in_pad_rows", i64)]
 
 
 class FrameRef(C.Structure):
@@ -158,6 +158,16 @@ def conv_sched_ws():
 
 
 def require_cuda(*tensors):
+    """Every wrapper launches on the CURRENT device's current stream: refuse CPU tensors (no fallback) and tensors that
+    live on another GPU (the kernel would run on the wrong device -- wrap the call in ``torch.cuda.device(t.device)``)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise LidalError("lidal_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise LidalError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}: lidal_b200 launches on the "
+                             "current device's stream (use torch.cuda.set_device / torch.cuda.device)")

@@ -62,16 +62,27 @@ struct TcParams {
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
   int dbg;                 // LIDAL_DBG knock-out bits for bottleneck hunting (results are WRONG when set): 1 = no gather copies,
                            // 2 = no MMA issue, 4 = no output stores
+  int zero_row, zero_mask; // prod_mode 3: rows [zero_row, zero_row + zero_mask] of the input tensor are all zero: absent neighbours
+                           // are gathered from there (spread over the pool so no single L2 line is hammered)
   int prod_warps;          // prod_mode 1: warps that own stages = min(8, stages) -- a warp's consecutive stages must be at most
                            // one ring lap apart, or its parity wait on the empty barrier could be satisfied by an older phase
-  int prod_mode;           // 0: all producer warps fill every stage in lock-step; 1: each producer warp owns whole stages
+  int prod_mode;           // 0: all producer warps fill every stage in lock-step (cp.async); 1: each producer warp owns whole stages
+                           // (cp.async); 2: owned stages, register-staged LDG.128 -> STS.128 with a writer-side proxy fence;
+                           // 3: TMA tile::gather4, all warps on every stage (16 rows of each sub-tile per warp)
                            // (stage q belongs to warp q % prod_warps), so eight dependent fill chains run side by side
   unsigned* sched;         // dynamic tile scheduler: [0] next ticket, [1] retired CTAs (both zero between launches);
                            // nullptr = static round-robin
 };
 
+// Bottleneck-hunting switches (knock-outs, cycle accounting) exist only in a -DLIDAL_CONV_DEBUG build: in the production
+// kernel every `DBG(p)` test folds to zero and the instrumentation disappears.
+#ifdef LIDAL_CONV_DEBUG
+#define DBG(p) ((p).dbg)
+#else
+#define DBG(p) 0
+#endif
 // LIDAL_DBG & 128: cycle accounting of CTA 0 (lane 0 of one warp per role) into the scheduler cell, printed by the host
-#define DBG_ON ((p.dbg & 128) && p.sched && blockIdx.x == 0)
+#define DBG_ON ((DBG(p) & 128) && p.sched && blockIdx.x == 0)
 #define DBG_ADD(slot, val) atomicAdd(reinterpret_cast<unsigned long long*>(p.sched + 16) + (slot), (unsigned long long)(val))
 
 template <typename T> __device__ __forceinline__ float cvt_in(uint16_t raw);
@@ -93,7 +104,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
 template <int BK, int T, int KMAX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap out_map,
-               const __grid_constant__ CUtensorMap res_map, const TcParams p) {
+               const __grid_constant__ CUtensorMap res_map, const __grid_constant__ CUtensorMap in_map, const TcParams p) {
   constexpr int ROW_BYTES = BK * 2;
   constexpr int CHUNKS = ROW_BYTES / 16;                 // 16-byte chunks per row: 8 or 4
   constexpr int A_BYTES = TILE_M * ROW_BYTES;            // 16 KB or 8 KB
@@ -118,8 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   uint64_t* empty_bar = full_bar + MAX_STAGES;                     // [MAX_STAGES]
   uint64_t* tfull_bar = empty_bar + MAX_STAGES;                    // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
-  uint32_t* s_flags = (uint32_t*)(tempty_bar + 2);                 // [MAX_STAGES] reserved (per-stage flag words of the older protocol)
-  uint32_t* s_tmem = s_flags + MAX_STAGES;                         // [1]
+  uint32_t* s_tmem = (uint32_t*)(tempty_bar + 2) + MAX_STAGES;     // [1] (MAX_STAGES words of slack kept in front: tail_bytes() layout)
   uint32_t* s_mask = s_tmem + 1;                                   // [2] active-offset mask of the producers' tile (by parity)
   uint64_t* res_bar = (uint64_t*)(s_mask + 2 + 1);                 // [4] residual rows landed (one per epilogue warp), 8-byte aligned
   uint64_t* tstart_bar = res_bar + 4;                              // [2] tile id of an accumulator set published (MMA warp -> epilogue)
@@ -147,7 +157,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       // every gather thread of the stage posts one asynchronous arrival + 1 expect_tx arrive for the TMA weight tile
-      mbar_init(&full_bar[s], (p.prod_mode == 1 ? 32 : NUM_PROD_THREADS) + 1);
+      mbar_init(&full_bar[s], p.prod_mode == 3 ? 1 : (p.prod_mode >= 1 ? 32 : NUM_PROD_THREADS) + 1);
       mbar_init(&empty_bar[s], 1);                     // released by tcgen05.commit
     }
     for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
@@ -188,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       if (DBG_ON && t == 0) DBG_ADD(5, clock64() - dbg_w);
       if (t == 0) {
         if (first_last & 1u) s_stage_tile[stage] = cur_word;     // tile id | stage count << 24, read once per tile
-        if (p.dbg & 16) mbar_arrive(&full_bar[stage]);
+        if (DBG(p) & 16) mbar_arrive(&full_bar[stage]);
         else {
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
           tma_load_2d(st_u32 + a_blk, &w_map, b_col, b_row, &full_bar[stage]);
@@ -204,7 +214,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           // pack8: 16 bytes = the 8 (padded) channels of one offset; otherwise channels [cb*BK + chunk*8, +8) of the row
           const char* src = in_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b;
           const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
-          if (!(p.dbg & 1)) cp_async16(st_u32 + sub * A_BYTES + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
+          if (!(DBG(p) & 1)) cp_async16(st_u32 + sub * A_BYTES + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
         }
       }
       cp_async_arrive_noinc(&full_bar[stage]);            // asynchronous: fires when this thread's copies have landed
@@ -228,7 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         const int64_t o = o0 + (q % R4) * 4;
         int4 v = make_int4(-1, -1, -1, -1);
         if (k < KMAX && k < p.k_vol && o < n_out) {
-          if (!p.nbr || (p.dbg & 64)) {
+          if (!p.nbr || (DBG(p) & 64)) {
             v.x = (int)o;
             if (o + 1 < n_out) v.y = (int)o + 1;
             if (o + 2 < n_out) v.z = (int)o + 2;
@@ -272,7 +282,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           int4 v = nb_reg[j];
           // one unsigned compare rejects both "no neighbour" (-1) and out-of-range rows
           const bool ox = (uint32_t)v.x < n_in_u, oy = (uint32_t)v.y < n_in_u, oz = (uint32_t)v.z < n_in_u, ow = (uint32_t)v.w < n_in_u;
-          v.x = ox ? v.x : -1; v.y = oy ? v.y : -1; v.z = oz ? v.z : -1; v.w = ow ? v.w : -1;
+          if (p.prod_mode == 3) {                          // absent neighbour -> a row of the zero pool (TMA cannot skip rows)
+            const int z = p.zero_row + ((q * 4 + k * 13) & p.zero_mask);
+            v.x = ox ? v.x : z; v.y = oy ? v.y : p.zero_row + ((z + 1) & p.zero_mask);
+            v.z = oz ? v.z : p.zero_row + ((z + 2) & p.zero_mask); v.w = ow ? v.w : p.zero_row + ((z + 3) & p.zero_mask);
+          } else {
+            v.x = ox ? v.x : -1; v.y = oy ? v.y : -1; v.z = oz ? v.z : -1; v.w = ow ? v.w : -1;
+          }
           *reinterpret_cast<int4*>(&s_idx[k * TM + (q % R4) * 4]) = v;
           if (ox | oy | oz | ow) my_bits |= 1u << k;
         }
@@ -306,7 +322,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
               nbv[sub][i] = kk < p.k_vol ? s_idx[kk * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS] : -1;
           issue(nbv, kb, kb * BK, 0, (kb == 0 ? 1u : 0u) | (kb == nkb - 1 ? 2u : 0u));
         }
-      } else if (p.prod_mode == 1) {
+      } else if (p.prod_mode == 3) {
+        // TMA gather, all producer warps on every stage: warp w brings rows [16w, 16w + 16) of each 128-row sub-tile with
+        // four tile::gather4 instructions (lanes 0-3; lanes 4-7 serve the second sub-tile), so a stage is issued in the
+        // time of 4-8 TMA instructions per warp.  Thread 0 arms the stage's barrier with the byte count of the whole stage
+        // (gathered rows + weight tile); absent neighbours were redirected to the zero pool when the indices were staged.
+        int remaining = __popc(mask) * kc_blocks;
+        cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
+        bool first = true;
+        const int g_sub = lane >> 2, g_row = pw * 16 + (lane & 3) * 4;
+        for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
+          if (!((mask >> k) & 1)) continue;
+          int4 v = make_int4(0, 0, 0, 0);
+          if (lane < 4 * T) v = *reinterpret_cast<const int4*>(&s_idx[k * TM + g_sub * TILE_M + g_row]);
+          for (int cb = 0; cb < kc_blocks; ++cb, --remaining, first = false) {
+            mbar_wait(&empty_bar[stage], ph ^ 1);
+            if (t == 0) {
+              if (first) s_stage_tile[stage] = cur_word;
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(a_blk + b_bytes));
+              tma_load_2d(st_u32 + a_blk, &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
+            }
+            if (lane < 4 * T && !(DBG(p) & 1))
+              tma_gather4(st_u32 + g_sub * A_BYTES + g_row * ROW_BYTES, &in_map, cb * BK, v.x, v.y, v.z, v.w, &full_bar[stage]);
+            st_u32 += stage_bytes;
+            if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+          }
+        }
+      } else if (p.prod_mode >= 1) {
         // Per-warp stage ownership: the CTA's stages are numbered in issue order and stage q is filled entirely by
         // producer warp q % prod_warps (lane = 16-byte chunk of a row x a group of consecutive rows, four row indices per LDS.128).
         // Every warp walks the same (offset, channel block) sequence and skips the stages it does not own, so eight
@@ -328,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
               if (dbg_me) DBG_ADD(5, clock64() - dbg_w);
               if (lane == 0) {
                 if (first) s_stage_tile[stage] = cur_word;
-                if (p.dbg & 16) mbar_arrive(&full_bar[stage]);
+                if (DBG(p) & 16) mbar_arrive(&full_bar[stage]);
                 else {
                   mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
                   tma_load_2d(st_u32 + a_blk, &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
@@ -337,6 +379,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
               const char* src_cb = lane_src + cb * (BK * 2);
               const int4* idx4 = reinterpret_cast<const int4*>(&s_idx[k * TM + lgrp * RPL]);
               const uint32_t dst0 = st_u32 + lane_dst;
+              if (p.prod_mode == 2) {
+                // Register-staged gather: 8 independent 16-byte loads in flight per lane, then 8 shared-memory stores
+                // (absent rows store zeros and load nothing).  Measured on B200 (tools/experiments/gather_bw.cu): LDG + STS
+                // moves twice the bytes per warp that cp.async does for scattered 16-byte pieces.  The stores go through the
+                // generic proxy, so the writer fences towards the async proxy (tcgen05 reads) before it arrives.
+#pragma unroll 1
+                for (int j8 = 0; j8 < RPL / 8; ++j8) {
+                  const int4 va = idx4[2 * j8], vb = idx4[2 * j8 + 1];
+                  const int nb8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+                  uint4 v[8];
+#pragma unroll
+                  for (int u = 0; u < 8; ++u)
+                    v[u] = nb8[u] >= 0 ? __ldg(reinterpret_cast<const uint4*>(src_cb + (int64_t)nb8[u] * ld_in_b)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                  for (int u = 0; u < 8; ++u) {
+                    const int j = j8 * 8 + u;
+                    const uint32_t sw = (BK == 64) ? (uint32_t)(lchunk ^ (j & 7)) : (uint32_t)(lchunk ^ ((j >> 1) & 3));
+                    if (!(DBG(p) & 1))
+                      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)j * ROW_BYTES + sw * 16), "r"(v[u].x),
+                                   "r"(v[u].y), "r"(v[u].z), "r"(v[u].w)
+                                   : "memory");
+                  }
+                }
+                fence_proxy_async();
+                mbar_arrive(&full_bar[stage]);
+              } else {
 #pragma unroll 4
               for (int j4 = 0; j4 < RPL / 4; ++j4) {
                 const int4 v = idx4[j4];
@@ -346,10 +414,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
                   const int j = j4 * 4 + u;                // row within the lane's group; (lgrp * RPL) % 8 == 0
                   const uint32_t sw = (BK == 64) ? (uint32_t)(lchunk ^ (j & 7)) : (uint32_t)(lchunk ^ ((j >> 1) & 3));
                   const int nb = nb4[u];
-                  if (!(p.dbg & 1)) cp_async16(dst0 + (uint32_t)j * ROW_BYTES + sw * 16, src_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b, nb >= 0 ? 16u : 0u);
+                  if (!(DBG(p) & 1)) cp_async16(dst0 + (uint32_t)j * ROW_BYTES + sw * 16, src_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b, nb >= 0 ? 16u : 0u);
                 }
               }
               cp_async_arrive_noinc(&full_bar[stage]);
+              }
             }
             if (++seq == p.prod_warps) seq = 0;
             st_u32 += stage_bytes;
@@ -374,7 +443,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     }
     if (dbg_me) DBG_ADD(4, clock64() - dbg_p0);
     // sentinel stage: no data, tile word -1 tells the MMA warp (and through it the epilogue) that this CTA is out of work
-    if (p.prod_mode == 1) {
+    if (p.prod_mode == 3) {
+      mbar_wait(&empty_bar[stage], ph ^ 1);
+      if (t == 0) {
+        s_stage_tile[stage] = -1;
+        mbar_arrive(&full_bar[stage]);                      // the barrier expects one arrival (thread 0's expect_tx)
+      }
+    } else if (p.prod_mode >= 1) {
       if (seq == pw) {
         mbar_wait(&empty_bar[stage], ph ^ 1);
         if (lane == 0) {
@@ -438,7 +513,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           mbar_wait(&full_bar[stage], ph);
           if (dbg_me) DBG_ADD(1, clock64() - dbg_t);
         }
-        if (!(p.dbg & 8)) fence_proxy_async();            // gathered rows were written through the generic proxy (cp.async)
+        if (p.prod_mode < 2 && !(DBG(p) & 8)) fence_proxy_async();   // cp.async wrote through the generic proxy and cannot fence on the writer side
         tc_fence_after();
         if (elect_one()) {
           const uint32_t b_lo = st_lo + b_units;
@@ -446,7 +521,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           for (int sub = 0; sub < T; ++sub) {             // every sub-tile reuses the same weight tile
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
-              if (!(p.dbg & 2)) umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), st_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
+              if (!(DBG(p) & 2)) umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), st_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
                             b_lo + (uint32_t)kk * 2u, desc_hi, idesc, (kk == 0 && e == 0) ? 0u : 1u);   // first MMA overwrites
           }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
@@ -545,7 +620,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           fence_proxy_async();                              // generic-proxy smem writes -> visible to the copy engine
           __syncwarp();
           if (lane == 0) {
-            if (any_live && !(p.dbg & 4))
+            if (any_live && !(DBG(p) & 4))
               for (int g = 0; g < groups; ++g) tma_store_2d(&out_map, g * 32, (int)row0, smem_u32(sbuf + g * 2048));
             bulk_commit();
           }
@@ -574,7 +649,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         if (dbg_me) DBG_ADD(10, clock64() - dbg_t);
         const int64_t tile = s_acc_tile[acc];
         if (tile < 0) { if (dbg_me) DBG_ADD(9, clock64() - dbg_e0); break; }
-        if (p.dbg & 32) { mbar_wait(&tfull_bar[acc], acc_ph); tc_fence_after(); }
+        if (DBG(p) & 32) { mbar_wait(&tfull_bar[acc], acc_ph); tc_fence_after(); }
         else
         for (int sub = 0; sub < T; ++sub) {
           const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
@@ -643,7 +718,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             }
           }
           fence_proxy_async();                            // my generic-proxy smem writes -> visible to the bulk-copy engine
-          if (live && !(p.dbg & 4)) bulk_store(p.out + orow * p.ld_out * 2, smem_u32(my_row), row_bytes);
+          if (live && !(DBG(p) & 4)) bulk_store(p.out + orow * p.ld_out * 2, smem_u32(my_row), row_bytes);
           bulk_commit();
         }   // sub-tiles
         tc_fence_before();
@@ -888,9 +963,30 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
   static const int prod_mode_env = getenv("LIDAL_PROD_MODE") ? atoi(getenv("LIDAL_PROD_MODE")) : 0;   // A/B switch
+  static const int tma_gather_env = getenv("LIDAL_TMA_GATHER") ? atoi(getenv("LIDAL_TMA_GATHER")) : 1;
   static const int dbg_env = getenv("LIDAL_DBG") ? atoi(getenv("LIDAL_DBG")) : 0;
   p.dbg = dbg_env;
   p.prod_mode = pack8 ? 0 : prod_mode_env;
+  p.zero_row = 0; p.zero_mask = 0;
+  CUtensorMap in_map = map;                      // placeholder unless the TMA gather is used
+  // TMA gather producer: needs a pool of all-zero rows right behind the input (absent neighbours are fetched from there),
+  // a neighbour table (k_vol > 1 or permuted rows) and row indices that fit the tensor map's int32 coordinates
+  if (!pack8 && tma_gather_env && a.nbr && a.in_pad_rows >= 16 && (a.in_pad_rows & (a.in_pad_rows - 1)) == 0 &&
+      a.n_in + a.in_pad_rows < ((int64_t)1 << 31) && ((uintptr_t)a.in & 15) == 0 && (a.ld_in * 2) % 16 == 0 &&
+      (tma_gather_env >= 2 || bk == 64)) {
+    cuuint64_t idim[2] = {(cuuint64_t)a.c_in, (cuuint64_t)(a.n_in + a.in_pad_rows)};
+    cuuint64_t istr[1] = {(cuuint64_t)a.ld_in * 2};
+    cuuint32_t ibox[2] = {(cuuint32_t)bk, 1};
+    r = encode(&in_map, a.act_dtype == LB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+               const_cast<void*>(a.in), idim, istr, ibox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+      p.prod_mode = 3;
+      p.zero_row = (int)a.n_in;
+      p.zero_mask = (int)a.in_pad_rows - 1;
+    }
+  }
   p.prod_warps = stages < NUM_PROD_THREADS / 32 ? stages : NUM_PROD_THREADS / 32;
   static const bool static_tiles = getenv("LIDAL_STATIC_TILES") != nullptr;   // A/B switch
   p.sched = static_tiles ? nullptr : (unsigned*)a.sched_ws;   // caller-owned, zeroed once, private to this stream
@@ -909,7 +1005,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
         if (dev_ >= 0 && dev_ < 64) opted[dev_] = true;                                                               \
       }                                                                                                               \
     }                                                                                                                 \
-    conv_tc_kernel<BKV, TV, KV><<<grid, NUM_THREADS, smem, st>>>(map, out_map, res_map, p);                              \
+    conv_tc_kernel<BKV, TV, KV><<<grid, NUM_THREADS, smem, st>>>(map, out_map, res_map, in_map, p);                              \
     LB_LAUNCHED(1);                                                                                                   \
   } while (0)
 #define LB_TC_LAUNCH_K(BKV, TV)                                                                                       \
@@ -925,7 +1021,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
 #undef LB_TC_LAUNCH_K
 #undef LB_TC_LAUNCH
   LB_LAUNCH_CHECK();
-  if ((p.dbg & 128) && p.sched) {
+  if ((DBG(p) & 128) && p.sched) {
     unsigned long long h[12];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, p.sched + 16, sizeof(h), cudaMemcpyDeviceToHost);

@@ -23,6 +23,27 @@ from .compat.nn import functional as F
 from .compat.nn.utils import get_kernel_offsets
 
 
+ZPAD = int(__import__('os').environ.get('LIDAL_ZPAD', 64))          # all-zero rows kept behind every activation buffer: the TMA gather producer of lb_conv_fwd fetches the
+                   # rows of missing neighbours from there (lb_conv_args.in_pad_rows)
+
+
+def _alloc(n, c, dtype, device):
+    """Activation buffer [n, c] backed by n + ZPAD rows whose tail is zero."""
+    buf = torch.empty((n + ZPAD, c), dtype=dtype, device=device)
+    buf[n:].zero_()
+    buf._zpad = True
+    return buf[:n]
+
+
+def _pad_rows(x):
+    """ZPAD if ``x`` (a row-0 view of an ``_alloc`` buffer, possibly a column slice) is followed by the zero pool, else 0."""
+    base = x._base if x._base is not None else x
+    if getattr(base, "_zpad", False) and base.dim() == 2 and base.shape[0] == x.shape[0] + ZPAD and x.stride(0) == base.stride(0) \
+            and x.storage_offset() - base.storage_offset() < base.stride(0):
+        return ZPAD
+    return 0
+
+
 def _fold_bn(bn, extra_bias=None):
     scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float()
     shift = (bn.bias - bn.running_mean * scale).float()
@@ -71,7 +92,8 @@ class _Conv:
         nbr, out_rows = nbr if isinstance(nbr, tuple) else (nbr, None)
         out_dtype = out_dtype or x.dtype
         if out is None:
-            out = torch.empty((n_out, self.cout), dtype=out_dtype, device=x.device)
+            out = _alloc(n_out, self.cout, out_dtype, x.device) if out_dtype != torch.float32 else \
+                torch.empty((n_out, self.cout), dtype=out_dtype, device=x.device)
         a = L.ConvArgs()
         a.inp, a.n_in, a.ld_in = x.data_ptr(), x.shape[0], x.stride(0)
         a.out, a.n_out, a.ld_out = out.data_ptr(), n_out, out.stride(0)
@@ -87,6 +109,7 @@ class _Conv:
                    | (L.LB_CONV_PACK8 if self.pack8 else 0) | (L.LB_CONV_TILE128 if FORCE_TILE128 else 0)
                    | (L.LB_CONV_NO_STAGED if NO_STAGED else 0))
         a.sched_ws = L.conv_sched_ws()
+        a.in_pad_rows = _pad_rows(x) if nbr is not None else 0
         trace = F.CONV_TRACE
         ev = trace.begin() if trace is not None else None
         L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
@@ -294,7 +317,7 @@ class InferenceEngine:
 
     # ---- trunk pieces
     def _cast(self, x, dtype):
-        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+        out = _alloc(x.shape[0], x.shape[1], dtype, x.device)
         L.check(L.lib().lb_cast(L.ptr(x), L.DT_OF[x.dtype], x.stride(0), L.ptr(out), L.DT_OF[dtype], out.stride(0),
                                 x.shape[0], x.shape[1], L.stream()))
         return out
@@ -328,7 +351,7 @@ class InferenceEngine:
         dev, dt = self.device, self.dtype
         # cat_i = [up_i output | encoder skip] at level 4-i
         widths = [self.up[i].cout + self.dec[i][0].c1.cin - self.up[i].cout for i in range(4)]
-        return [torch.empty((m.n[3 - i], widths[i]), dtype=dt, device=dev) for i in range(4)]
+        return [_alloc(m.n[3 - i], widths[i], dt, dev) for i in range(4)]
 
     @torch.no_grad()
     def __call__(self, coords, feats, return_feat: bool = False):
@@ -491,6 +514,10 @@ class HostPipeline:
             ent = [torch.empty((cap, coords_host.shape[1]), dtype=coords_host.dtype, device=dev),
                    torch.empty((cap, feats_host.shape[1]), dtype=feats_host.dtype, device=dev), None]
             self._in_pool[slot] = ent
+            # the caching allocator may hand back a block that kernels still queued on the compute stream are reading
+            # (activations of the previous step are released as soon as engine() returns): the copy stream must not
+            # write into it before they have finished
+            self.h2d_stream.wait_stream(torch.cuda.current_stream(dev))
         return ent
 
     def submit(self, coords_host: torch.Tensor, feats_host: torch.Tensor):

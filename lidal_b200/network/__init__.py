@@ -7,7 +7,7 @@ definitions living in this repo: the same U-Net is described once as a table
 (``UNET_CHANNELS``) and instantiated against any backend exposing the torchsparse-1.4.0 surface
 (``lidal_b200.compat`` on CUDA, ``oracle/torchsparse`` on CPU).  Module attribute names follow the
 reference so ``state_dict`` keys/shapes are identical (checked against the reference's own
-classes by ``tests/test_oracle_models.py`` when ``/root/reference`` is present).
+classes by ``tests/test_oracle.py`` and ``tests/test_abi.py`` when ``/root/reference`` is present).
 """
 from __future__ import annotations
 

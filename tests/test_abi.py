@@ -55,7 +55,7 @@ def test_struct_layouts_match_header(tmp_path):
         assert got[(cname, "sizeof")] == ctypes.sizeof(ct), cname
         for fname, _t in ct._fields_:
             assert got[(cname, fname)] == getattr(ct, fname).offset, (cname, fname)
-    assert got[("lb_conv_args", "sizeof")] == 160 and got[("lb_frame_ref", "sizeof")] == 32
+    assert got[("lb_conv_args", "sizeof")] == 168 and got[("lb_frame_ref", "sizeof")] == 32
 
 
 def test_no_cpu_fallback():

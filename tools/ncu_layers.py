@@ -13,7 +13,8 @@ m = engine.Maps(coords)
 g = torch.Generator().manual_seed(0)
 for lvl, cin, cout in ((0, 96, 96), (0, 32, 32), (1, 96, 96), (2, 128, 128), (3, 256, 256), (4, 256, 256)):
     n = m.n[lvl]
-    x = torch.randn(n, cin, generator=g).cuda().bfloat16()
+    x = engine._alloc(n, cin, torch.bfloat16, "cuda")
+    x.copy_(torch.randn(n, cin, generator=g).cuda())
     conv = engine._Conv((torch.randn(27, cin, cout, generator=g) * 0.05).cuda(), None, relu=True)
     out = torch.empty(n, cout, dtype=torch.bfloat16, device="cuda")
     for _ in range(2):
