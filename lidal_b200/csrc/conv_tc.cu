@@ -29,8 +29,11 @@ namespace lb {
 constexpr int TILE_M = 128;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int NUM_PROD_THREADS = 256;   // 8 gather warps: two per scheduler, so dependent address/LDS/cp.async chains overlap
-constexpr int NUM_THREADS = NUM_EPI_THREADS + NUM_PROD_THREADS + 32;
+constexpr int NUM_THREADS = NUM_EPI_THREADS + NUM_PROD_THREADS + 64;
 constexpr int MMA_WARP = (NUM_EPI_THREADS + NUM_PROD_THREADS) / 32;
+constexpr int WEIGHT_WARP = MMA_WARP + 1;   // issues the TMA weight-tile loads (and arms the stage barriers) so that the gather
+                                            // warps' per-stage instruction stream carries nothing but the gather itself
+constexpr int PROD_BAR_THREADS = NUM_PROD_THREADS + 32;   // named barrier 1: the gather warps + the weight warp
 constexpr int MAX_STAGES = 12;
 constexpr int MAX_KVOL = 27;
 
@@ -60,6 +63,7 @@ struct TcParams {
   int stg_bufs;            // staging buffers per epilogue warp (2: the stores of one sub-tile drain while the next is built)
   int n_acc;               // TMEM accumulator sets (2 = epilogue overlaps the next tile, 1 when 2*T*c_out > 512)
   int pack8;               // LB_CONV_PACK8: K axis = (offset, 8 channels), 8 offsets per 64-wide K block
+  int wwarp;               // 1: the weight warp loads the weight tiles (lock-step cp.async producer); 0: producer thread 0 does
   int dbg;                 // LIDAL_DBG knock-out bits for bottleneck hunting (results are WRONG when set): 1 = no gather copies,
                            // 2 = no MMA issue, 4 = no output stores
   int zero_row, zero_mask; // prod_mode 3: rows [zero_row, zero_row + zero_mask] of the input tensor are all zero: absent neighbours
@@ -196,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       const long long dbg_w = (DBG_ON && t == 0) ? clock64() : 0;
       mbar_wait(&empty_bar[stage], ph ^ 1);               // slot free (first lap passes immediately)
       if (DBG_ON && t == 0) DBG_ADD(5, clock64() - dbg_w);
-      if (t == 0) {
+      if (t == 0 && !p.wwarp) {
         if (first_last & 1u) s_stage_tile[stage] = cur_word;     // tile id | stage count << 24, read once per tile
         if (DBG(p) & 16) mbar_arrive(&full_bar[stage]);
         else {
@@ -271,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       const int64_t tile = tile_of(cur);
       // (A) every producer has finished reading s_idx / s_mask[par^1] of the previous tile
       long long dbg_t = dbg_me ? clock64() : 0;
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");
       if (dbg_me) { DBG_ADD(6, clock64() - dbg_t); DBG_ADD(8, 1); }
       uint32_t my_bits = 0;
 #pragma unroll
@@ -303,7 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
       // (B) indices and mask of this tile are complete
       dbg_t = dbg_me ? clock64() : 0;
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");
       if (dbg_me) DBG_ADD(7, clock64() - dbg_t);
       uint32_t mask = __reduce_or_sync(0xffffffffu, s_mask[par]);   // same value in every lane; REDUX makes it provably uniform
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
@@ -460,13 +464,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
     } else {
       mbar_wait(&empty_bar[stage], ph ^ 1);
-      if (t == 0) {
+      if (t == 0 && !p.wwarp) {
         s_stage_tile[stage] = -1;
         mbar_arrive(&full_bar[stage]);                      // stands in for the expect_tx arrival of a normal stage
       }
       mbar_arrive(&full_bar[stage]);
     }
     cp_async_wait<0>();                                   // nothing of ours may still be in flight at teardown
+  } else if (warp == WEIGHT_WARP) {
+    // =============================================================== WEIGHT LOADER
+    // Walks the same (tile, offset, channel block) sequence as the gather warps: it joins their two per-tile barriers to
+    // learn the tile's offset mask and the next ticket, and for every stage arms the full barrier with the weight tile's
+    // byte count and issues the TMA load.  The tile word (id | stage count) travels with the tile's first stage.
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&w_map) : "memory");
+    int stage = 0;
+    uint32_t ph = 0, st_u32 = smem_u32(ring);
+    const uint32_t ring_u32 = st_u32;
+    int64_t cur = blockIdx.x;
+    uint32_t par = 0;
+    for (; cur < num_tiles; par ^= 1) {
+      const int64_t tile = tile_of(cur);
+      asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");   // (A)
+      asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");   // (B)
+      uint32_t mask = __reduce_or_sync(0xffffffffu, s_mask[par]);
+      if (mask == 0) mask = 1;
+      const int nx = (int)__reduce_or_sync(0xffffffffu, (uint32_t)s_next[0]);
+      if (p.wwarp) {
+        int remaining = __popc(mask) * kc_blocks;
+        const int cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
+        bool first = true;
+        for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
+          if (!((mask >> k) & 1)) continue;
+          for (int cb = 0; cb < kc_blocks; ++cb, first = false) {
+            mbar_wait(&empty_bar[stage], ph ^ 1);
+            if (lane == 0) {
+              if (first) s_stage_tile[stage] = cur_word;
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
+              tma_load_2d(st_u32 + a_blk, &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
+            }
+            st_u32 += stage_bytes;
+            if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+          }
+        }
+      }
+      cur = nx >= 0 ? nx : num_tiles;
+    }
+    if (p.wwarp) {
+      mbar_wait(&empty_bar[stage], ph ^ 1);
+      if (lane == 0) {
+        s_stage_tile[stage] = -1;                         // sentinel: this CTA is out of work
+        mbar_arrive(&full_bar[stage]);
+      }
+    }
   } else if (warp == MMA_WARP) {
     // =============================================================== MMA ISSUER
     // The issuing warp is a single instruction stream: every instruction here is on the critical path of every stage,
@@ -963,7 +1012,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.nb = nb;
   p.pack8 = pack8 ? 1 : 0;
   static const int prod_mode_env = getenv("LIDAL_PROD_MODE") ? atoi(getenv("LIDAL_PROD_MODE")) : 0;   // A/B switch
-  static const int tma_gather_env = getenv("LIDAL_TMA_GATHER") ? atoi(getenv("LIDAL_TMA_GATHER")) : 1;
+  static const int tma_gather_env = getenv("LIDAL_TMA_GATHER") ? atoi(getenv("LIDAL_TMA_GATHER")) : 0;   // measured slower in situ (profiles/r02_conv_producer_modes.txt)
   static const int dbg_env = getenv("LIDAL_DBG") ? atoi(getenv("LIDAL_DBG")) : 0;
   p.dbg = dbg_env;
   p.prod_mode = pack8 ? 0 : prod_mode_env;
@@ -987,6 +1036,8 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
       p.zero_mask = (int)a.in_pad_rows - 1;
     }
   }
+  static const int wwarp_env = getenv("LIDAL_WEIGHT_WARP") ? atoi(getenv("LIDAL_WEIGHT_WARP")) : 1;   // A/B switch
+  p.wwarp = (!pack8 && p.prod_mode == 0 && wwarp_env) ? 1 : 0;
   p.prod_warps = stages < NUM_PROD_THREADS / 32 ? stages : NUM_PROD_THREADS / 32;
   static const bool static_tiles = getenv("LIDAL_STATIC_TILES") != nullptr;   // A/B switch
   p.sched = static_tiles ? nullptr : (unsigned*)a.sched_ws;   // caller-owned, zeroed once, private to this stream

@@ -23,12 +23,15 @@ from .compat.nn import functional as F
 from .compat.nn.utils import get_kernel_offsets
 
 
-ZPAD = int(__import__('os').environ.get('LIDAL_ZPAD', 64))          # all-zero rows kept behind every activation buffer: the TMA gather producer of lb_conv_fwd fetches the
-                   # rows of missing neighbours from there (lb_conv_args.in_pad_rows)
+# The TMA gather producer of lb_conv_fwd (LIDAL_TMA_GATHER=1, off by default: measured slower than cp.async in situ) fetches
+# the rows of missing neighbours from a pool of all-zero rows behind the input (lb_conv_args.in_pad_rows).
+ZPAD = int(__import__('os').environ.get('LIDAL_ZPAD', 64)) if int(__import__('os').environ.get('LIDAL_TMA_GATHER', 0)) else 0
 
 
 def _alloc(n, c, dtype, device):
-    """Activation buffer [n, c] backed by n + ZPAD rows whose tail is zero."""
+    """Activation buffer [n, c]; with the TMA gather producer enabled it is backed by n + ZPAD rows whose tail is zero."""
+    if ZPAD == 0:
+        return torch.empty((n, c), dtype=dtype, device=device)
     buf = torch.empty((n + ZPAD, c), dtype=dtype, device=device)
     buf[n:].zero_()
     buf._zpad = True
@@ -37,6 +40,8 @@ def _alloc(n, c, dtype, device):
 
 def _pad_rows(x):
     """ZPAD if ``x`` (a row-0 view of an ``_alloc`` buffer, possibly a column slice) is followed by the zero pool, else 0."""
+    if ZPAD == 0:
+        return 0
     base = x._base if x._base is not None else x
     if getattr(base, "_zpad", False) and base.dim() == 2 and base.shape[0] == x.shape[0] + ZPAD and x.stride(0) == base.stride(0) \
             and x.storage_offset() - base.storage_offset() < base.stride(0):
@@ -159,10 +164,19 @@ class _HostCounters:
     def ptr(self, i):
         return C.c_void_p(self.buf.data_ptr() + 4 * i)
 
-    def read(self, i) -> int:
-        self.ev.record()
-        self.ev.synchronize()
+    def read(self, i, ev=None) -> int:
+        """Value of slot i.  ``ev`` (from ``mark()``, recorded right after the producing launch) makes the wait cover only
+        that launch: work queued afterwards keeps the GPU busy while the host learns the count."""
+        if ev is None:
+            ev = self.ev
+            ev.record()
+        ev.synchronize()
         return int(self.buf[i])
+
+    def mark(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
 
     def pinned_copy(self, dev_scalar: torch.Tensor, i: int):
         """Queue a copy of a device int32 scalar into slot i; the returned callable reads it after the next ``read``."""
@@ -245,33 +259,36 @@ class Maps:
         for lvl in range(5):
             s = 2 ** lvl
             c = self.coords[lvl]
+            n_c = c.shape[0]
+            if lvl < 4:
+                # level transition first (no sort, no hash queries): parents in first-occurrence order + both maps.  Its row
+                # count is the only thing the host needs; everything queued below keeps the GPU busy while it is read back.
+                cn_full = torch.empty_like(c)
+                cnt = _counters(dev)
+                dn_full = torch.empty((8, n_c), dtype=torch.int, device=dev)
+                up = torch.empty((8, n_c), dtype=torch.int, device=dev)
+                nbytes = L.lib().lb_downsample_maps_ws_bytes(n_c)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                L.check(L.lib().lb_downsample_maps(L.ptr(c), n_c, s, L.ptr(cn_full), cnt.ptr(lvl), L.ptr(dn_full), n_c, L.ptr(up),
+                                                   L.ptr(ws), nbytes, L.stream()))
+                counted = cnt.mark()
             table = F._build_table(F.sphash(c))
             self.tables.append(table)
             off3 = _offsets(3, s, dev)
-            nbr3 = torch.empty((27, c.shape[0]), dtype=torch.int, device=dev)
+            nbr3 = torch.empty((27, n_c), dtype=torch.int, device=dev)
             # submanifold map: in == out coordinates, point-symmetric offsets -> probe 14 offsets, mirror the other 13
-            L.check(L.lib().lb_kmap_query_sym(L.ptr(table[0]), table[1], L.ptr(c), c.shape[0], L.ptr(off3), 27,
+            L.check(L.lib().lb_kmap_query_sym(L.ptr(table[0]), table[1], L.ptr(c), n_c, L.ptr(off3), 27,
                                               L.ptr(nbr3), nbr3.stride(0), L.stream()))
             self.nbr3.append(_mask_sorted(nbr3) if SORT_MAPS else nbr3)
             if lvl == 4:
                 break
-            # level transition in one pass (no sort, no hash queries): parents in first-occurrence order + both maps
-            n_c = c.shape[0]
-            cn_full = torch.empty_like(c)
-            cnt = _counters(dev)
-            dn_full = torch.empty((8, n_c), dtype=torch.int, device=dev)
-            up = torch.empty((8, n_c), dtype=torch.int, device=dev)
-            nbytes = L.lib().lb_downsample_maps_ws_bytes(n_c)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            L.check(L.lib().lb_downsample_maps(L.ptr(c), n_c, s, L.ptr(cn_full), cnt.ptr(lvl), L.ptr(dn_full), n_c, L.ptr(up),
-                                               L.ptr(ws), nbytes, L.stream()))
-            m_c = cnt.read(lvl)
+            self.nbr_up.append(_mask_sorted(up) if SORT_MAPS else up)
+            m_c = cnt.read(lvl, counted)
             cn = cn_full[:m_c]
             dn = dn_full[:, :m_c]
             self.coords.append(cn)
             self.n.append(cn.shape[0])
             self.nbr_dn.append(_mask_sorted(dn) if SORT_MAPS else dn)
-            self.nbr_up.append(_mask_sorted(up) if SORT_MAPS else up)
 
 
 def _maps_algorithmic_bytes(self):
