@@ -374,8 +374,30 @@ class InferenceEngine:
     def __call__(self, coords, feats, return_feat: bool = False):
         """logits f32 [N, n_cls]; with ``return_feat`` also the model's second output (network/minkunet.py:122 ``y4.F``,
         network/spvcnn.py:155 ``z3.F``): the 96-channel features in the engine's 16-bit activation type."""
+        return self.forward(self.prepare(coords, feats), return_feat)
+
+    @torch.no_grad()
+    def prepare(self, coords, feats) -> "Prepared":
+        """Everything that depends only on the coordinates: voxel grouping (SPVCNN), the 9 kernel maps and the point <-> voxel
+        queries.  This is the only phase with host round trips (row counts of the levels), so callers that stream batches run
+        it on a side stream while the previous batch's ``forward`` occupies the GPU (``StreamPipeline``)."""
         L.require_cuda(coords, feats)
-        logits, feat = self._spvcnn(coords, feats) if self.is_spvcnn else self._minkunet(coords, feats)
+        pr = Prepared()
+        coords = coords.contiguous()
+        if self.is_spvcnn:
+            pr.zc, vcoords, pr.feats = self._initial_voxelize(coords, feats)
+            m = pr.m = self._maps(vcoords)
+            pr.q = {}
+            for lvl in (0, 4, 2):
+                pr.q[lvl] = self._corner_query(pr.zc, m, lvl) + self._cell_query(pr.zc, m, lvl)
+        else:
+            pr.m, pr.feats = self._maps(coords), feats
+        return pr
+
+    @torch.no_grad()
+    def forward(self, pr: "Prepared", return_feat: bool = False):
+        """The network proper on prepared maps: no host synchronisation, every launch is queued on the current stream."""
+        logits, feat = self._spvcnn(pr) if self.is_spvcnn else self._minkunet(pr)
         return (logits, feat) if return_feat else logits
 
     @staticmethod
@@ -386,8 +408,8 @@ class InferenceEngine:
             box["m"] = Maps(coords)
         return box["m"]
 
-    def _minkunet(self, coords, feats):
-        m = self._maps(coords.contiguous())
+    def _minkunet(self, pr):
+        m, feats = pr.m, pr.feats
         cats = self._cat_buffers(m)
         x = self._stem(self._pad8(feats), m, cats[3])
         for lvl in range(1, 5):
@@ -464,33 +486,86 @@ class InferenceEngine:
         vfeats = self._vox(feats.contiguous(), inv, counts, nv)
         return zc, vcoords, vfeats
 
-    def _spvcnn(self, coords, feats):
-        zc, vcoords, vfeats = self._initial_voxelize(coords.contiguous(), feats)
-        m = self._maps(vcoords)
+    def _spvcnn(self, pr):
+        m, vfeats = pr.m, pr.feats
+        (iq0, w0, ci0, cn0), (iq4, w4, ci4, cn4), (iq2, w2, ci2, cn2) = pr.q[0], pr.q[4], pr.q[2]
         cats = self._cat_buffers(m)
         x0 = self._stem(self._pad8(vfeats), m, cats[3])
-        iq0, w0 = self._corner_query(zc, m, 0)
         z0 = self._devox(x0, iq0, w0)                                            # [Np, 32]
-        ci0, cn0 = self._cell_query(zc, m, 0)
         x = self._cast(self._vox(z0, ci0, cn0, m.n[0]), self.dtype)
         for lvl in range(1, 5):
             skip_out = cats[3 - lvl][:, self.up[3 - lvl].cout:] if lvl < 4 else None
             x = self._encode(x, m, lvl, out=skip_out)
-        iq4, w4 = self._corner_query(zc, m, 4)
         z1 = self.mlp[0](z0, None, z0.shape[0], residual=self._devox(x, iq4, w4), relu_first=True)   # [Np, 256]
-        ci4, cn4 = self._cell_query(zc, m, 4)
         y = self._cast(self._vox(z1, ci4, cn4, m.n[4]), self.dtype)              # dropout: identity in eval
         y = self._decode(y, m, 1, cats[0])
         y = self._decode(y, m, 2, cats[1])
-        iq2, w2 = self._corner_query(zc, m, 2)
         z2 = self.mlp[1](z1, None, z1.shape[0], residual=self._devox(y, iq2, w2), relu_first=True)   # [Np, 128]
-        ci2, cn2 = self._cell_query(zc, m, 2)
         y = self._cast(self._vox(z2, ci2, cn2, m.n[2]), self.dtype)
         y = self._decode(y, m, 3, cats[2])
         y = self._decode(y, m, 4, cats[3])
         z3 = self.mlp[2](z2, None, z2.shape[0], residual=self._devox(y, iq0, w0), relu_first=True)   # [Np, 96]
         logits = self.classifier(z3, None, z3.shape[0], out_dtype=torch.float32)
         return logits[:, : self.n_cls], z3
+
+
+class Prepared:
+    """Coordinate-only state of one batch (``InferenceEngine.prepare``): maps ``m``, input features ``feats`` (voxel means
+    for SPVCNN), float point coordinates ``zc`` and the per-level point queries ``q[lvl] = (corner idx, weights, cell idx, counts)``."""
+    __slots__ = ("m", "feats", "zc", "q", "ready")
+
+    def __init__(self):
+        self.m = self.feats = self.zc = self.ready = None
+        self.q = {}
+
+    def tensors(self):
+        m = self.m
+        for t in m.coords:
+            yield t
+        for tab in m.tables:
+            yield tab[0]
+        for group in (m.nbr3, m.nbr_dn, m.nbr_up):
+            for item in group:
+                for t in (item if isinstance(item, tuple) else (item,)):
+                    yield t._base if t._base is not None else t
+        for t in (self.feats, self.zc):
+            if t is not None:
+                yield t
+        for q in self.q.values():
+            yield from q
+
+
+class StreamPipeline:
+    """Streams batches through the engine with the host round trips off the critical path: ``prepare`` of batch i runs on a
+    side stream (its row-count read-backs block the host only), ``forward`` of batch i on the caller's stream.  Because
+    ``submit(i)`` returns as soon as forward(i) is QUEUED, the next ``submit`` prepares batch i+1 while the GPU is still
+    busy with forward(i): map construction and its synchronisation bubbles hide behind the convolutions."""
+
+    def __init__(self, engine: "InferenceEngine"):
+        self.engine = engine
+        self.prep_stream = torch.cuda.Stream(device=engine.device)
+
+    def prepare(self, coords, feats, after=None, wait_main=True) -> Prepared:
+        """``after``: event that makes the inputs valid (e.g. their H2D copy); else ``wait_main`` orders the side stream behind
+        everything queued on the caller's stream -- pass False when the inputs are already complete (resident batches, or
+        tensors produced on the side stream itself), otherwise the previous batch's forward would be waited for."""
+        main = torch.cuda.current_stream(self.engine.device)
+        with torch.cuda.stream(self.prep_stream):
+            if after is not None:
+                self.prep_stream.wait_event(after)          # e.g. the H2D copy of this batch
+            elif wait_main:
+                self.prep_stream.wait_stream(main)          # inputs produced on the caller's stream
+            pr = self.engine.prepare(coords, feats)
+            pr.ready = torch.cuda.Event()
+            pr.ready.record(self.prep_stream)
+        for t in pr.tensors():                              # allocated on the side stream, consumed on the caller's stream
+            t.record_stream(main)
+        return pr
+
+    def submit(self, coords, feats, return_feat=False, after=None, wait_main=True):
+        pr = self.prepare(coords, feats, after, wait_main)
+        torch.cuda.current_stream(self.engine.device).wait_event(pr.ready)
+        return self.engine.forward(pr, return_feat)
 
 
 class HostPipeline:
@@ -507,6 +582,7 @@ class HostPipeline:
         self.h2d_stream = torch.cuda.Stream(device=engine.device)
         self.d2h_stream = torch.cuda.Stream(device=engine.device)
         self.depth = depth
+        self.stream_pipe = StreamPipeline(engine)
         self.pending = []          # (logits_dev, out_host, done_event)
         self._out_pool = {}
         self._in_pool = {}
@@ -554,7 +630,7 @@ class HostPipeline:
             ready.record(self.h2d_stream)
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ready)
-        logits = self.engine(c, f)
+        logits = self.stream_pipe.submit(c, f, after=ready)   # maps of this batch are built while the previous forward runs
         computed = torch.cuda.Event()
         computed.record(cur)
         ent[2] = computed

@@ -184,12 +184,25 @@ def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: i
     t = [ev() for _ in range(5)]
     scorer = score.SequenceScorer(dev, nei_num, dis_thresh, n_total=n_frames)
     timings: dict = {"frames_total": n_frames, "frames_own": len(own), "world": world}
+    from . import voxelizer
+    from .engine import StreamPipeline
+    sp = StreamPipeline(engine)
+    main = torch.cuda.current_stream(dev)
+    sp.prep_stream.wait_stream(main)
     t[0].record()
     for fid in own:
         raw, pose, sv_id, regions = frame_source(fid)
-        raw_dev = torch.as_tensor(raw).to(dev, non_blocking=True)
-        xyz = score.register_points(raw_dev, pose)
-        prob, _pred = prob_inference_frame(engine, raw_dev, seed + fid, inf_reps)
+        # coordinate-only work of frame i (upload, registration, TTA voxelizer, kernel maps: all the host round trips) on the
+        # side stream, while the GPU is still busy with the network of frame i-1 on the main stream
+        with torch.cuda.stream(sp.prep_stream):
+            raw_dev = torch.as_tensor(raw).to(dev, non_blocking=True)
+            xyz = score.register_points(raw_dev, pose)
+            coords, feats, inverse = voxelizer.tta_batch_gpu(raw_dev, seed=seed + fid, inf_reps=inf_reps)
+        pr = sp.prepare(coords, feats, wait_main=False)
+        for x in (raw_dev, xyz, coords, feats, inverse):
+            x.record_stream(main)
+        main.wait_event(pr.ready)
+        prob, _pred = score.tta_tail(engine.forward(pr), inverse, inf_reps)
         scorer.add_frame(xyz, prob, sv_id, regions, fid=fid)
     t[1].record()
     # ---- halo: neighbour-window frames owned by other ranks
