@@ -429,6 +429,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
           }
         }
+      } else if (p.wwarp) {
+        // Lock-step gather with multi-block stages: a stage carries up to p.nb consecutive (offset, channel block) blocks of
+        // the tile, so the slot wait, the barrier arrival and the ring bookkeeping are paid once per p.nb blocks (the weight
+        // warp arms the barrier and loads the matching weight tiles; the MMA warp issues all blocks of a stage back to back).
+        int remaining = __popc(mask) * kc_blocks;         // blocks of this tile still to issue
+        int j = 0;                                        // block slot inside the open stage
+        for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
+          if (!((mask >> k) & 1)) continue;
+#pragma unroll
+          for (int sub = 0; sub < T; ++sub)
+#pragma unroll
+            for (int i = 0; i < PASSES; ++i) nbv[sub][i] = s_idx[k * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS];
+          for (int cb = 0; cb < kc_blocks; ++cb) {
+            if (j == 0) mbar_wait(&empty_bar[stage], ph ^ 1);     // slot free (first lap passes immediately)
+            const char* in_cb = in_col + cb * (BK * 2);
+            const uint32_t blk_u32 = st_u32 + (uint32_t)(j * a_blk);
+#pragma unroll
+            for (int sub = 0; sub < T; ++sub) {
+#pragma unroll
+              for (int i = 0; i < PASSES; ++i) {
+                const int r = row0 + i * ROWS_PER_PASS;
+                const int nb = nbv[sub][i];
+                const char* src = in_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b;
+                const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
+                if (!(DBG(p) & 1)) cp_async16(blk_u32 + sub * A_BYTES + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
+              }
+            }
+            --remaining;
+            if (++j == p.nb || remaining == 0) {
+              cp_async_arrive_noinc(&full_bar[stage]);    // asynchronous: fires when this thread's copies have landed
+              j = 0;
+              st_u32 += stage_bytes;
+              if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+            }
+          }
+        }
       } else {
         int remaining = __popc(mask) * kc_blocks;
         cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
@@ -490,20 +526,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       if (mask == 0) mask = 1;
       const int nx = (int)__reduce_or_sync(0xffffffffu, (uint32_t)s_next[0]);
       if (p.wwarp) {
-        int remaining = __popc(mask) * kc_blocks;
+        int remaining = __popc(mask) * kc_blocks;         // blocks of this tile
         const int cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
         bool first = true;
+        int j = 0;
         for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
           if (!((mask >> k) & 1)) continue;
-          for (int cb = 0; cb < kc_blocks; ++cb, first = false) {
-            mbar_wait(&empty_bar[stage], ph ^ 1);
-            if (lane == 0) {
-              if (first) s_stage_tile[stage] = cur_word;
-              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)b_bytes);
-              tma_load_2d(st_u32 + a_blk, &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
+          for (int cb = 0; cb < kc_blocks; ++cb) {
+            if (j == 0) {                                 // open a stage: arm its barrier with all of its weight bytes
+              mbar_wait(&empty_bar[stage], ph ^ 1);
+              if (lane == 0) {
+                if (first) s_stage_tile[stage] = cur_word;
+                const int in_stage = remaining < p.nb ? remaining : p.nb;
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(in_stage * b_bytes));
+              }
+              first = false;
             }
-            st_u32 += stage_bytes;
-            if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+            if (lane == 0) tma_load_2d(st_u32 + (uint32_t)(p.nb * a_blk + j * b_pad), &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
+            --remaining;
+            if (++j == p.nb || remaining == 0) {
+              j = 0;
+              st_u32 += stage_bytes;
+              if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+            }
           }
         }
       }
@@ -523,7 +568,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     const uint32_t idesc = make_idesc(TILE_M, p.c_out, p.is_bf16 ? 1 : 0);
     const uint32_t desc_hi = (SBO >> 4) | (1u << 14) | (LAYOUT << 29);             // bits 32-45 SBO, 46 version, 61-63 swizzle
     const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);      // bits 0-13 address >> 4, 16-29 LBO = 1
-    const uint32_t stage_units = (uint32_t)stage_bytes >> 4, b_units = (uint32_t)(p.nb * a_blk) >> 4;
+    const uint32_t stage_units = (uint32_t)stage_bytes >> 4, b_units = (uint32_t)(p.nb * a_blk) >> 4, b_pad_units = (uint32_t)b_pad >> 4;
     constexpr uint32_t A_UNITS = A_BYTES >> 4;
     int stage = 0;
     uint32_t ph = 0, st_lo = ring_lo;
@@ -550,13 +595,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         if (dbg_me) DBG_ADD(0, clock64() - dbg_m0);
         break;
       }
-      const int n_st = (int)(word >> 24);
+      const int n_blk = (int)(word >> 24);                       // blocks of the tile; a stage carries up to p.nb of them
       if (lane == 0) {
         s_acc_tile[acc] = (int)(word & 0xffffffu);               // the epilogue learns its tile before the MMAs finish
         mbar_arrive(&tstart_bar[acc]);
       }
-      if (dbg_me) DBG_ADD(3, n_st);
-      for (int e = 0; e < n_st; ++e) {
+      if (dbg_me) DBG_ADD(3, n_blk);
+      for (int e = 0, done = 0; done < n_blk; ++e) {
+        const int nbs = (n_blk - done) < p.nb ? (n_blk - done) : p.nb;
         if (e) {
           dbg_t = dbg_me ? clock64() : 0;
           mbar_wait(&full_bar[stage], ph);
@@ -565,18 +611,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         if (p.prod_mode < 2 && !(DBG(p) & 8)) fence_proxy_async();   // cp.async wrote through the generic proxy and cannot fence on the writer side
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t b_lo = st_lo + b_units;
+          for (int j = 0; j < nbs; ++j) {                 // the blocks of this stage, back to back
+            const uint32_t a_lo = st_lo + (uint32_t)j * (uint32_t)T * A_UNITS;
+            const uint32_t b_lo = st_lo + b_units + (uint32_t)j * b_pad_units;
 #pragma unroll
-          for (int sub = 0; sub < T; ++sub) {             // every sub-tile reuses the same weight tile
+            for (int sub = 0; sub < T; ++sub) {           // every sub-tile reuses the same weight tile
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
-              if (!(DBG(p) & 2)) umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), st_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
-                            b_lo + (uint32_t)kk * 2u, desc_hi, idesc, (kk == 0 && e == 0) ? 0u : 1u);   // first MMA overwrites
+              for (int kk = 0; kk < BK / 16; ++kk)        // +32 bytes along K inside the swizzle atom = +2 in the address field
+                if (!(DBG(p) & 2)) umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), a_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
+                              b_lo + (uint32_t)kk * 2u, desc_hi, idesc, (kk == 0 && e == 0 && j == 0) ? 0u : 1u);   // first MMA overwrites
+            }
           }
           umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-          if (e == n_st - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+          if (done + nbs == n_blk) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
         __syncwarp();
+        done += nbs;
         st_lo += stage_units;
         if (++stage == p.stages) { stage = 0; ph ^= 1; st_lo = ring_lo; }
       }
@@ -967,12 +1017,24 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const size_t budget = 227 * 1024 - 1024 - tail_bytes(T);
   // blocks per stage: measured on B200, carrying several blocks per stage (fewer, coarser stages) is not faster than
   // a deep ring of single-block stages -- the kernel is bound by L2 traffic, not by the per-stage hand-shake.
+  // (round 2: with the weight warp, the per-stage hand-shake of the gather warps is the bound on the fine levels --
+  // profiles/r02_conv_knockouts.txt -- so stages carry up to LIDAL_NB_MAX blocks wherever >= 3 such stages still fit)
+  static const int nb_max = getenv("LIDAL_NB_MAX") ? atoi(getenv("LIDAL_NB_MAX")) : 2;
+  static const int prod_mode_env0 = getenv("LIDAL_PROD_MODE") ? atoi(getenv("LIDAL_PROD_MODE")) : 0;
+  static const int wwarp_env0 = getenv("LIDAL_WEIGHT_WARP") ? atoi(getenv("LIDAL_WEIGHT_WARP")) : 1;
   int nb = 1;
+  static const int tma_gather_env0 = getenv("LIDAL_TMA_GATHER") ? atoi(getenv("LIDAL_TMA_GATHER")) : 0;
+  if (!pack8 && prod_mode_env0 == 0 && wwarp_env0 && !tma_gather_env0 && a.k_vol * (a.c_in / bk) > 1) {
+    const size_t stg = (a.out_dtype != LB_DT_F32 && !(a.flags & LB_CONV_NO_STAGED_EPILOGUE)) ? staging_bytes(a.c_out) : 0;
+    for (int cand = nb_max; cand > 1; --cand)
+      if (budget > stg && (budget - stg) / ((size_t)cand * block_bytes) >= 3) { nb = cand; break; }
+  }
   const size_t stage_bytes = nb * block_bytes;
   // smem-staged epilogue (coalesced bulk row copies) when the output is 16-bit and the ring keeps enough stages:
   // all blocks of a tile for short K loops (1x1 layers are pure epilogue), at least 5 stages otherwise
   const int blocks_per_tile = pack8 ? (a.k_vol * 8 + bk - 1) / bk : a.k_vol * (a.c_in / bk);
-  const int want_stages = blocks_per_tile < 5 ? (blocks_per_tile < 3 ? 3 : blocks_per_tile) : 5;
+  int want_stages = blocks_per_tile < 5 ? (blocks_per_tile < 3 ? 3 : blocks_per_tile) : 5;
+  if (nb > 1) want_stages = (want_stages + nb - 1) / nb < 3 ? 3 : (want_stages + nb - 1) / nb;   // same number of blocks in flight
   p.staged = 0;
   p.stg_bufs = 1;
   size_t budget_eff = budget;
