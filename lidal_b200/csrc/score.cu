@@ -56,8 +56,10 @@ __host__ __device__ __forceinline__ GridView grid_view(const void* g) {
   return v;
 }
 constexpr long long CELL_BIAS = 1 << 20;
+// (every user -- grid build, cell-relative coordinates, queries -- goes through this one function, so cell membership is
+// consistent by construction; a multiply by the reciprocal replaces three double divisions per query)
 __device__ __forceinline__ long long cell_of(double x, double cell) {
-  long long c = (long long)floor(x / cell);
+  long long c = (long long)floor(x * (1.0 / cell));
   return c < -CELL_BIAS + 2 ? -CELL_BIAS + 2 : (c > CELL_BIAS - 2 ? CELL_BIAS - 2 : c);
 }
 __device__ __forceinline__ uint64_t cell_key(long long ix, long long iy, long long iz) {
@@ -174,33 +176,34 @@ nn_search_kernel(const void* __restrict__ q_grid, int64_t nq, const __grid_const
     const float gap2z[3] = {rzf * rzf, 0.f, (cellf - rzf) * (cellf - rzf)};
     double best = INFINITY;
     int bi = 0x7fffffff;
+    // which of the 27 cells can hold a match: straight-line predicated arithmetic (no divergence), one bit per cell
+    uint32_t cells = 0;
 #pragma unroll
-    for (int ix = 0; ix < 3; ++ix) {
-      if (gap2x[ix] > t2f) continue;
+    for (int ix = 0; ix < 3; ++ix)
 #pragma unroll
-      for (int iy = 0; iy < 3; ++iy) {
-        const float gxy = gap2x[ix] + gap2y[iy];
-        if (gxy > t2f) continue;
+      for (int iy = 0; iy < 3; ++iy)
 #pragma unroll
-        for (int iz = 0; iz < 3; ++iz) {
-          if (gxy + gap2z[iz] > t2f) continue;
-          const int ox = ix - 1, oy = iy - 1, oz = iz - 1;
-          const int2 run = grid_find(g, cell_key(cx + ox, cy + oy, cz + oz));
-          if (run.y == 0) continue;
-          const float fx = rxf - (float)ox * cellf, fy = ryf - (float)oy * cellf, fz = rzf - (float)oz * cellf;
-          for (int j = run.x; j < run.x + run.y; ++j) {
-            const float ex = fx - __ldg(&g.rel[3 * (int64_t)j]), ey = fy - __ldg(&g.rel[3 * (int64_t)j + 1]),
-                        ez = fz - __ldg(&g.rel[3 * (int64_t)j + 2]);
-            if (ex * ex + ey * ey + ez * ez > t2f) continue;
-            // sklearn euclidean rdist: d = 0; d += t*t per axis, no FMA contraction
-            const double tx = __dsub_rn(qx, __ldg(&g.xyz[3 * (int64_t)j]));
-            const double ty = __dsub_rn(qy, __ldg(&g.xyz[3 * (int64_t)j + 1]));
-            const double tz = __dsub_rn(qz, __ldg(&g.xyz[3 * (int64_t)j + 2]));
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
-            const int oj = __ldg(&g.orig[j]);
-            if (d2 < best || (d2 == best && oj < bi)) { best = d2; bi = oj; }
-          }
-        }
+        for (int iz = 0; iz < 3; ++iz)
+          cells |= (gap2x[ix] + gap2y[iy] + gap2z[iz] <= t2f) ? (1u << (ix * 9 + iy * 3 + iz)) : 0u;
+    // every lane walks only its own surviving cells (~6): the warp iterates max-popcount times instead of 27
+    while (cells) {
+      const int c = __ffs(cells) - 1;
+      cells &= cells - 1;
+      const int ox = c / 9 - 1, oy = (c / 3) % 3 - 1, oz = c % 3 - 1;
+      const int2 run = grid_find(g, cell_key(cx + ox, cy + oy, cz + oz));
+      if (run.y == 0) continue;
+      const float fx = rxf - (float)ox * cellf, fy = ryf - (float)oy * cellf, fz = rzf - (float)oz * cellf;
+      for (int j = run.x; j < run.x + run.y; ++j) {
+        const float ex = fx - __ldg(&g.rel[3 * (int64_t)j]), ey = fy - __ldg(&g.rel[3 * (int64_t)j + 1]),
+                    ez = fz - __ldg(&g.rel[3 * (int64_t)j + 2]);
+        if (ex * ex + ey * ey + ez * ez > t2f) continue;
+        // sklearn euclidean rdist: d = 0; d += t*t per axis, no FMA contraction
+        const double tx = __dsub_rn(qx, __ldg(&g.xyz[3 * (int64_t)j]));
+        const double ty = __dsub_rn(qy, __ldg(&g.xyz[3 * (int64_t)j + 1]));
+        const double tz = __dsub_rn(qz, __ldg(&g.xyz[3 * (int64_t)j + 2]));
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
+        const int oj = __ldg(&g.orig[j]);
+        if (d2 < best || (d2 == best && oj < bi)) { best = d2; bi = oj; }
       }
     }
     nn_fm[(int64_t)f * nq + sp] = (bi != 0x7fffffff && __dsqrt_rn(best) <= thresh) ? bi : -1;
