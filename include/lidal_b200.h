@@ -243,6 +243,17 @@ int lb_voxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_feats, con
 int lb_devoxelize_fwd_ex(const void* feats, int feats_dtype, int64_t ld_feats, const int32_t* idx, const float* w,
                          int64_t n, int64_t m, int c, void* out, int out_dtype, int64_t ld_out, void* stream);
 
+/* Atomic-free F.spvoxelize for the engine.  lb_segment_order: from the point -> voxel index (idx int32 [n], -1 = none) and
+ * its histogram (counts int32 [m], lb_count) build seg_ptr int32 [m+1] (exclusive scan) and order int32 [seg_ptr[m]] = the
+ * point ids of every voxel, contiguous per voxel (order inside a voxel unspecified) -- coordinates only, reusable by every
+ * voxelize at that level.  lb_voxelize_segments: out[v] = mean of feats[order[seg_ptr[v] .. seg_ptr[v+1])] in fp32,
+ * written as 16-bit [m, ld_out]; feats 16-bit [n, ld_feats]; c % 8 == 0. */
+size_t lb_segment_order_ws_bytes(int64_t m);
+int lb_segment_order(const int32_t* idx, int64_t n, const int32_t* counts, int64_t m, int32_t* seg_ptr, int32_t* order, void* ws,
+                     size_t ws_bytes, void* stream);
+int lb_voxelize_segments(const void* feats, int dtype, int64_t ld_feats, const int32_t* order, const int32_t* seg_ptr, int64_t m, int c,
+                         void* out, int64_t ld_out, void* stream);
+
 /* Score-mode voxelizer (dataset/sk_dataset.py:143-169), two steps around the caller's
  * data-dependent random shift:  lb_tta_transform: coords_f64 = (raw[:, :3] @ trans_m) * scale (float64 [n,3]) and
  * feats f32 [n,4] = (transformed xyz as f32, intensity);  lb_tta_quantize: (coords_f64 + offset).astype(int) ->

@@ -80,6 +80,9 @@ SIGNATURES = {
     "lb_point_corner_query": (i32, [vp, i64, i64, i32, vp, sz, vp, vp, vp]),
     "lb_voxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, vp]),
     "lb_devoxelize_fwd_ex": (i32, [vp, i32, i64, vp, vp, i64, i64, i32, vp, i32, i64, vp]),
+    "lb_segment_order_ws_bytes": (sz, [i64]),
+    "lb_segment_order": (i32, [vp, i64, vp, i64, vp, vp, vp, sz, vp]),
+    "lb_voxelize_segments": (i32, [vp, i32, i64, vp, vp, i64, i32, vp, i64, vp]),
     "lb_tta_transform": (i32, [vp, i64, C.POINTER(dbl), dbl, vp, vp, vp]),
     "lb_tta_quantize": (i32, [vp, i64, C.POINTER(dbl), i32, i32, vp, vp, vp, vp]),
     "lb_tta_views_ws_bytes": (sz, [i64, i32]),

@@ -11,6 +11,7 @@
 //   lb_region_mean_f32 / lb_region_feat_mean   ReDAL.py:74-79 (and the f32 mean of LiDAL.py:98)
 #include "common.cuh"
 #include "np_sum.cuh"
+#include <type_traits>
 
 namespace lb {
 
@@ -245,6 +246,68 @@ region_feat_mean_kernel(const float* __restrict__ feat, int64_t ld, int c, const
   out[(int64_t)r * c + col] = __fdiv_rn(acc, (float)(e - b));
 }
 
+// ------------------------------------------------------------------------------------------- segmented voxelize (engine)
+// F.spvoxelize (network/utils.py:56) without atomics: the points of every voxel are listed contiguously (segment_order: a
+// counting sort of the point -> voxel index, built once per level from the coordinates alone), then one thread group per
+// voxel adds its points' rows in fp32 and writes the mean in the 16-bit activation type -- no zero fill, no fp32 round trip.
+__global__ void segment_scatter_kernel(const int* __restrict__ idx, int64_t n, int64_t m, const uint32_t* __restrict__ seg_ptr,
+                                       unsigned* __restrict__ cursor, int* __restrict__ order) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = __ldg(&idx[i]);
+    if (v < 0 || v >= m) continue;
+    order[seg_ptr[v] + atomicAdd(&cursor[v], 1u)] = (int)i;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void acc16(float (&a)[8], const uint4 w) {
+  const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+      a[2 * j] += __uint_as_float(wd[j] << 16);
+      a[2 * j + 1] += __uint_as_float(wd[j] & 0xffff0000u);
+    } else {
+      a[2 * j] += __half2float(__ushort_as_half((unsigned short)(wd[j] & 0xffffu)));
+      a[2 * j + 1] += __half2float(__ushort_as_half((unsigned short)(wd[j] >> 16)));
+    }
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+voxelize_segments_kernel(const T* __restrict__ feats, int64_t ld_f, const int* __restrict__ order, const uint32_t* __restrict__ seg_ptr,
+                         int64_t m, int c, T* __restrict__ out, int64_t ld_o) {
+  const int cpr = c >> 3;                                   // 16-byte chunks per row
+  const int64_t total = m * cpr;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / cpr;
+    const int ch = (int)(t - v * cpr);
+    const uint32_t b = seg_ptr[v], e = seg_ptr[v + 1];
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t i = b;
+    for (; i + 2 <= e; i += 2) {                            // two independent gathers in flight
+      const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(&feats[(int64_t)__ldg(&order[i]) * ld_f + ch * 8]));
+      const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(&feats[(int64_t)__ldg(&order[i + 1]) * ld_f + ch * 8]));
+      acc16<T>(a, w0);
+      acc16<T>(a, w1);
+    }
+    if (i < e) acc16<T>(a, __ldg(reinterpret_cast<const uint4*>(&feats[(int64_t)__ldg(&order[i]) * ld_f + ch * 8])));
+    const float r = e > b ? __frcp_rn((float)(e - b)) : 0.f;
+    uint4 o;
+    if (std::is_same<T, __nv_bfloat16>::value) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(a[0] * r, a[1] * r), p1 = __floats2bfloat162_rn(a[2] * r, a[3] * r);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(a[4] * r, a[5] * r), p3 = __floats2bfloat162_rn(a[6] * r, a[7] * r);
+      o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                     *reinterpret_cast<uint32_t*>(&p3));
+    } else {
+      __half2 p0 = __floats2half2_rn(a[0] * r, a[1] * r), p1 = __floats2half2_rn(a[2] * r, a[3] * r);
+      __half2 p2 = __floats2half2_rn(a[4] * r, a[5] * r), p3 = __floats2half2_rn(a[6] * r, a[7] * r);
+      o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                     *reinterpret_cast<uint32_t*>(&p3));
+    }
+    *reinterpret_cast<uint4*>(&out[v * ld_o + ch * 8]) = o;
+  }
+}
+
 }  // namespace lb
 using namespace lb;
 
@@ -344,6 +407,41 @@ extern "C" int lb_region_feat_mean(const float* feat, int64_t ld, int c, const i
   if (n_regions == 0) return LB_OK;
   LB_CHECK_ARG(feat && region_ptr && region_pts && out, "null pointer");
   region_feat_mean_kernel<<<dim3((c + 127) / 128, n_regions), 128, 0, as_stream(stream)>>>(feat, ld, c, region_ptr, region_pts, out); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" size_t lb_segment_order_ws_bytes(int64_t m) {
+  if (m < 1) m = 1;
+  return (((size_t)m * 4 + 255) & ~(size_t)255) + scan_ws_bytes(m) + 512;
+}
+extern "C" int lb_segment_order(const int32_t* idx, int64_t n, const int32_t* counts, int64_t m, int32_t* seg_ptr, int32_t* order,
+                                void* ws, size_t ws_bytes, void* stream) {
+  LB_CHECK_ARG(n >= 0 && m >= 0 && seg_ptr && ws, "bad arguments");
+  if (ws_bytes < lb_segment_order_ws_bytes(m)) { set_error("lb_segment_order: workspace too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  if (m == 0) { LB_CUDA(cudaMemsetAsync(seg_ptr, 0, 4, st)); return LB_OK; }
+  LB_CHECK_ARG(counts && (n == 0 || (idx && order)), "null pointer");
+  unsigned* cursor = (unsigned*)ws;
+  void* sws = (char*)ws + (((size_t)m * 4 + 255) & ~(size_t)255);
+  // seg_ptr[0..m) = exclusive scan of counts, seg_ptr[m] = total
+  int rc = exclusive_scan_u32((const uint32_t*)counts, (uint32_t*)seg_ptr, m, (uint32_t*)seg_ptr + m, sws, st);
+  if (rc != LB_OK) return rc;
+  LB_CUDA(cudaMemsetAsync(cursor, 0, (size_t)m * 4, st));
+  if (n > 0) { segment_scatter_kernel<<<grid_for(n, 256), 256, 0, st>>>(idx, n, m, (const uint32_t*)seg_ptr, cursor, order); LB_LAUNCHED(1); }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_voxelize_segments(const void* feats, int dtype, int64_t ld_feats, const int32_t* order, const int32_t* seg_ptr, int64_t m,
+                                    int c, void* out, int64_t ld_out, void* stream) {
+  LB_CHECK_ARG(m >= 0 && c > 0 && c % 8 == 0 && ld_feats % 8 == 0 && ld_out % 8 == 0 && ld_feats >= c && ld_out >= c, "bad sizes (c, strides % 8)");
+  if (m == 0) return LB_OK;
+  LB_CHECK_ARG(feats && order && seg_ptr && out && ((((uintptr_t)feats) | ((uintptr_t)out)) & 15) == 0, "null or unaligned pointer");
+  cudaStream_t st = as_stream(stream);
+  const int g = grid_for(m * (c / 8), 256, 32);
+  if (dtype == LB_DT_BF16) { voxelize_segments_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)feats, ld_feats, order, (const uint32_t*)seg_ptr, m, c, (__nv_bfloat16*)out, ld_out); LB_LAUNCHED(1); }
+  else if (dtype == LB_DT_F16) { voxelize_segments_kernel<__half><<<g, 256, 0, st>>>((const __half*)feats, ld_feats, order, (const uint32_t*)seg_ptr, m, c, (__half*)out, ld_out); LB_LAUNCHED(1); }
+  else { set_error("lb_voxelize_segments: 16-bit features only"); return LB_EINVAL; }
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -435,14 +435,25 @@ class InferenceEngine:
                                                   L.ptr(w), L.stream()))
         return idx, w
 
-    def _cell_query(self, pts, m, lvl):
+    def _cell_query(self, pts, m, lvl, segments=True):
+        """network/utils.py:42-49 fused: point -> voxel index and its histogram.  ``segments`` (the engine's use) returns the
+        atomic-free form instead: (seg_ptr, order) of lb_segment_order."""
         n = pts.shape[0]
         idx = torch.empty(n, dtype=torch.int, device=pts.device)
         t = m.tables[lvl]
         L.check(L.lib().lb_point_cell_query(L.ptr(pts), pts.stride(0), n, 2 ** lvl, L.ptr(t[0]), t[1], L.ptr(idx), L.stream()))
         counts = torch.empty(m.n[lvl], dtype=torch.int, device=pts.device)
         L.check(L.lib().lb_count(L.ptr(idx), n, L.ptr(counts), m.n[lvl], L.stream()))
-        return idx, counts
+        if not segments:
+            return idx, counts
+        # the points of every voxel, contiguous per voxel: voxelize becomes an atomic-free segmented mean (coordinates only,
+        # so it is built in the prepare phase)
+        seg_ptr = torch.empty(m.n[lvl] + 1, dtype=torch.int, device=pts.device)
+        order = torch.empty(n, dtype=torch.int, device=pts.device)
+        nb = L.lib().lb_segment_order_ws_bytes(m.n[lvl])
+        ws = torch.empty(nb, dtype=torch.uint8, device=pts.device)
+        L.check(L.lib().lb_segment_order(L.ptr(idx), n, L.ptr(counts), m.n[lvl], L.ptr(seg_ptr), L.ptr(order), L.ptr(ws), nb, L.stream()))
+        return seg_ptr, order
 
     def _devox(self, x, idx, w, out_dtype=None):
         n, c = idx.shape[0], x.shape[1]
@@ -460,6 +471,15 @@ class InferenceEngine:
             L.check(L.lib().lb_voxelize_fwd_ex(L.ptr(f), L.DT_OF[f.dtype], f.stride(0), L.ptr(idx), L.ptr(counts), f.shape[0],
                                                m_rows, f.shape[1], L.ptr(acc), L.stream()))
         return acc
+
+    def _vox_seg(self, f, seg_ptr, order, m_rows):
+        """point_to_voxel (network/utils.py:38-61) as a segmented mean: 16-bit in, 16-bit out, no atomics."""
+        out = _alloc(m_rows, f.shape[1], f.dtype, f.device)
+        # SURVEY 8d: voxelize = (Np + Nv) * C * e + 4 * Np
+        with _stage("voxelize", (f.shape[0] + m_rows) * f.shape[1] * f.element_size() + 4 * f.shape[0]):
+            L.check(L.lib().lb_voxelize_segments(L.ptr(f), L.DT_OF[f.dtype], f.stride(0), L.ptr(order), L.ptr(seg_ptr), m_rows, f.shape[1],
+                                                 L.ptr(out), out.stride(0), L.stream()))
+        return out
 
     def _initial_voxelize(self, coords, feats):
         """network/utils.py:13-33: voxels = unique hashes of the floored point coordinates (the reference orders them by
@@ -492,16 +512,16 @@ class InferenceEngine:
         cats = self._cat_buffers(m)
         x0 = self._stem(self._pad8(vfeats), m, cats[3])
         z0 = self._devox(x0, iq0, w0)                                            # [Np, 32]
-        x = self._cast(self._vox(z0, ci0, cn0, m.n[0]), self.dtype)
+        x = self._vox_seg(z0, ci0, cn0, m.n[0])
         for lvl in range(1, 5):
             skip_out = cats[3 - lvl][:, self.up[3 - lvl].cout:] if lvl < 4 else None
             x = self._encode(x, m, lvl, out=skip_out)
         z1 = self.mlp[0](z0, None, z0.shape[0], residual=self._devox(x, iq4, w4), relu_first=True)   # [Np, 256]
-        y = self._cast(self._vox(z1, ci4, cn4, m.n[4]), self.dtype)              # dropout: identity in eval
+        y = self._vox_seg(z1, ci4, cn4, m.n[4])                                  # dropout: identity in eval
         y = self._decode(y, m, 1, cats[0])
         y = self._decode(y, m, 2, cats[1])
         z2 = self.mlp[1](z1, None, z1.shape[0], residual=self._devox(y, iq2, w2), relu_first=True)   # [Np, 128]
-        y = self._cast(self._vox(z2, ci2, cn2, m.n[2]), self.dtype)
+        y = self._vox_seg(z2, ci2, cn2, m.n[2])
         y = self._decode(y, m, 3, cats[2])
         y = self._decode(y, m, 4, cats[3])
         z3 = self.mlp[2](z2, None, z2.shape[0], residual=self._devox(y, iq0, w0), relu_first=True)   # [Np, 96]

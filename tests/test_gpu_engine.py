@@ -92,7 +92,7 @@ def test_unique_and_point_queries_vs_oracle(oracle_ts, small_scan):
         want_w = Fo.calc_ti_weights(pts, want_idx, scale=s)
         assert torch.equal(idx.cpu().long(), want_idx.t())
         torch.testing.assert_close(w.cpu(), want_w.t().contiguous(), rtol=1e-5, atol=1e-7)
-        ci, cn = InferenceEngine._cell_query(eng, pts.cuda(), m, lvl)
+        ci, cn = InferenceEngine._cell_query(eng, pts.cuda(), m, lvl, segments=False)
         want_ci = Fo.sphashquery(Fo.sphash(cell), Fo.sphash(vox))
         assert torch.equal(ci.cpu().long(), want_ci)
         assert torch.equal(cn.cpu(), Fo.spcount(want_ci.int(), vox.shape[0]))

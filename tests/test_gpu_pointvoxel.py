@@ -89,3 +89,37 @@ def test_gpu_voxelizer_matches_reference_transform():
     assert np.array_equal(got_c.cpu().numpy(), want_c)
     assert np.array_equal(got_inv.cpu().numpy(), want_inv)
     np.testing.assert_allclose(got_f.cpu().numpy(), want_f, rtol=2e-7, atol=1e-6)
+
+
+def test_segmented_voxelize_matches_scatter_mean():
+    """lb_segment_order + lb_voxelize_segments (engine: atomic-free point_to_voxel) == the scatter-mean of F.spvoxelize on the
+    same 16-bit features: unmatched points (-1) are skipped, empty voxels stay zero, the order list is a partition."""
+    from lidal_b200 import _lib as L
+    g = torch.Generator().manual_seed(3)
+    n, m = 50_000, 4_000
+    for c in (32, 128, 256):
+        idx = torch.randint(-1, m, (n,), generator=g).int()
+        idx[idx == 7] = -1                                       # voxel 7 stays empty
+        feats = torch.randn(n, c + 8, generator=g).bfloat16()[:, :c]           # strided rows
+        idx_d, feats_d = idx.cuda(), feats.cuda()
+        counts = torch.empty(m, dtype=torch.int, device="cuda")
+        L.check(L.lib().lb_count(L.ptr(idx_d), n, L.ptr(counts), m, L.stream()))
+        seg = torch.empty(m + 1, dtype=torch.int, device="cuda")
+        order = torch.full((n,), -7, dtype=torch.int, device="cuda")
+        nb = L.lib().lb_segment_order_ws_bytes(m)
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        L.check(L.lib().lb_segment_order(L.ptr(idx_d), n, L.ptr(counts), m, L.ptr(seg), L.ptr(order), L.ptr(ws), nb, L.stream()))
+        seg_h, order_h = seg.cpu().numpy(), order.cpu().numpy()
+        total = int(seg_h[-1])
+        assert total == int((idx >= 0).sum()) and np.array_equal(np.diff(seg_h), counts.cpu().numpy())
+        assert np.array_equal(np.sort(order_h[:total]), np.nonzero((idx >= 0).numpy())[0])
+        assert np.array_equal(idx.numpy()[order_h[:total]], np.repeat(np.arange(m), np.diff(seg_h)))
+        out = torch.empty((m, c), dtype=torch.bfloat16, device="cuda")
+        L.check(L.lib().lb_voxelize_segments(L.ptr(feats_d), L.LB_DT_BF16, feats_d.stride(0), L.ptr(order), L.ptr(seg), m, c, L.ptr(out),
+                                             c, L.stream()))
+        want = torch.zeros(m, c, dtype=torch.float64)
+        sel = idx >= 0
+        want.index_add_(0, idx[sel].long(), feats[sel].double())
+        want = want / counts.cpu().double().clamp_min(1)[:, None]
+        torch.testing.assert_close(out.cpu().double(), want, rtol=1e-2, atol=1e-2)
+        assert float(out[7].abs().max()) == 0.0
