@@ -1038,7 +1038,11 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.staged = 0;
   p.stg_bufs = 1;
   size_t budget_eff = budget;
-  if (a.out_dtype != LB_DT_F32 && !(a.flags & LB_CONV_NO_STAGED_EPILOGUE) && budget > staging_bytes(a.c_out) &&
+  // permuted rows leave the staged epilogue as ONE bulk copy per row and lane (32 serialised UBLKCP per warp and sub-tile):
+  // for narrow outputs that costs more than the handful of direct 16-byte stores it replaces (A/B: LIDAL_STAGED_MIN_COUT)
+  static const int staged_min_cout = getenv("LIDAL_STAGED_MIN_COUT") ? atoi(getenv("LIDAL_STAGED_MIN_COUT")) : 64;
+  const bool narrow_permuted = a.out_rows && a.c_out < staged_min_cout;
+  if (a.out_dtype != LB_DT_F32 && !(a.flags & LB_CONV_NO_STAGED_EPILOGUE) && !narrow_permuted && budget > staging_bytes(a.c_out) &&
       (budget - staging_bytes(a.c_out)) / stage_bytes >= (size_t)want_stages) {
     p.staged = 1;
     // short K loops (1x1 layers) are pure epilogue: a second staging buffer per warp lets the copy engine drain one

@@ -562,8 +562,10 @@ class StreamPipeline:
     busy with forward(i): map construction and its synchronisation bubbles hide behind the convolutions."""
 
     def __init__(self, engine: "InferenceEngine"):
+        import collections
         self.engine = engine
         self.prep_stream = torch.cuda.Stream(device=engine.device)
+        self._live = collections.deque()
 
     def prepare(self, coords, feats, after=None, wait_main=True) -> Prepared:
         """``after``: event that makes the inputs valid (e.g. their H2D copy); else ``wait_main`` orders the side stream behind
@@ -578,14 +580,24 @@ class StreamPipeline:
             pr = self.engine.prepare(coords, feats)
             pr.ready = torch.cuda.Event()
             pr.ready.record(self.prep_stream)
-        for t in pr.tensors():                              # allocated on the side stream, consumed on the caller's stream
-            t.record_stream(main)
         return pr
+
+    def retire(self, *objects):
+        """Keep ``objects`` (tensors allocated on the side stream but read by kernels queued on the caller's stream) alive until
+        that queued work has finished, then let them go.  Holding references -- instead of ``Tensor.record_stream`` -- keeps
+        the caching allocator's per-stream pools in steady state: nothing is ever deferred, nothing forces a fresh cudaMalloc."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.engine.device))
+        self._live.append((objects, ev))
+        while self._live and self._live[0][1].query():
+            self._live.popleft()
 
     def submit(self, coords, feats, return_feat=False, after=None, wait_main=True):
         pr = self.prepare(coords, feats, after, wait_main)
         torch.cuda.current_stream(self.engine.device).wait_event(pr.ready)
-        return self.engine.forward(pr, return_feat)
+        out = self.engine.forward(pr, return_feat)
+        self.retire(pr)
+        return out
 
 
 class HostPipeline:

@@ -199,11 +199,10 @@ def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: i
             xyz = score.register_points(raw_dev, pose)
             coords, feats, inverse = voxelizer.tta_batch_gpu(raw_dev, seed=seed + fid, inf_reps=inf_reps)
         pr = sp.prepare(coords, feats, wait_main=False)
-        for x in (raw_dev, xyz, coords, feats, inverse):
-            x.record_stream(main)
         main.wait_event(pr.ready)
         prob, _pred = score.tta_tail(engine.forward(pr), inverse, inf_reps)
         scorer.add_frame(xyz, prob, sv_id, regions, fid=fid)
+        sp.retire(pr, raw_dev, coords, feats, inverse)          # side-stream allocations stay alive until this frame's kernels are done
     t[1].record()
     # ---- halo: neighbour-window frames owned by other ranks
     if world > 1:
