@@ -28,7 +28,11 @@ namespace lb {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_EPI_THREADS = 128;
-constexpr int NUM_PROD_THREADS = 256;   // 8 gather warps: two per scheduler, so dependent address/LDS/cp.async chains overlap
+#ifndef LIDAL_PROD_WARPS
+#define LIDAL_PROD_WARPS 8
+#endif
+constexpr int NUM_PROD_THREADS = 32 * LIDAL_PROD_WARPS;   // 8 gather warps: two per scheduler, so dependent address/LDS/cp.async chains overlap
+static_assert(LIDAL_PROD_WARPS == 8 || LIDAL_PROD_WARPS == 16, "the thread -> row mapping of the gather warps assumes 8 or 16 warps");
 constexpr int NUM_THREADS = NUM_EPI_THREADS + NUM_PROD_THREADS + 64;
 constexpr int MMA_WARP = (NUM_EPI_THREADS + NUM_PROD_THREADS) / 32;
 constexpr int WEIGHT_WARP = MMA_WARP + 1;   // issues the TMA weight-tile loads (and arms the stage barriers) so that the gather
@@ -1088,7 +1092,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   // a neighbour table (k_vol > 1 or permuted rows) and row indices that fit the tensor map's int32 coordinates
   if (!pack8 && tma_gather_env && a.nbr && a.in_pad_rows >= 16 && (a.in_pad_rows & (a.in_pad_rows - 1)) == 0 &&
       a.n_in + a.in_pad_rows < ((int64_t)1 << 31) && ((uintptr_t)a.in & 15) == 0 && (a.ld_in * 2) % 16 == 0 &&
-      (tma_gather_env >= 2 || bk == 64)) {
+      (tma_gather_env >= 2 || bk == 64) && LIDAL_PROD_WARPS == 8) {
     cuuint64_t idim[2] = {(cuuint64_t)a.c_in, (cuuint64_t)(a.n_in + a.in_pad_rows)};
     cuuint64_t istr[1] = {(cuuint64_t)a.ld_in * 2};
     cuuint32_t ibox[2] = {(cuuint32_t)bk, 1};

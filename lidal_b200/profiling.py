@@ -79,10 +79,12 @@ def conv_roofline(run, resident, steps=3):
     achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     best = max(tc, key=lambda r: r["flops"] / max(r["ms"], 1e-6)) if tc else None
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    if os.path.exists(tpath):          # dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed ncu pass
-        tj = json.load(open(tpath))
-        traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_conv_traffic.json (ncu, per launch)"
+    for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):       # dram__bytes_read.sum + dram__bytes_write.sum per launch
+        tpath = os.path.join(ROOT, "profiles", name)                        # from a committed ncu pass of the bench command
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], f"profiles/{name} (ncu, per launch)"
+            break
     alg_bytes = sum(2.0 * (r["n_out"] * r["cin"] + r["n_out"] * r["cout"]) + 4.0 * r["k"] * r["n_out"] + 2.0 * r["k"] * r["cin"] * r["cout"]
                     for r in tc) / max(len(tc), 1)
     if os.environ.get("LIDAL_LAYER_TABLE"):
