@@ -201,8 +201,16 @@ def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: i
         pr = sp.prepare(coords, feats, wait_main=False)
         main.wait_event(pr.ready)
         prob, _pred = score.tta_tail(engine.forward(pr), inverse, inf_reps)
-        scorer.add_frame(xyz, prob, sv_id, regions, fid=fid)
+        fr = scorer.add_frame(xyz, prob, sv_id, regions, fid=fid)
         sp.retire(pr, raw_dev, coords, feats, inverse)          # side-stream allocations stay alive until this frame's kernels are done
+        if fid == own[0] and len(own) > 8:
+            # The resident set grows by ~20 MB per frame (prob map, coordinates, hash grid).  Taking it from the driver one
+            # cudaMalloc at a time would stall the pipeline every few frames (cudaMalloc synchronises), so the caching
+            # allocator is primed once with the whole sequence's worth and hands out pieces of it afterwards.
+            per_frame = xyz.numel() * 8 + prob.numel() * 4 + fr.grid.numel() + 2 * (1 << 20)
+            with torch.cuda.stream(main):
+                reserve = torch.empty(int(per_frame * (len(own) + 2 * nei_num) * 1.05), dtype=torch.uint8, device=dev)
+                del reserve
     t[1].record()
     # ---- halo: neighbour-window frames owned by other ranks
     if world > 1:

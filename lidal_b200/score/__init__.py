@@ -375,7 +375,9 @@ class _CsrIndex:
 
     def near(self, sv):
         m = self.members
-        return [j for j in self.nbr_idx[self.row_ptr[sv]:self.row_ptr[sv + 1]] if j in m]
+        if not m:
+            return []
+        return [j for j in self.nbr_idx[self.row_ptr[sv]:self.row_ptr[sv + 1]].tolist() if j in m]
 
     def add(self, sv):
         self.members.add(sv)
@@ -448,7 +450,7 @@ def select_regions(sv_flags, sv_interds, sv_interes, sv_pnums, sv_centers, train
                                         L.ptr(_ws(nbytes, dev)), nbytes, L.stream()))
         if method == "csr" or int(counts.sum(dtype=torch.int64).item()) <= CSR_MAX_PAIRS:
             row_ptr, nbr_idx = region_pairs(c_dev, sv_dis_thresh)
-            csr = (row_ptr.cpu().tolist(), nbr_idx.cpu().tolist())
+            csr = (row_ptr.cpu().tolist(), nbr_idx.cpu().numpy())          # lists of a region are converted on demand
     cells = None if csr is not None else region_cells(centers, sv_dis_thresh)
 
     def new_index():

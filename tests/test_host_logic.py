@@ -18,7 +18,7 @@ def _cpu_pairs(centers, radius):
         near = np.where((d < radius) & (np.arange(len(centers)) != i))[0]
         rows.append(near)
         ptr.append(ptr[-1] + len(near))
-    return ptr, np.concatenate(rows).tolist()
+    return ptr, np.concatenate(rows)
 
 
 def _walk_both_passes(flags, d, e, pn, c, tpn, argsort, index="grid"):
