@@ -45,14 +45,55 @@ def make_batches(rank: int, n_sets: int = N_INPUT_SETS, batch: int = BATCH, kind
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons / power of one GPU sampled during the timed region.  In-process NVML (pynvml) on a
+    thread, initialised when the object is built -- i.e. before warm-up, so that no NVML start-up (which attaches to every
+    GPU of the box and, with one sampler per rank, stalled the other ranks' launches at N = 8) lands inside the timed
+    region; `nvidia-smi -lms` as a subprocess only when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.path = index, None, None
+    def __init__(self, index: int, period_s: float = 0.05):
+        self.index, self.proc, self.path, self.period = index, None, None, period_s
+        self.rows, self.thread, self.stop, self.nvml, self.handle, self.max_mhz = [], None, None, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self._sample()                       # first call pays NVML's lazy set-up here, not in the timed region
+            self.rows.clear()
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n, h = self.nvml, self.handle
+        try:
+            reasons = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.rows.append((float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), float(n.nvmlDeviceGetPowerUsage(h)) / 1e3, int(reasons)))
+
+    def _loop(self):
+        while not self.stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self.stop.wait(self.period)
 
     def __enter__(self):
+        if self.nvml is not None:
+            import threading
+            self.stop = threading.Event()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return self
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -64,6 +105,13 @@ class ClockSampler:
         return self
 
     def __exit__(self, *exc):
+        if self.thread is not None:
+            try:
+                self._sample()                   # at least one sample taken under load even for a very short region
+            except Exception:
+                pass
+            self.stop.set()
+            self.thread.join(timeout=2)
         if self.proc:
             time.sleep(0.25)
             self.proc.terminate()
@@ -74,11 +122,18 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.nvml is not None:
+            rows = list(self.rows)
+            if rows:
+                out.update(sm_mhz=statistics.median(r[0] for r in rows), sm_max_mhz=self.max_mhz, samples=len(rows),
+                           power_w_max=max(r[1] for r in rows), source="nvml")
+                out["reasons"] = [name for name, bit in self.REASONS.items() if any(r[2] & bit for r in rows)]
+            return out
         try:
             rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
             sm = [float(r[1]) for r in rows]
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=float(rows[0][2]), samples=len(rows),
-                       power_w_max=max(float(r[3]) for r in rows))
+                       power_w_max=max(float(r[3]) for r in rows), source="nvidia-smi")
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
             for j, n in enumerate(names):
                 if any(r[5 + j].strip().lower().startswith("active") for r in rows):
@@ -206,6 +261,7 @@ def run_lidal(eng, dev, rank, world, n_frames, kind, n_cls, barrier, seed=11):
         "timing": "CUDA events over inference + halo + scoring + all_gather, plus host time of the selection; max over ranks",
         "phases_ms_max_over_ranks": {"prob_inference": total[2], "halo_exchange": total[3], "interframe_scoring": total[4],
                                      "region_all_gather": total[5], "selection": total[6]},
+        "selection_parts_ms_rank0": {k: tm[k] for k in ("select_pairs_ms", "select_sort_ms", "select_walk_ms", "select_path") if k in tm},
         "collective": {"halo_ms": total[3], "halo_bytes_received_rank0": tm.get("halo_bytes_received", 0),
                        "halo_frames_received_rank0": tm.get("halo_frames_received", 0), "all_gather_ms": tm.get("all_gather_ms", 0.0),
                        "all_gather_bytes_per_rank": tm.get("all_gather_bytes_per_rank", 0)},
@@ -246,12 +302,13 @@ def run_train(args, dev, rank, world, local_rank, barrier):
         opt.step()
         return loss
 
+    clk = ClockSampler(local_rank)               # NVML attached before warm-up
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.lib().lb_launch_count()
-    with ClockSampler(local_rank) as clk:
+    with clk:
         barrier()
         e0.record()
         for i in range(args.steps):
@@ -363,6 +420,7 @@ def main():
         from lidal_b200.engine import StreamPipeline
         stream_pipe = StreamPipeline(eng)        # maps of batch i+1 are built on a side stream while batch i's network runs
     step = (lambda c, f: stream_pipe.submit(c, f, wait_main=False)) if stream_pipe is not None else run   # resident inputs: complete
+    clk = ClockSampler(local_rank)               # NVML attached before warm-up
     for i in range(args.warmup):
         step(*resident[i % len(resident)])
     barrier()
@@ -370,7 +428,7 @@ def main():
     # ---- value: inputs resident in HBM
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.lib().lb_launch_count()
-    with ClockSampler(local_rank) as clk:
+    with clk:
         barrier()
         e0.record()
         for i in range(args.steps):

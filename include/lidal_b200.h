@@ -343,6 +343,21 @@ size_t lb_region_pairs_ws_bytes(int64_t n);
 int lb_region_pairs(const float* centers, int64_t n, float radius, int32_t* row, int32_t* nbr_idx, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* HOST function (no device work): the greedy walk of LiDAL.py:242-270 (labelled pass) / :293-325 (pseudo-label pass)
+ * over the regions in `visit` order (int64 region ids, already sorted by the caller: descending divergence for the first
+ * pass, ascending for the second).  interds / interes double [n_regions] (the float32 region means widened exactly),
+ * pnums int64 [n_regions]; row_ptr int64 [n_regions+1] + nbr_idx int32: the in-range lists of lb_region_pairs (host
+ * copies); flags int64 [n_regions] in/out.  A candidate with an accepted region within range swaps with it when its
+ * entropy is better (prefer_higher_entropy: LiDAL.py:254, otherwise :306); when several accepted regions are in range the
+ * reference takes the first one in the iteration order of a CPython set -- replayed slot-exactly (set_last_dummy selects
+ * the dummy-reuse rule of the interpreter version; the Python host verifies the model against its own `set` first).
+ * point_limit = round(0.01 * train_point_num) (LiDAL.py:240); skip_zero: LiDAL.py:296.  n_added_out (optional) = regions
+ * accepted at the end. */
+int lb_select_walk(const int64_t* visit, int64_t n_visit, const double* interds, const double* interes,
+                   const int64_t* pnums, const int64_t* row_ptr, const int32_t* nbr_idx, int64_t n_regions,
+                   int64_t* flags, int64_t flag_value, int64_t point_limit, int prefer_higher_entropy, int skip_zero,
+                   int set_last_dummy, int64_t* n_added_out);
+
 /* Frame-level baselines on the same prob maps (score/frame_level/softmax_entropy.py:34,
  * margin_sampling.py:33-34, least_confidence_sampling.py): out3 (device double[3]) = mean entropy(prob), mean
  * (top1 - top2), mean top1 over the n points of one frame. */

@@ -106,6 +106,7 @@ SIGNATURES = {
     "lb_argsort_f32": (i32, [vp, i64, vp, vp, sz, vp]),
     "lb_region_pairs_ws_bytes": (sz, [i64]),
     "lb_region_pairs": (i32, [vp, i64, flt, vp, vp, vp, sz, vp]),
+    "lb_select_walk": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, i64, i64, i32, i32, i32, vp]),
 }
 
 _lib = None

@@ -241,7 +241,7 @@ def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: i
     flags = None
     if select_with is not None:
         h0 = time.perf_counter()
-        flags = score.select_regions(select_with[0], out[0], out[1], out[2], out[3], select_with[1], device=dev)
+        flags = score.select_regions(select_with[0], out[0], out[1], out[2], out[3], select_with[1], device=dev, timings=timings)
         timings["selection_ms"] = (time.perf_counter() - h0) * 1e3
     if keep_scorer:
         timings["scorer"] = scorer

@@ -6,7 +6,8 @@
                                  the file lists may be the reference's .npy / .pickle paths (read once, then
                                  resident in HBM) or in-memory arrays.
 ``select_regions``               score/sv_level/LiDAL.py:230-325: device radix sort + device 5 m neighbour lists,
-                                 host replay of the greedy walk with a real CPython ``set`` (bit-exact ids).
+                                 native host replay of the greedy walk (``lb_select_walk``) with the iteration order
+                                 of a CPython ``set`` modelled slot-exactly and checked against the interpreter (bit-exact ids).
 """
 from __future__ import annotations
 
@@ -308,9 +309,9 @@ def argsort_f32(keys: torch.Tensor) -> torch.Tensor:
     return order
 
 
-def region_pairs(centers: torch.Tensor, radius: float):
-    """CSR (row_ptr int64 [n+1], idx int32 [nnz]) of regions with float32 distance < radius (LiDAL.py:252-254).  Kept as a
-    device utility (all-pairs lists); ``select_regions`` no longer needs it -- it indexes only the regions added so far."""
+def region_pairs(centers: torch.Tensor, radius: float, max_pairs=None):
+    """CSR (row_ptr int64 [n+1], idx int32 [nnz]) of regions with float32 distance < radius (LiDAL.py:252-254): a hash grid
+    over all centres, counted and filled on device.  Returns None when the lists would exceed ``max_pairs``."""
     L.require_cuda(centers)
     centers = centers.contiguous().float()
     n = centers.shape[0]
@@ -321,6 +322,8 @@ def region_pairs(centers: torch.Tensor, radius: float):
     row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=centers.device)
     row_ptr[1:] = torch.cumsum(counts, 0)
     nnz = int(row_ptr[-1].item())
+    if max_pairs is not None and nnz > max_pairs:
+        return None
     if nnz >= 2 ** 31:
         raise L.LidalError(f"region_pairs: {nnz} pairs exceed the int32 offsets of lb_region_pairs; build the lists in chunks")
     offs = row_ptr[:-1].to(torch.int32).contiguous()
@@ -370,14 +373,20 @@ class _GridIndex:
 class _CsrIndex:
     """All in-range pairs precomputed on device (``region_pairs``): a candidate's lookups are set-membership tests only."""
 
+    EAGER_PAIRS = 1 << 22            # up to here the whole pair array becomes one Python list up front (slicing it is cheaper
+                                     # than a numpy slice + tolist per candidate); above, rows are converted on demand
+
     def __init__(self, row_ptr, nbr_idx):
-        self.row_ptr, self.nbr_idx, self.members = row_ptr, nbr_idx, set()
+        self.row_ptr, self.members = row_ptr, set()
+        self.eager = len(nbr_idx) <= self.EAGER_PAIRS
+        self.nbr_idx = nbr_idx.tolist() if self.eager and not isinstance(nbr_idx, list) else nbr_idx
 
     def near(self, sv):
         m = self.members
         if not m:
             return []
-        return [j for j in self.nbr_idx[self.row_ptr[sv]:self.row_ptr[sv + 1]].tolist() if j in m]
+        row = self.nbr_idx[self.row_ptr[sv]:self.row_ptr[sv + 1]]
+        return list(m.intersection(row if self.eager else row.tolist()))
 
     def add(self, sv):
         self.members.add(sv)
@@ -386,13 +395,128 @@ class _CsrIndex:
         self.members.discard(sv)
 
 
+class _SetOrder:
+    """Slot positions of a CPython ``set`` of small non-negative ints, replayed operation by operation (open addressing,
+    9 linear probes, perturb shift 5, growth at fill*5 >= mask*3 to the first power of two above used*4 -- Objects/setobject.c).
+    The reference's greedy walk stops at the FIRST in-range member in the set's iteration order (LiDAL.py:246-252); with
+    the slots known that member is ``min(near, key=slot)`` instead of a scan over every added region.  The model is
+    verified against the running interpreter's own ``set`` before it is trusted (``_set_model``)."""
+
+    __slots__ = ("keys", "mask", "fill", "used", "slot", "last_dummy")
+
+    def __init__(self, last_dummy=True):
+        self.keys, self.mask, self.fill, self.used, self.slot, self.last_dummy = [None] * 8, 7, 0, 0, {}, last_dummy
+
+    def add(self, key):
+        keys, mask = self.keys, self.mask
+        i, perturb, free = key & mask, key, -1
+        while True:
+            for j in range(i, i + 10 if i + 9 <= mask else i + 1):
+                k = keys[j]
+                if k is None:
+                    if free >= 0:
+                        j = free
+                    else:
+                        self.fill += 1
+                    keys[j] = key
+                    self.slot[key] = j
+                    self.used += 1
+                    if free < 0 and self.fill * 5 >= mask * 3:
+                        self._resize(self.used * 2 if self.used > 50000 else self.used * 4)
+                    return
+                if k == key:
+                    return
+                if k == -1 and (self.last_dummy or free < 0):
+                    free = j
+            perturb >>= 5
+            i = (i * 5 + 1 + perturb) & mask
+
+    def remove(self, key):
+        self.keys[self.slot.pop(key)] = -1       # dummy entry: still counted in fill, reusable by a later insertion
+        self.used -= 1
+
+    def _resize(self, minused):
+        size = 8
+        while size <= minused:
+            size <<= 1
+        mask, new, slot = size - 1, [None] * size, self.slot
+        for key in self.keys:                      # old table order, clean insertion (no dummies in the new table)
+            if key is None or key == -1:
+                continue
+            i, perturb = key & mask, key
+            while True:
+                if new[i] is None:
+                    break
+                if i + 9 <= mask:
+                    for j in range(i + 1, i + 10):
+                        if new[j] is None:
+                            break
+                    else:
+                        j = -1
+                    if j >= 0:
+                        i = j
+                        break
+                perturb >>= 5
+                i = (i * 5 + 1 + perturb) & mask
+            new[i] = key
+            slot[key] = i
+        self.keys, self.mask, self.fill = new, mask, self.used
+
+    def __iter__(self):
+        return (k for k in self.keys if k is not None and k != -1)
+
+    def __len__(self):
+        return self.used
+
+
+_SET_MODEL = []
+
+
+def _set_model():
+    """The ``_SetOrder`` variant whose iteration order equals the running interpreter's ``set`` on a randomised add /
+    remove sequence crossing several resizes (cached); None when neither does -- the walk then scans a real set."""
+    if not _SET_MODEL:
+        rng = np.random.RandomState(12345)
+        found = None
+        for last_dummy in (True, False):
+            ok = True
+            for trial in range(3):
+                real, model, members = set(), _SetOrder(last_dummy), []
+                for step in range(6000):
+                    if members and rng.rand() < 0.35:
+                        key = members.pop(rng.randint(len(members)))
+                        real.remove(key)
+                        model.remove(key)
+                    else:
+                        key = int(rng.randint(0, 40000 * (trial + 1)))
+                        if key not in real:
+                            members.append(key)
+                        real.add(key)
+                        model.add(key)
+                    if step % 500 == 499 and list(real) != list(model):
+                        ok = False
+                        break
+                if not ok or list(real) != list(model):
+                    ok = False
+                    break
+            if ok:
+                found = last_dummy
+                break
+        _SET_MODEL.append(found)
+    return _SET_MODEL[0]
+
+
 def _greedy_walk(order, cand_ids, interds, interes, pnums, index, flags, flag_value, point_limit, prefer_higher_entropy, skip_zero):
     """Host replay of LiDAL.py:242-270 / 293-325.  The reference scans a CPython ``set`` of the regions added so far and
     stops at the FIRST member within 5 m; which member that is depends on the set's iteration order, so the same add /
-    remove sequence is fed to a real ``set`` and its order is consulted only when two or more members are in range.
+    remove sequence is fed to a slot-exact model of the interpreter's ``set`` (``_SetOrder``, checked against the real one;
+    a real ``set`` is scanned if the check fails) and its order is consulted only when two or more members are in range.
     ``index`` answers "which added regions lie within 5 m of this candidate" (_GridIndex or _CsrIndex)."""
-    added = set()
+    model = _set_model()
+    added = set() if model is None else _SetOrder(model)
+    slot_of = None if model is None else added.slot.__getitem__
     cand_list = cand_ids.tolist()
+    interds, interes, pnums = np.asarray(interds).tolist(), np.asarray(interes).tolist(), np.asarray(pnums).tolist()   # exact
     for idx in order.tolist():
         sv = cand_list[idx]                                  # hash(int) == hash(np.int64): same set order as the reference
         if skip_zero and interds[sv] == 0:
@@ -401,8 +525,10 @@ def _greedy_walk(order, cand_ids, interds, interes, pnums, index, flags, flag_va
         if near:
             hit = near[0]
             if len(near) > 1:
-                inrange = set(near)
-                hit = next(m for m in added if m in inrange)
+                if slot_of is not None:
+                    hit = min(near, key=slot_of)             # first in-range member in the set's iteration order
+                else:
+                    hit = next(filter(set(near).__contains__, added))
             better = interes[hit] < interes[sv] if prefer_higher_entropy else interes[hit] > interes[sv]
             if better:
                 flags[sv] = flag_value
@@ -422,53 +548,90 @@ def _greedy_walk(order, cand_ids, interds, interes, pnums, index, flags, flag_va
     return flags
 
 
+def native_walk(visit, interds, interes, pnums, row_ptr, nbr_idx, flags, flag_value, point_limit, prefer_higher_entropy,
+                skip_zero, last_dummy=True):
+    """``lb_select_walk`` on host arrays: the same walk as ``_greedy_walk`` over CSR neighbour lists; ``flags`` (int numpy
+    array) is updated in place.  ``visit``: region ids in visiting order."""
+    as_p = lambda a: a.ctypes.data_as(C.c_void_p)            # noqa: E731
+    keep = [np.ascontiguousarray(visit, dtype=np.int64), np.ascontiguousarray(interds, dtype=np.float64),
+            np.ascontiguousarray(interes, dtype=np.float64), np.ascontiguousarray(pnums, dtype=np.int64),
+            np.ascontiguousarray(row_ptr, dtype=np.int64), np.ascontiguousarray(nbr_idx, dtype=np.int32),
+            np.ascontiguousarray(flags, dtype=np.int64)]
+    n_added = C.c_int64(0)
+    L.check(L.lib().lb_select_walk(as_p(keep[0]), keep[0].size, as_p(keep[1]), as_p(keep[2]), as_p(keep[3]), as_p(keep[4]),
+                                   as_p(keep[5]), flags.size, as_p(keep[6]), int(flag_value), int(point_limit),
+                                   int(bool(prefer_higher_entropy)), int(bool(skip_zero)), int(bool(last_dummy)), C.byref(n_added)))
+    flags[:] = keep[6]
+    return int(n_added.value)
+
+
 CSR_MAX_PAIRS = 1 << 27          # above this the all-pairs lists are not built (memory); the grid index is used instead
 
 
 def select_regions(sv_flags, sv_interds, sv_interes, sv_pnums, sv_centers, train_point_num, sv_dis_thresh=5.0,
-                   device="cuda", method="auto"):
+                   device="cuda", method="auto", timings=None):
     """LiDAL.py:230-325.  Inputs are the global per-region arrays (numpy); returns int flags (0 / 1 labelled / 2 pseudo).
 
     The two sorts run on device (radix argsort of the unlabelled regions' divergence, LiDAL.py:235,283) and so does the
     5 m neighbourhood search (``region_pairs``, a hash grid over all centres) unless the pair lists would be too large
-    (``method="grid"``: only the added regions are indexed, on the host).  The greedy walk is inherently sequential and
-    is replayed on the host.  Ties: the reference's ``np.argsort`` is an unstable introsort, so the visiting order of EQUAL
-    keys is only defined by numpy itself -- when the device sort sees equal keys it falls back to ``np.argsort`` for
-    that pass, so the selected ids stay identical to the reference's in every case."""
+    (``method="grid"``: only the added regions are indexed, on the host).  The greedy walk is inherently sequential: it
+    runs on the host, natively (``lb_select_walk``) over the device-built lists when the set-order model matches the
+    interpreter (``method="auto"``/``"native"``), else as the Python replay (``"csr"``/``"grid"``).  Ties: the reference's
+    ``np.argsort`` is an unstable introsort, so the visiting order of EQUAL keys is only defined by numpy itself -- when
+    the device sort sees equal keys it falls back to ``np.argsort`` for that pass, so the selected ids stay identical to
+    the reference's in every case.  ``timings`` (dict, optional) receives the host milliseconds of each part."""
+    import time as _time
     dev = torch.device(device)
+    t0 = _time.perf_counter()
     flags = np.asarray(sv_flags).astype(int)
     interds, interes = np.asarray(sv_interds), np.asarray(sv_interes)
     pnums = np.asarray(sv_pnums)
     centers = np.ascontiguousarray(np.asarray(sv_centers, np.float32))
     d_dev = torch.as_tensor(np.asarray(sv_interds, np.float32)).to(dev)
-    csr = None
-    if method in ("auto", "csr"):
-        c_dev = torch.from_numpy(centers).to(dev)
-        counts = torch.zeros(centers.shape[0], dtype=torch.int32, device=dev)
-        nbytes = L.lib().lb_region_pairs_ws_bytes(centers.shape[0])
-        L.check(L.lib().lb_region_pairs(L.ptr(c_dev), centers.shape[0], float(sv_dis_thresh), L.ptr(counts), None,
-                                        L.ptr(_ws(nbytes, dev)), nbytes, L.stream()))
-        if method == "csr" or int(counts.sum(dtype=torch.int64).item()) <= CSR_MAX_PAIRS:
-            row_ptr, nbr_idx = region_pairs(c_dev, sv_dis_thresh)
-            csr = (row_ptr.cpu().tolist(), nbr_idx.cpu().numpy())          # lists of a region are converted on demand
-    cells = None if csr is not None else region_cells(centers, sv_dis_thresh)
-
-    def new_index():
-        return _CsrIndex(*csr) if csr is not None else _GridIndex(centers, cells, sv_dis_thresh)
+    csr, native = None, None
+    if method in ("auto", "csr", "native"):
+        pairs = region_pairs(torch.from_numpy(centers).to(dev), sv_dis_thresh, None if method != "auto" else CSR_MAX_PAIRS)
+        if pairs is not None:
+            model = _set_model() if method in ("auto", "native") else None
+            if method == "native" and model is None:
+                raise L.LidalError("select_regions(method='native'): the set-order model does not match this interpreter")
+            if model is not None:
+                native = (np.ascontiguousarray(pairs[0].cpu().numpy()), np.ascontiguousarray(pairs[1].cpu().numpy()), model,
+                          np.ascontiguousarray(interds, dtype=np.float64), np.ascontiguousarray(interes, dtype=np.float64),
+                          np.ascontiguousarray(pnums, dtype=np.int64))
+            else:
+                csr = (pairs[0].cpu().tolist(), pairs[1].cpu().numpy())      # lists of a region are converted on demand
+    cells = None if (csr is not None or native is not None) else region_cells(centers, sv_dis_thresh)
+    t1 = _time.perf_counter()
+    sort_s = [0.0]
 
     def sorted_candidates():
+        h = _time.perf_counter()
         ids = np.where(flags == 0)[0]
         keys = d_dev[torch.from_numpy(ids).to(dev)]
         order_dev = argsort_f32(keys)
         sk = keys[order_dev.long()]
         has_ties = bool((sk[1:] == sk[:-1]).any().item()) if ids.size > 1 else False
         order = np.argsort(interds[ids]) if has_ties else order_dev.cpu().numpy()
+        sort_s[0] += _time.perf_counter() - h
         return ids, order
+
+    def walk(order, ids, flag_value, prefer_higher_entropy, skip_zero):
+        if native is None:
+            index = _CsrIndex(*csr) if csr is not None else _GridIndex(centers, cells, sv_dis_thresh)
+            return _greedy_walk(order, ids, interds, interes, pnums, index, flags, flag_value, limit, prefer_higher_entropy, skip_zero)
+        row_ptr, nbr_idx, model, d64, e64, pn64 = native
+        native_walk(ids[order], d64, e64, pn64, row_ptr, nbr_idx, flags, flag_value, limit, prefer_higher_entropy, skip_zero, model)
 
     ids, order = sorted_candidates()                                           # :232-235
     limit = round(0.01 * train_point_num)                                      # :240
-    _greedy_walk(order[::-1], ids, interds, interes, pnums, new_index(), flags, 1, limit, True, False)
+    walk(order[::-1], ids, 1, True, False)
     ids, order = sorted_candidates()                                           # :281-283 (before the reset)
     flags[flags == 2] = 0                                                      # :286
-    _greedy_walk(order, ids, interds, interes, pnums, new_index(), flags, 2, limit, False, True)
+    walk(order, ids, 2, False, True)
+    if timings is not None:
+        t2 = _time.perf_counter()
+        timings.update(select_pairs_ms=(t1 - t0) * 1e3, select_sort_ms=sort_s[0] * 1e3,
+                       select_walk_ms=(t2 - t1 - sort_s[0]) * 1e3, select_path="native" if native is not None else
+                       ("python-csr" if csr is not None else "python-grid"))
     return flags

@@ -66,3 +66,58 @@ def test_synthetic_shapes():
     assert c.dtype == np.int32 and c.shape[1] == 4 and f.shape == (c.shape[0], 4)
     assert inv.shape[0] == 8 * raw[::8].shape[0] and inv.max() == c.shape[0] - 1
     assert c[:, :3].min() >= 0 and c[:, :3].max() < 8192 and set(np.unique(c[:, 3])) == set(range(8))
+
+
+def test_set_order_model_matches_the_interpreter():
+    """_SetOrder replays CPython's set table for small ints: same iteration order as a real set after random add / remove
+    sequences crossing several resizes (the check select_regions itself performs before trusting the model)."""
+    assert score._set_model() is not None
+    rng = np.random.RandomState(7)
+    real, model, members = set(), score._SetOrder(score._set_model()), []
+    for step in range(20000):
+        if members and rng.rand() < 0.45:
+            k = members.pop(rng.randint(len(members)))
+            real.remove(k)
+            model.remove(k)
+        else:
+            k = int(rng.randint(0, 200000))
+            if k not in real:
+                members.append(k)
+            real.add(k)
+            model.add(k)
+    assert list(real) == list(model) and len(model) == len(real)
+    slots = [model.slot[k] for k in real]
+    assert slots == sorted(slots)
+
+
+def _native_both_passes(flags, d, e, pn, c, tpn):
+    ptr, nbr = _cpu_pairs(c, np.float32(5.0))
+    limit = round(0.01 * int(tpn))
+    ids = np.where(flags == 0)[0]
+    score.native_walk(ids[np.argsort(d[ids])[::-1]], d, e, pn, ptr, nbr, flags, 1, limit, True, False, score._set_model())
+    ids = np.where(flags == 0)[0]
+    order = np.argsort(d[ids])
+    flags[flags == 2] = 0
+    score.native_walk(ids[order], d, e, pn, ptr, nbr, flags, 2, limit, False, True, score._set_model())
+    return flags
+
+
+def test_native_walk_equals_python_replay_and_golden(golden):
+    """lb_select_walk (host C++, modelled set order) == the Python replay on a real set == the reference's golden flags."""
+    g = golden["selection"]
+    for d_key, tpn_key, out_key in (("sv_interds", "tight_tpn", "tight_out"), ("loose_interds", "loose_tpn", "loose_out")):
+        flags = _native_both_passes(g["sv_flags"].astype(int), g[d_key], g["sv_interes"], g["sv_pnums"],
+                                    np.ascontiguousarray(g["sv_centers"], dtype=np.float32), g[tpn_key])
+        assert np.array_equal(flags, g[out_key]), d_key
+    for seed, frames, frac in ((3, 100, 20), (5, 150, 8), (9, 60, 60)):
+        sv_flags, d, e, pn, c = synth.region_table(frames, seed=seed)
+        tpn = int(pn.sum()) * frac
+        want = _walk_both_passes(sv_flags.astype(int), d, e, pn, c, tpn, np.argsort, index="csr")
+        saved, score._SET_MODEL[:] = list(score._SET_MODEL), [None]          # force the real-set scan in the Python replay
+        try:
+            scan = _walk_both_passes(sv_flags.astype(int), d, e, pn, c, tpn, np.argsort, index="grid")
+        finally:
+            score._SET_MODEL[:] = saved
+        got = _native_both_passes(sv_flags.astype(int), d, e, pn, c, tpn)
+        assert np.array_equal(want, scan) and np.array_equal(got, want), seed
+        assert (got == 1).sum() > 0 and (got == 2).sum() > 0
