@@ -33,7 +33,7 @@ extern "C" {
 #define LB_ECAP (-2)   /* capacity / workspace too small                          */
 #define LB_ECUDA (-3)  /* CUDA runtime error or no device                         */
 
-#define LB_ABI_VERSION 2
+#define LB_ABI_VERSION 3
 
 int lb_abi_version(void);
 const char* lb_last_error(void); /* [host] thread-local text of the last failure */
@@ -99,6 +99,11 @@ int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int 
 int lb_kmap_sort_by_mask_ld(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm, int32_t* nbr_sorted,
                             int64_t sorted_ld, void* ws, size_t ws_bytes, void* stream);
 
+/* Active-offset mask of every group of 128 consecutive rows of a neighbour table (any row order; normally the mask-sorted
+ * one): tile_masks uint32 [ceil(n_out / 128)], bit j of entry g = OR over rows o in [128 g, 128 g + 128) of (nbr[j][o] >= 0).
+ * Built once per map and passed to every convolution that uses it (lb_conv_args.tile_masks). */
+int lb_kmap_tile_masks(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, uint32_t* tile_masks, void* stream);
+
 /* Per-offset inverse of a neighbour table (transposed convolution / dgrad roles):
  * nbr int32 [k, nbr_ld] with values in [0, n_in) or -1  ->  nbr_t int32 [k, n_in], nbr_t[k][nbr[k][o]] = o. */
 int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* nbr_t, int64_t n_in,
@@ -152,6 +157,7 @@ int lb_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int end_bit, void* 
 #define LB_CONV_TILE128 16   /* force 128-row CTA tiles (default: 256-row tiles, two accumulators per weight tile, on large inputs) */
 #define LB_CONV_NO_STAGED_EPILOGUE 32 /* A/B switch: per-thread 16-byte epilogue stores instead of smem-staged bulk rows */
 #define LB_CONV_RELU_FIRST 4 /* with LB_CONV_RELU: relu(v*scale+shift) + residual (SPVCNN point branch)  */
+#define LB_CONV_NO_LEAN 64   /* A/B switch: keep the per-tile prologue even when tile_masks are given / the rows are identity */
 
 typedef struct lb_conv_args {
   const void* in;          /* [n_in, ld_in] act_dtype                                        */
@@ -177,6 +183,11 @@ typedef struct lb_conv_args {
   int64_t in_pad_rows;     /* 0, or a power of two >= 16: rows [n_in, n_in + in_pad_rows) of `in` exist and are all ZERO.
                               Enables the TMA gather producer (tile::gather4 cannot skip rows, so missing neighbours are
                               fetched from this pool); without it the cp.async producer is used.                       */
+  const uint32_t* tile_masks; /* optional uint32 [ceil(n_out / 128)] from lb_kmap_tile_masks(nbr, nbr_ld, n_out, k_vol): bit k of
+                              entry g is set iff some row of rows [128 g, 128 g + 128) has a neighbour at offset k.  With it the
+                              kernel skips its per-tile prologue (no index staging, no offset-mask reduction, static tile order);
+                              a bit that is missing where a neighbour exists would drop that contribution, so build it from
+                              exactly the table passed as `nbr`.  NULL = the prologue computes the mask per tile.        */
 } lb_conv_args;
 
 size_t lb_conv_sched_ws_bytes(void);

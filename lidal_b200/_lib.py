@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("LIDAL_LIB") or os.path.join(HERE, "liblidal_b200.so")
 
 LB_DT_BF16, LB_DT_F16, LB_DT_F32 = 0, 1, 2
 LB_CONV_RELU, LB_CONV_FORCE_SIMT, LB_CONV_RELU_FIRST, LB_CONV_PACK8, LB_CONV_TILE128, LB_CONV_NO_STAGED = 1, 2, 4, 8, 16, 32
+LB_CONV_NO_LEAN = 64
 DT_OF = {torch.bfloat16: LB_DT_BF16, torch.float16: LB_DT_F16, torch.float32: LB_DT_F32}
 
 vp, i64, i32, sz, dbl, flt = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double, C.c_float
@@ -25,7 +26,7 @@ class ConvArgs(C.Structure):
     _fields_ = [("inp", vp), ("n_in", i64), ("ld_in", i64), ("out", vp), ("n_out", i64), ("ld_out", i64),
                 ("n_out_dev", vp), ("nbr", vp), ("nbr_ld", i64), ("out_rows", vp), ("weight", vp),
                 ("k_vol", i32), ("c_in", i32), ("c_out", i32), ("scale", vp), ("shift", vp), ("residual", vp),
-                ("ld_res", i64), ("act_dtype", i32), ("out_dtype", i32), ("flags", i32), ("sched_ws", vp), ("in_pad_rows", i64)]
+                ("ld_res", i64), ("act_dtype", i32), ("out_dtype", i32), ("flags", i32), ("sched_ws", vp), ("in_pad_rows", i64), ("tile_masks", vp)]
 
 
 class FrameRef(C.Structure):
@@ -53,6 +54,7 @@ SIGNATURES = {
     "lb_kmap_sort_by_mask": (i32, [vp, i64, i64, i32, vp, vp, vp, sz, vp]),
     "lb_kmap_sort_by_mask_ld": (i32, [vp, i64, i64, i32, vp, vp, i64, vp, sz, vp]),
     "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
+    "lb_kmap_tile_masks": (i32, [vp, i64, i64, i32, vp, vp]),
     "lb_unique_ws_bytes": (sz, [i64]),
     "lb_unique_i64": (i32, [vp, i64, i32, vp, vp, vp, vp, vp, sz, vp]),
     "lb_group_by_key_ws_bytes": (sz, [i64]),

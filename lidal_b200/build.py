@@ -25,6 +25,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out: str, extra_flags) -> str:
+    """A/B build of the library with extra nvcc flags (e.g. -DLIDAL_CONV_DEBUG) into ``out``; select it with LIDAL_LIB=out."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objdir = out + ".obj"
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc, *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *extra_flags, "-c", src, "-o", obj]))
+    for pr in procs:
+        if pr.wait() != 0:
+            raise RuntimeError("nvcc failed")
+    subprocess.check_call([nvcc, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB

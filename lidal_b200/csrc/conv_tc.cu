@@ -22,12 +22,14 @@
 // Measured on B200 (ncu, round 1): the kernel is bound by instructions per ring stage in the producer warps and in
 // the single issuing warp, not by DRAM, L2 or the tensor pipe on the 32/96-channel layers -- hence the care taken to
 // keep both per-stage paths short (running addresses, uniform control flow through REDUX, elect.sync issue).
+#include <type_traits>
 #include "tc_ptx.cuh"
 
 namespace lb {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_EPI_THREADS = 256;     // two epilogue groups of four warps (TMEM lane quadrant = warp % 4)
+constexpr int EPI_WARPS = NUM_EPI_THREADS / 32;
 #ifndef LIDAL_PROD_WARPS
 #define LIDAL_PROD_WARPS 8
 #endif
@@ -80,6 +82,15 @@ struct TcParams {
                            // (stage q belongs to warp q % prod_warps), so eight dependent fill chains run side by side
   unsigned* sched;         // dynamic tile scheduler: [0] next ticket, [1] retired CTAs (both zero between launches);
                            // nullptr = static round-robin
+  const uint32_t* tile_masks;   // lean producer: active-offset mask of every 128-row group of the (mask-sorted) neighbour table
+  int lean;                // 0: per-tile prologue through s_idx (modes above); 1: prologue-free gather (tile masks, indices read
+                           // straight from the table, static snake schedule); 2: identity input rows -> the A operand arrives by TMA
+                           // tile loads issued by the weight warp, the gather warps stay idle
+  int lean_arrive;         // lean == 1: 0 = every gather thread posts cp.async.mbarrier.arrive.noinc (256 arrivals per stage);
+                           // 1 = commit groups, a stage is published `lean_lag` stages later by ONE arrival per warp after
+                           // cp.async.wait_group + a writer-side proxy fence
+  int lean_lag;            // stages a warp keeps unpublished (1..3, < stages - 1)
+  int idx_bytes;           // shared memory reserved for s_idx (0 in lean mode: the bytes go to the ring)
 };
 
 // Bottleneck-hunting switches (knock-outs, cycle accounting) exist only in a -DLIDAL_CONV_DEBUG build: in the production
@@ -131,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   uint8_t* ring = smem;
   uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
   int* s_idx = (int*)tail;                                         // [MAX_KVOL][T * TILE_M]
-  float* s_scale = (float*)(tail + MAX_KVOL * T * TILE_M * 4);   // [256]
+  float* s_scale = (float*)(tail + p.idx_bytes);                   // [256]
   float* s_shift = s_scale + 256;                                  // [256]
   uint64_t* full_bar = (uint64_t*)(s_shift + 256);                 // [MAX_STAGES]
   uint64_t* empty_bar = full_bar + MAX_STAGES;                     // [MAX_STAGES]
@@ -139,13 +150,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
   uint32_t* s_tmem = (uint32_t*)(tempty_bar + 2) + MAX_STAGES;     // [1] (MAX_STAGES words of slack kept in front: tail_bytes() layout)
   uint32_t* s_mask = s_tmem + 1;                                   // [2] active-offset mask of the producers' tile (by parity)
-  uint64_t* res_bar = (uint64_t*)(s_mask + 2 + 1);                 // [4] residual rows landed (one per epilogue warp), 8-byte aligned
-  uint64_t* tstart_bar = res_bar + 4;                              // [2] tile id of an accumulator set published (MMA warp -> epilogue)
+  uint64_t* res_bar = (uint64_t*)(s_mask + 2 + 1);                 // [8] residual rows landed (one per epilogue warp), 8-byte aligned
+  uint64_t* tstart_bar = res_bar + EPI_WARPS;                              // [2] tile id of an accumulator set published (MMA warp -> epilogue)
   int* s_next = (int*)(tstart_bar + 2);                            // [1] next ticket of this CTA (-1: none), producers only
   int* s_stage_tile = s_next + 2;                                  // [MAX_STAGES] tile id carried by a tile's first stage
   int* s_acc_tile = s_stage_tile + MAX_STAGES;                     // [2] tile id held by each accumulator set (-1: no more work)
+  int* s_dbg = s_acc_tile + 2;                                     // [2 * MAX_STAGES] debug build only: clock of a stage's gather issue / MMA commit
   const int stg_pitch = p.c_out * 2 + 16;                          // staged epilogue: row pitch (+16 B: conflict-free 128-bit LDS)
-  uint8_t* s_stage = tail + (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 256 + 1023) & ~(size_t)1023);
+  uint8_t* s_stage = tail + (((size_t)p.idx_bytes + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 256 + 1023) & ~(size_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_out = p.n_out_dev ? (int64_t)*p.n_out_dev : p.n_out;
@@ -165,14 +177,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       // every gather thread of the stage posts one asynchronous arrival + 1 expect_tx arrive for the TMA weight tile
-      mbar_init(&full_bar[s], p.prod_mode == 3 ? 1 : (p.prod_mode >= 1 ? 32 : NUM_PROD_THREADS) + 1);
+      mbar_init(&full_bar[s], p.lean == 2 ? 1 : (p.lean == 1 && p.lean_arrive) ? LIDAL_PROD_WARPS + 1
+                              : p.prod_mode == 3 ? 1 : (p.prod_mode >= 1 ? 32 : NUM_PROD_THREADS) + 1);
       mbar_init(&empty_bar[s], 1);                     // released by tcgen05.commit
     }
-    for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tstart_bar[a], 1);
-      mbar_init(&tempty_bar[a], NUM_EPI_THREADS);   // every epilogue thread arrives once per tile
+      mbar_init(&tempty_bar[a], T == 2 ? NUM_EPI_THREADS : NUM_EPI_THREADS / 2);   // every epilogue thread that drains the set arrives once per tile
     }
     fence_barrier_init();
   }
@@ -182,7 +195,203 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp >= 4 && warp < MMA_WARP) {
+  // ---------------- lean mode: no per-tile prologue.  Every role derives the same static tile sequence on its own -- round i
+  // of CTA b takes ticket i * grid + (i odd ? grid - 1 - b : b) (a snake, so every CTA gets expensive and cheap tiles alike)
+  // and tickets walk the mask-sorted tiles from the last (most offsets) down -- and reads the tile's offset mask from the
+  // table lb_kmap_tile_masks built once per map.  Nothing is staged in shared memory and no CTA-wide barrier is left on the
+  // gather path; the roles meet only at the ring's full / empty barriers.
+  const int n_groups128 = (int)((n_out + TILE_M - 1) / TILE_M);
+  auto lean_tile = [&](int round) -> int {
+    const int64_t tk = (int64_t)round * gridDim.x + ((round & 1) ? (int64_t)(gridDim.x - 1 - blockIdx.x) : (int64_t)blockIdx.x);
+    return tk < num_tiles ? (int)(num_tiles - 1 - tk) : -1;
+  };
+  auto lean_mask = [&](int tile) -> uint32_t {
+    if (p.lean == 2) return 1u;
+    uint32_t m = __ldg(p.tile_masks + tile * T);
+    if (T == 2 && tile * 2 + 1 < n_groups128) m |= __ldg(p.tile_masks + tile * 2 + 1);
+    if (p.k_vol < 32) m &= (1u << p.k_vol) - 1u;
+    return m ? m : 1u;                                      // keep the pipeline uniform: one all-zero block
+  };
+
+  if (p.lean == 1 && warp >= EPI_WARPS && warp < MMA_WARP) {
+    // =============================================================== LEAN GATHER WARPS
+    // Thread t copies the 16-byte chunk (t % CHUNKS) of rows row0 + i * ROWS_PER_PASS of every 128-row sub-tile.  The row
+    // indices of an offset come straight from the neighbour table (one 4-byte load per slot, all CHUNKS lanes of a row read
+    // the same word) and are fetched TWO offsets ahead of their use, across tile boundaries, so the copy stream never waits
+    // for them; the tile's offset mask is fetched one tile ahead.
+    const int t = threadIdx.x - NUM_EPI_THREADS;
+    const int chunk = t % CHUNKS, row0 = t / CHUNKS;
+    constexpr int PASSES = TILE_M / ROWS_PER_PASS;
+    constexpr int NS = T * PASSES;                          // gather slots of a thread per block
+    const uint32_t ring_u32 = smem_u32(ring);
+    uint32_t st_u32 = ring_u32;
+    int stage = 0;
+    uint32_t ph = 0;
+    const int64_t ld_in_b = p.ld_in * 2;
+    const char* in_col = p.in + chunk * 16;
+    const int n_out_i = (int)n_out;
+    uint32_t dst_off[NS];                                   // smem offset of each slot inside a block (swizzled chunk position)
+#pragma unroll
+    for (int sub = 0; sub < T; ++sub)
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) {
+        const int r = row0 + i * ROWS_PER_PASS;
+        const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
+        dst_off[sub * PASSES + i] = (uint32_t)(sub * A_BYTES + r * ROW_BYTES) + sw * 16;
+      }
+    // iterator over the (tile, offset) pairs of this CTA, in issue order
+    int round = 0;
+    int it_tile = lean_tile(0);
+    uint32_t it_mask = it_tile >= 0 ? lean_mask(it_tile) : 0u;
+    int nx_tile = lean_tile(1);
+    uint32_t nx_mask = nx_tile >= 0 ? lean_mask(nx_tile) : 0u;
+    bool it_first = true;
+    // descriptor of a fetched pair: -1 = no more work; else bit 30 = first pair of its tile, bits 8.. = offsets of the tile
+    auto fetch = [&](int (&dst)[NS]) -> int {
+      if (it_mask == 0u) {
+        it_tile = nx_tile;
+        it_mask = nx_mask;
+        it_first = true;
+        if (it_tile >= 0) {
+          ++round;
+          nx_tile = lean_tile(round + 1);
+          nx_mask = nx_tile >= 0 ? lean_mask(nx_tile) : 0u;
+        }
+      }
+      if (it_tile < 0) return -1;
+      const int k = __ffs(it_mask) - 1;
+      const int desc = (it_first ? (1 << 30) | (__popc(it_mask) << 8) : 0);
+      it_first = false;
+      it_mask &= it_mask - 1u;
+      const int* src = p.nbr + (int64_t)k * p.nbr_ld + (int64_t)it_tile * TM + row0;
+#pragma unroll
+      for (int sub = 0; sub < T; ++sub)
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+          const int o = sub * TILE_M + i * ROWS_PER_PASS;
+          dst[sub * PASSES + i] = (it_tile * TM + row0 + o < n_out_i) ? __ldg(src + o) : -1;
+        }
+      return desc;
+    };
+    int nb_a[NS], nb_b[NS], nb_c[NS];
+    int d_a = fetch(nb_a);
+    int d_b = d_a >= 0 ? fetch(nb_b) : -1;
+    int d_c = d_b >= 0 ? fetch(nb_c) : -1;
+    int j = 0, remaining = 0;
+    int pend = 0, arr_stage = 0;                            // lean_arrive: committed but unpublished stages, oldest of them
+    while (d_a >= 0) {
+      if (d_a & (1 << 30)) remaining = ((d_a >> 8) & 0xff) * kc_blocks;
+      for (int cb = 0; cb < kc_blocks; ++cb) {
+        if (j == 0) mbar_wait(&empty_bar[stage], ph ^ 1);   // slot free (first lap passes immediately)
+        const char* in_cb = in_col + cb * (BK * 2);
+        const uint32_t blk_u32 = st_u32 + (uint32_t)(j * a_blk);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const int nb = nb_a[s];
+          cp_async16(blk_u32 + dst_off[s], in_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b, nb >= 0 ? 16u : 0u);
+        }
+        --remaining;
+        if (++j == p.nb || remaining == 0) {
+          if (p.lean_arrive) {
+            cp_async_commit();
+            if (++pend > p.lean_lag) {
+              if (p.lean_lag == 1) cp_async_wait<1>(); else if (p.lean_lag == 2) cp_async_wait<2>(); else cp_async_wait<3>();
+              fence_proxy_async();                          // my landed copies -> visible to the tensor core's async proxy
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&full_bar[arr_stage]);
+              if (++arr_stage == p.stages) arr_stage = 0;
+              --pend;
+            }
+          } else {
+            cp_async_arrive_noinc(&full_bar[stage]);        // asynchronous: fires when this thread's copies have landed
+          }
+          j = 0;
+          st_u32 += stage_bytes;
+          if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) { nb_a[s] = nb_b[s]; nb_b[s] = nb_c[s]; }
+      d_a = d_b;
+      d_b = d_c;
+      d_c = d_c >= 0 ? fetch(nb_c) : -1;
+    }
+    if (p.lean_arrive) {                                    // publish what is still pending
+      cp_async_wait<0>();
+      fence_proxy_async();
+      __syncwarp();
+      for (; pend > 0; --pend) {
+        if (lane == 0) mbar_arrive(&full_bar[arr_stage]);
+        if (++arr_stage == p.stages) arr_stage = 0;
+      }
+    }
+    // sentinel stage (the weight warp writes its tile word): complete the barrier's arrival count
+    mbar_wait(&empty_bar[stage], ph ^ 1);
+    if (!p.lean_arrive || lane == 0) mbar_arrive(&full_bar[stage]);
+    cp_async_wait<0>();
+  } else if (p.lean && warp == WEIGHT_WARP) {
+    // =============================================================== LEAN WEIGHT / TILE LOADER
+    // Opens every stage: arms the full barrier with the stage's TMA byte count, publishes the tile word with a tile's first
+    // stage and issues the weight-tile loads; for identity input rows (lean == 2) also the A operand as plain TMA tile loads
+    // (box = BK channels x 128 rows, same swizzle as the gather would produce), so such layers run without gather warps.
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&w_map) : "memory");
+      if (p.lean == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
+    }
+    int stage = 0;
+    uint32_t ph = 0, st_u32 = smem_u32(ring);
+    const uint32_t ring_u32 = st_u32;
+    const uint32_t blk_tx = (uint32_t)b_bytes + (p.lean == 2 ? (uint32_t)a_blk : 0u);
+    int round = 0;
+    int tile = lean_tile(0);
+    uint32_t mask = tile >= 0 ? lean_mask(tile) : 0u;
+    while (tile >= 0) {
+      const int ntile = lean_tile(round + 1);               // next tile's mask: in flight while this tile is issued
+      const uint32_t nmask = ntile >= 0 ? lean_mask(ntile) : 0u;
+      int remaining = __popc(mask) * kc_blocks;
+      const int cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
+      bool first = true;
+      int j = 0;
+      for (uint32_t m = mask; m; m &= m - 1u) {
+        const int k = __ffs(m) - 1;
+        for (int cb = 0; cb < kc_blocks; ++cb) {
+          if (j == 0) {
+            mbar_wait(&empty_bar[stage], ph ^ 1);
+            if (lane == 0) {
+              if (first) s_stage_tile[stage] = cur_word;
+              const int in_stage = remaining < p.nb ? remaining : p.nb;
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)in_stage * blk_tx);
+            }
+            first = false;
+          }
+          if (lane == 0) {
+            tma_load_2d(st_u32 + (uint32_t)(p.nb * a_blk + j * b_pad), &w_map, cb * BK, k * p.c_out, &full_bar[stage]);
+            if (p.lean == 2) {
+#pragma unroll
+              for (int sub = 0; sub < T; ++sub)
+                tma_load_2d(st_u32 + (uint32_t)(j * a_blk + sub * A_BYTES), &in_map, cb * BK, tile * TM + sub * TILE_M, &full_bar[stage]);
+            }
+          }
+          --remaining;
+          if (++j == p.nb || remaining == 0) {
+            j = 0;
+            st_u32 += stage_bytes;
+            if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
+          }
+        }
+      }
+      tile = ntile;
+      mask = nmask;
+      ++round;
+    }
+    mbar_wait(&empty_bar[stage], ph ^ 1);
+    if (lane == 0) {
+      s_stage_tile[stage] = -1;                             // sentinel: this CTA is out of work
+      mbar_arrive(&full_bar[stage]);
+    }
+  } else if (p.lean && warp >= EPI_WARPS && warp < MMA_WARP) {
+    // lean == 2: the A operand comes by TMA, the gather warps have nothing to do
+  } else if (warp >= EPI_WARPS && warp < MMA_WARP) {
     // =============================================================== PRODUCERS
     const int t = threadIdx.x - NUM_EPI_THREADS;          // 0..127
     const int chunk = t % CHUNKS, row0 = t / CHUNKS;
@@ -434,41 +643,102 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           }
         }
       } else if (p.wwarp) {
-        // Lock-step gather with multi-block stages: a stage carries up to p.nb consecutive (offset, channel block) blocks of
-        // the tile, so the slot wait, the barrier arrival and the ring bookkeeping are paid once per p.nb blocks (the weight
-        // warp arms the barrier and loads the matching weight tiles; the MMA warp issues all blocks of a stage back to back).
-        int remaining = __popc(mask) * kc_blocks;         // blocks of this tile still to issue
-        int j = 0;                                        // block slot inside the open stage
-        for (int k = __ffs(mask) - 1; k < 32 && (mask >> k); ++k) {
-          if (!((mask >> k) & 1)) continue;
+        // Lock-step gather trimmed to the instructions that cannot be avoided.  (ncu source view, round 2: every role of this
+        // kernel is a chain of dependent instructions that issues one every ~10 cycles, so the time of a ring stage is the
+        // LENGTH of the longest per-stage chain.  The gather warps ran ~150 instructions per block -- 64-bit address
+        // arithmetic per slot and block, four branches of stage bookkeeping; now ~30.)  Per offset: each slot's source row
+        // pointer and fill size are formed once (one IMAD.WIDE per slot).  Per block: T * PASSES LDGSTS whose global and
+        // shared offsets are immediates (the channel-block loop is unrolled for c_in / BK in {1, 2, 3, 4, 6}).  Per stage of
+        // p.nb blocks: one slot wait, one arrival, a branch-free ring advance on running 32-bit addresses.
+        constexpr int NS = T * PASSES;
+        const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        uint32_t bar_off = (uint32_t)stage * 8u;
+        const uint32_t bar_end = (uint32_t)p.stages * 8u;
+        const uint32_t ld32 = (uint32_t)ld_in_b;                               // row pitch in bytes (< 2^32: ld_in is a row width)
+        const uint32_t sw0 = (BK == 64) ? (uint32_t)(chunk ^ (row0 & 7)) : (uint32_t)(chunk ^ ((row0 >> 1) & 3));   // ROWS_PER_PASS % 8 == 0
+        const uint32_t t_off = (uint32_t)(row0 * ROW_BYTES) + sw0 * 16u;
+        const int* idx_t = s_idx + row0;
+        int remaining = __popc(mask) * kc_blocks;                              // blocks of this tile still to issue
+        int j = 0;                                                             // block slot inside the open stage
+        uint32_t dst = st_u32 + t_off;                                         // this thread's first slot of the open block
+        auto close_block = [&]() {
+          --remaining;
+          dst += (uint32_t)a_blk;
+          if (++j == p.nb || remaining == 0) {
+            cp_async_arrive_noinc_u32(full0 + bar_off);                        // asynchronous: fires when this thread's copies have landed
+            if (DBG_ON && t == 0) s_dbg[bar_off >> 3] = (int)clock();
+            j = 0;
+            st_u32 += stage_bytes;
+            bar_off += 8u;
+            const bool wrap = bar_off == bar_end;
+            bar_off = wrap ? 0u : bar_off;
+            st_u32 = wrap ? ring_u32 : st_u32;
+            ph ^= wrap ? 1u : 0u;
+            dst = st_u32 + t_off;
+          }
+        };
+        auto open_block = [&]() {
+          if (j == 0) {
+            const int dbg_c0 = (DBG_ON && t == 0) ? (int)clock() : 0;
+            mbar_wait_u32(empty0 + bar_off, ph ^ 1);                           // slot free (first lap passes immediately)
+            if (DBG_ON && t == 0) {
+              const int now = (int)clock();
+              DBG_ADD(5, now - dbg_c0);
+              if (now - dbg_c0 > 150) { DBG_ADD(13, now - s_dbg[MAX_STAGES + (bar_off >> 3)]); DBG_ADD(14, 1); }   // blocked: MMA commit -> slot seen free
+            }
+          }
+        };
+        auto one_offset = [&](auto kc_c, int k) {
+          constexpr int KC = decltype(kc_c)::value;
+          const char* src[NS];
+          uint32_t sz[NS];
 #pragma unroll
           for (int sub = 0; sub < T; ++sub)
 #pragma unroll
-            for (int i = 0; i < PASSES; ++i) nbv[sub][i] = s_idx[k * TM + sub * TILE_M + row0 + i * ROWS_PER_PASS];
-          for (int cb = 0; cb < kc_blocks; ++cb) {
-            if (j == 0) mbar_wait(&empty_bar[stage], ph ^ 1);     // slot free (first lap passes immediately)
-            const char* in_cb = in_col + cb * (BK * 2);
-            const uint32_t blk_u32 = st_u32 + (uint32_t)(j * a_blk);
+            for (int i = 0; i < PASSES; ++i) {
+              const int nb = idx_t[k * TM + sub * TILE_M + i * ROWS_PER_PASS];
+              sz[sub * PASSES + i] = nb >= 0 ? 16u : 0u;
+              src[sub * PASSES + i] = in_col + (uint64_t)(uint32_t)(nb >= 0 ? nb : 0) * ld32;
+            }
 #pragma unroll
-            for (int sub = 0; sub < T; ++sub) {
+          for (int cb = 0; cb < KC; ++cb) {
+            open_block();
+            const int dbg_g0 = (DBG_ON && t == 0) ? (int)clock() : 0;
 #pragma unroll
-              for (int i = 0; i < PASSES; ++i) {
-                const int r = row0 + i * ROWS_PER_PASS;
-                const int nb = nbv[sub][i];
-                const char* src = in_cb + (int64_t)(nb >= 0 ? nb : 0) * ld_in_b;
-                const uint32_t sw = (BK == 64) ? (uint32_t)(chunk ^ (r & 7)) : (uint32_t)(chunk ^ ((r >> 1) & 3));
-                if (!(DBG(p) & 1)) cp_async16(blk_u32 + sub * A_BYTES + r * ROW_BYTES + sw * 16, src, nb >= 0 ? 16u : 0u);
+            for (int sub = 0; sub < T; ++sub)
+#pragma unroll
+              for (int i = 0; i < PASSES; ++i)
+                if (!(DBG(p) & 1))
+                  cp_async16(dst + (uint32_t)(sub * A_BYTES + i * ROWS_PER_PASS * ROW_BYTES), src[sub * PASSES + i] + cb * (BK * 2), sz[sub * PASSES + i]);
+            const int dbg_g1 = (DBG_ON && t == 0) ? (int)clock() : 0;
+            close_block();
+            if (DBG_ON && t == 0) { DBG_ADD(19, dbg_g1 - dbg_g0); DBG_ADD(20, (int)clock() - dbg_g1); }
+          }
+        };
+        for (uint32_t m = mask; m; m &= m - 1u) {
+          const int k = __ffs(m) - 1;
+          switch (kc_blocks) {
+            case 1: one_offset(std::integral_constant<int, 1>{}, k); break;
+            case 2: one_offset(std::integral_constant<int, 2>{}, k); break;
+            case 3: one_offset(std::integral_constant<int, 3>{}, k); break;
+            case 4: one_offset(std::integral_constant<int, 4>{}, k); break;
+            case 6: one_offset(std::integral_constant<int, 6>{}, k); break;
+            default:
+              for (int cb = 0; cb < kc_blocks; ++cb) {                       // other channel counts: same sequence, runtime offsets
+                open_block();
+#pragma unroll
+                for (int sub = 0; sub < T; ++sub)
+#pragma unroll
+                  for (int i = 0; i < PASSES; ++i) {
+                    const int nb = idx_t[k * TM + sub * TILE_M + i * ROWS_PER_PASS];
+                    cp_async16(dst + (uint32_t)(sub * A_BYTES + i * ROWS_PER_PASS * ROW_BYTES),
+                               in_col + (uint64_t)(uint32_t)(nb >= 0 ? nb : 0) * ld32 + cb * (BK * 2), nb >= 0 ? 16u : 0u);
+                  }
+                close_block();
               }
-            }
-            --remaining;
-            if (++j == p.nb || remaining == 0) {
-              cp_async_arrive_noinc(&full_bar[stage]);    // asynchronous: fires when this thread's copies have landed
-              j = 0;
-              st_u32 += stage_bytes;
-              if (++stage == p.stages) { stage = 0; ph ^= 1; st_u32 = ring_u32; }
-            }
           }
         }
+        stage = (int)(bar_off >> 3);
       } else {
         int remaining = __popc(mask) * kc_blocks;
         cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
@@ -574,9 +844,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);      // bits 0-13 address >> 4, 16-29 LBO = 1
     const uint32_t stage_units = (uint32_t)stage_bytes >> 4, b_units = (uint32_t)(p.nb * a_blk) >> 4, b_pad_units = (uint32_t)b_pad >> 4;
     constexpr uint32_t A_UNITS = A_BYTES >> 4;
-    int stage = 0;
+    // The whole issue loop runs in ONE thread (lane 0): waits, tile hand-over, MMAs and commits need no warp-level
+    // agreement, so there is no per-stage elect / warp sync and the barrier addresses are running 32-bit registers.
+    // (elect.sync rather than `lane == 0`: the compiler then knows the region is single-threaded and issues the UTCHMMA /
+    // UTCBAR instructions back to back instead of wrapping each one in an election loop.)
+    if (elect_one()) {
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t bar_end = (uint32_t)p.stages * 8u;
+    uint32_t bar_off = 0;
     uint32_t ph = 0, st_lo = ring_lo;
-    const bool dbg_me = DBG_ON && lane == 0;
+    const bool need_fence = p.prod_mode < 2 && !(p.lean == 2 || (p.lean == 1 && p.lean_arrive));
+    const bool dbg_me = DBG_ON;
     const long long dbg_m0 = dbg_me ? clock64() : 0;
     for (int64_t tcount = 0;; ++tcount) {
       const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
@@ -586,57 +864,79 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       if (dbg_me) DBG_ADD(2, clock64() - dbg_t);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T * p.c_out);
-      // first stage of the tile: its slot carries the tile word (tile id | stage count << 24; -1 = this CTA is done)
+      // first stage of the tile: its slot carries the tile word (tile id | block count << 24; -1 = this CTA is done)
       dbg_t = dbg_me ? clock64() : 0;
-      mbar_wait(&full_bar[stage], ph);
+      mbar_wait_u32(full0 + bar_off, ph);
       if (dbg_me) DBG_ADD(1, clock64() - dbg_t);
-      const uint32_t word = __reduce_or_sync(0xffffffffu, (uint32_t)s_stage_tile[stage]);   // uniform for the compiler
+      const uint32_t word = (uint32_t)*(volatile int*)&s_stage_tile[bar_off >> 3];
       if (word == 0xffffffffu) {
-        if (lane == 0) {
-          s_acc_tile[acc] = -1;
-          mbar_arrive(&tstart_bar[acc]);
+        s_acc_tile[acc] = -1;
+        mbar_arrive(&tstart_bar[acc]);
+        if (T == 1) {                                      // 128-row tiles: the other epilogue group owns the other accumulator set
+          const int acc2 = (int)((tcount + 1) & 1);
+          mbar_wait(&tempty_bar[acc2], (uint32_t)(((tcount + 1) >> 1) & 1) ^ 1);
+          s_acc_tile[acc2] = -1;
+          mbar_arrive(&tstart_bar[acc2]);
         }
         if (dbg_me) DBG_ADD(0, clock64() - dbg_m0);
         break;
       }
       const int n_blk = (int)(word >> 24);                       // blocks of the tile; a stage carries up to p.nb of them
-      if (lane == 0) {
-        s_acc_tile[acc] = (int)(word & 0xffffffu);               // the epilogue learns its tile before the MMAs finish
-        mbar_arrive(&tstart_bar[acc]);
-      }
+      s_acc_tile[acc] = (int)(word & 0xffffffu);                 // the epilogue learns its tile before the MMAs finish
+      mbar_arrive(&tstart_bar[acc]);
       if (dbg_me) DBG_ADD(3, n_blk);
       for (int e = 0, done = 0; done < n_blk; ++e) {
         const int nbs = (n_blk - done) < p.nb ? (n_blk - done) : p.nb;
         if (e) {
           dbg_t = dbg_me ? clock64() : 0;
-          mbar_wait(&full_bar[stage], ph);
-          if (dbg_me) DBG_ADD(1, clock64() - dbg_t);
-        }
-        if (p.prod_mode < 2 && !(DBG(p) & 8)) fence_proxy_async();   // cp.async wrote through the generic proxy and cannot fence on the writer side
-        tc_fence_after();
-        if (elect_one()) {
-          for (int j = 0; j < nbs; ++j) {                 // the blocks of this stage, back to back
-            const uint32_t a_lo = st_lo + (uint32_t)j * (uint32_t)T * A_UNITS;
-            const uint32_t b_lo = st_lo + b_units + (uint32_t)j * b_pad_units;
-#pragma unroll
-            for (int sub = 0; sub < T; ++sub) {           // every sub-tile reuses the same weight tile
-#pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk)        // +32 bytes along K inside the swizzle atom = +2 in the address field
-                if (!(DBG(p) & 2)) umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), a_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
-                              b_lo + (uint32_t)kk * 2u, desc_hi, idesc, (kk == 0 && e == 0 && j == 0) ? 0u : 1u);   // first MMA overwrites
-            }
+          mbar_wait_u32(full0 + bar_off, ph);
+          if (dbg_me) {
+            const long long now = clock64();
+            DBG_ADD(1, now - dbg_t);
+            if (now - dbg_t > 150) { DBG_ADD(12, (int)now - s_dbg[bar_off >> 3]); DBG_ADD(15, 1); }   // blocked: gather issue -> data seen landed
           }
-          umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-          if (done + nbs == n_blk) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
-        __syncwarp();
+        const long long dbg_s1 = dbg_me ? clock64() : 0;
+        if (need_fence && !(DBG(p) & 8)) fence_proxy_async();   // cp.async wrote through the generic proxy and cannot fence on the writer side
+        tc_fence_after();
+        const long long dbg_s2 = dbg_me ? clock64() : 0;
+#pragma unroll 1
+        for (int j = 0; j < nbs; ++j) {                   // the blocks of this stage, back to back
+          const uint32_t a_lo = st_lo + (uint32_t)j * (uint32_t)T * A_UNITS;
+          const uint32_t b_lo = st_lo + b_units + (uint32_t)j * b_pad_units;
+#pragma unroll
+          for (int sub = 0; sub < T; ++sub) {             // every sub-tile reuses the same weight tile
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk)          // +32 bytes along K inside the swizzle atom = +2 in the address field
+              if (!(DBG(p) & 2)) umma_f16_lohi(d_tmem + (uint32_t)(sub * p.c_out), a_lo + (uint32_t)sub * A_UNITS + (uint32_t)kk * 2u,
+                            b_lo + (uint32_t)kk * 2u, desc_hi, idesc, (kk == 0 && e == 0 && j == 0) ? 0u : 1u);   // first MMA overwrites
+          }
+        }
+        const long long dbg_s3 = dbg_me ? clock64() : 0;
+        umma_commit_u32(empty0 + bar_off);                // smem slot reusable once these MMAs retire
+        if (done + nbs == n_blk) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
+        if (dbg_me) {
+          s_dbg[MAX_STAGES + (bar_off >> 3)] = (int)clock();
+          DBG_ADD(16, dbg_s2 - dbg_s1); DBG_ADD(17, dbg_s3 - dbg_s2); DBG_ADD(18, clock64() - dbg_s3);
+        }
         done += nbs;
         st_lo += stage_units;
-        if (++stage == p.stages) { stage = 0; ph ^= 1; st_lo = ring_lo; }
+        bar_off += 8u;
+        if (bar_off == bar_end) { bar_off = 0; ph ^= 1; st_lo = ring_lo; }
       }
     }
+    }
+    __syncwarp();
   } else {
-    // =============================================================== EPILOGUE (warps 0-3: TMEM lane quadrant = warp)
+    // =============================================================== EPILOGUE (warps 0-7: TMEM lane quadrant = warp % 4)
+    // Two groups of four warps.  With 256-row tiles (T == 2) group g drains sub-tile g of every tile; with 128-row tiles
+    // group g owns accumulator set g, i.e. every other tile.  Either way two epilogue chains -- row-index load, residual
+    // fetch, TMEM reads, conversion, stores -- run side by side: on the fine levels a tile's epilogue (fixed cost per row)
+    // is as long as its few-offset main loop, so a single chain was a co-bottleneck of the kernel.
+    const int eq = warp & 3, eg = warp >> 2;
+    constexpr bool SPLIT_SUB = (T == 2);
+    const int sub_lo = SPLIT_SUB ? eg : 0, sub_hi = SPLIT_SUB ? eg + 1 : T;
+    const int64_t t_first = SPLIT_SUB ? 0 : eg, t_step = SPLIT_SUB ? 1 : 2;
     if (p.staged == 2) {
       // TMA-tile staging (output rows in natural order, 1x1 layers): a warp's 32 rows x c_out channels sit in smem as
       // c_out/32 boxes of [32 rows][64 B] in the SWIZZLE_64B pattern (16-byte chunk q of row r at q ^ ((r >> 1) & 3):
@@ -650,15 +950,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       const uint32_t row_bytes = (uint32_t)p.c_out * 2;
       uint32_t res_ph = 0;
       int buf = 0;
-      int64_t tcount = 0;
-      for (;; ++tcount) {
+      int64_t tcount = t_first;
+      for (;; tcount += t_step) {
         const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
         const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
         mbar_wait(&tstart_bar[acc], acc_ph);              // the MMA warp has published this accumulator's tile
         const int64_t tile = s_acc_tile[acc];
         if (tile < 0) break;
-        for (int sub = 0; sub < T; ++sub) {
-          const int64_t row0 = tile * TM + sub * TILE_M + warp * 32;
+        for (int sub = sub_lo; sub < sub_hi; ++sub) {
+          const int64_t row0 = tile * TM + sub * TILE_M + eq * 32;
           const bool any_live = row0 < n_out;
           uint8_t* sbuf = my_stage + (size_t)buf * buf_bytes;
           if (lane == 0) {                                  // lane 0 owns the warp's bulk groups
@@ -670,7 +970,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             mbar_arrive_expect_tx(&res_bar[warp], 32u * row_bytes);      // whole boxes; rows past the end are zero-filled
             for (int g = 0; g < groups; ++g) tma_load_2d(smem_u32(sbuf + g * 2048), &res_map, g * 32, (int)row0, &res_bar[warp]);
           }
-          if (sub == 0) {
+          if (sub == sub_lo) {
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
           }
@@ -680,7 +980,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           }
           for (int c0 = 0; c0 < p.c_out; c0 += 32) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
+            tmem_ld32(tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
@@ -741,10 +1041,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       int buf = 0;
       const uint32_t row_bytes = (uint32_t)p.c_out * 2;
       uint32_t res_ph = 0;
-      int64_t tcount = 0;
+      int64_t tcount = t_first;
       const bool dbg_me = DBG_ON && threadIdx.x == 0;
       const long long dbg_e0 = dbg_me ? clock64() : 0;
-      for (;; ++tcount) {
+      for (;; tcount += t_step) {
         const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
         const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
         const long long dbg_t = dbg_me ? clock64() : 0;
@@ -754,8 +1054,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
         if (tile < 0) { if (dbg_me) DBG_ADD(9, clock64() - dbg_e0); break; }
         if (DBG(p) & 32) { mbar_wait(&tfull_bar[acc], acc_ph); tc_fence_after(); }
         else
-        for (int sub = 0; sub < T; ++sub) {
-          const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
+        for (int sub = sub_lo; sub < sub_hi; ++sub) {
+          const int64_t o = tile * TM + sub * TILE_M + eq * 32 + lane;
           const bool live = o < n_out;
           const int64_t orow = live ? (p.out_rows ? (int64_t)__ldg(&p.out_rows[o]) : o) : 0;
           uint8_t* my_row = my_stage + buf * buf_bytes + (size_t)lane * stg_pitch;
@@ -768,7 +1068,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
             __syncwarp();
             if (live) bulk_load(smem_u32(my_row), p.residual + orow * p.ld_res * 2, row_bytes, &res_bar[warp]);
           }
-          if (sub == 0) {
+          if (sub == sub_lo) {
             const long long dbg_f = dbg_me ? clock64() : 0;
             mbar_wait(&tfull_bar[acc], acc_ph);
             if (dbg_me) DBG_ADD(11, clock64() - dbg_f);
@@ -780,7 +1080,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           }
           for (int c0 = 0; c0 < p.c_out; c0 += 32) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
+            tmem_ld32(tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
@@ -829,9 +1129,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       }
       bulk_wait_all();                                    // all rows are in global memory before the CTA retires
     } else {
-    int64_t tcount = 0;
+    int64_t tcount = t_first;
     const int out_es = (p.out_dtype == LB_DT_F32) ? 4 : 2;
-    for (;; ++tcount) {
+    for (;; tcount += t_step) {
       const int acc = p.n_acc == 2 ? (int)(tcount & 1) : 0;
       const uint32_t acc_ph = (uint32_t)((p.n_acc == 2 ? tcount >> 1 : tcount) & 1);
       mbar_wait(&tstart_bar[acc], acc_ph);                // the MMA warp has published this accumulator's tile
@@ -839,15 +1139,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       if (tile < 0) break;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
-      for (int sub = 0; sub < T; ++sub) {
-      const int64_t o = tile * TM + sub * TILE_M + warp * 32 + lane;
+      for (int sub = sub_lo; sub < sub_hi; ++sub) {
+      const int64_t o = tile * TM + sub * TILE_M + eq * 32 + lane;
       const bool live = o < n_out;
       const int64_t orow = live ? (p.out_rows ? (int64_t)__ldg(&p.out_rows[o]) : o) : 0;
       char* out_row = p.out + orow * p.ld_out * out_es;
       const char* res_row = p.residual ? p.residual + orow * p.ld_res * 2 : nullptr;
       for (int c0 = 0; c0 < p.c_out; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(eq * 32) << 16) + (uint32_t)((acc * T + sub) * p.c_out + c0), v);
         if (live) {
           float f[32];
 #pragma unroll
@@ -945,11 +1245,12 @@ int conv_tc_supported(int k_vol, int c_in, int c_out, int act_dtype) {
   return 1;
 }
 
-static size_t tail_bytes(int T) {
-  // indices + scale/shift + ring/accumulator barriers + flags + (tmem ptr, masks, 4 residual barriers), rounded for staging
-  return (((size_t)MAX_KVOL * T * TILE_M * 4 + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 256 + 1023) & ~(size_t)1023);
+static size_t idx_bytes(int T, int lean) { return lean ? 0 : (size_t)MAX_KVOL * T * TILE_M * 4; }
+static size_t tail_bytes(int T, int lean = 0) {
+  // indices (none in lean mode) + scale/shift + ring/accumulator barriers + flags + (tmem ptr, masks, 4 residual barriers), rounded for staging
+  return ((idx_bytes(T, lean) + 2 * 256 * 4 + (2 * MAX_STAGES + 4) * 8 + MAX_STAGES * 4 + 256 + 1023) & ~(size_t)1023);
 }
-static size_t staging_bytes(int c_out, int bufs = 1) { return (size_t)bufs * 4 * 32 * (c_out * 2 + 16); }
+static size_t staging_bytes(int c_out, int bufs = 1) { return (size_t)bufs * EPI_WARPS * 32 * (c_out * 2 + 16); }   // one buffer per epilogue warp
 
 int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const bool pack8 = (a.flags & LB_CONV_PACK8) != 0;
@@ -979,6 +1280,28 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("lb_conv_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r); return LB_ECUDA; }
 
+  // Lean producer (no per-tile prologue): gathered layers need the tile-mask table of lb_kmap_tile_masks; identity layers
+  // (nbr == NULL) a tensor map over the input so the weight warp can bring the A operand by TMA tile loads.
+  // LIDAL_LEAN bit 0: gathered layers, bit 1: identity layers (A/B switch, default both).
+  static const int lean_env = getenv("LIDAL_LEAN") ? atoi(getenv("LIDAL_LEAN")) : 2;   // measured (profiles/r02_conv_lean_modes.txt): bit 0 is slower than the prologue path
+  static const int lean_gate = (getenv("LIDAL_PROD_MODE") && atoi(getenv("LIDAL_PROD_MODE"))) || (getenv("LIDAL_TMA_GATHER") && atoi(getenv("LIDAL_TMA_GATHER"))) ||
+                               (getenv("LIDAL_WEIGHT_WARP") && !atoi(getenv("LIDAL_WEIGHT_WARP"))) || getenv("LIDAL_DBG");
+  int lean = 0;
+  CUtensorMap in_map = map;                      // placeholder unless a TMA producer is used
+  if (!pack8 && !lean_gate && !(a.flags & LB_CONV_NO_LEAN) && !a.n_out_dev && a.n_out < ((int64_t)1 << 30) && a.n_in < ((int64_t)1 << 31)) {
+    if (a.nbr && a.tile_masks && (lean_env & 1)) lean = 1;
+    else if (!a.nbr && (lean_env & 2) && ((uintptr_t)a.in & 15) == 0 && (a.ld_in * 2) % 16 == 0 && a.n_in > 0) {
+      cuuint64_t idim[2] = {(cuuint64_t)a.c_in, (cuuint64_t)a.n_in};
+      cuuint64_t istr[1] = {(cuuint64_t)a.ld_in * 2};
+      cuuint32_t ibox[2] = {(cuuint32_t)bk, (cuuint32_t)TILE_M};
+      if (encode(&in_map, a.act_dtype == LB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                 const_cast<void*>(a.in), idim, istr, ibox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        lean = 2;
+    }
+  }
+
   TcParams p;
   p.in = (const char*)a.in; p.n_in = a.n_in; p.ld_in = a.ld_in;
   p.out = (char*)a.out; p.n_out = a.n_out; p.ld_out = a.ld_out;
@@ -993,7 +1316,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   int T = 1;
   {
     const size_t blk2 = (size_t)2 * TILE_M * bk * 2 + (((size_t)a.c_out * bk * 2 + 1023) & ~(size_t)1023);
-    const size_t budget2 = 227 * 1024 - 1024 - tail_bytes(2);
+    const size_t budget2 = 227 * 1024 - 1024 - tail_bytes(2, lean);
     static const int t2_min_stages = getenv("LIDAL_T2_MIN_STAGES") ? atoi(getenv("LIDAL_T2_MIN_STAGES")) : 4;
     static const int t2_min_waves = getenv("LIDAL_T2_MIN_WAVES") ? atoi(getenv("LIDAL_T2_MIN_WAVES")) : 8;
     if (tiles128 >= (int64_t)t2_min_waves * sm_count() && budget2 / blk2 >= (size_t)t2_min_stages && 2 * a.c_out <= 512) T = 2;
@@ -1005,7 +1328,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   // fits next to the ring (1x1 256->128: 0.27 ms with direct stores at T=2 vs 0.15 ms staged at T=1, measured)
   if (T == 2 && !pack8 && a.k_vol * (a.c_in / bk) < 5 && a.out_dtype != LB_DT_F32 && !(a.flags & LB_CONV_NO_STAGED_EPILOGUE)) {
     const size_t blk2 = (size_t)2 * TILE_M * bk * 2 + (((size_t)a.c_out * bk * 2 + 1023) & ~(size_t)1023);
-    const size_t budget2 = 227 * 1024 - 1024 - tail_bytes(2);
+    const size_t budget2 = 227 * 1024 - 1024 - tail_bytes(2, lean);
     const int bpt = a.k_vol * (a.c_in / bk);
     const size_t want = bpt < 3 ? 3 : bpt;
     if (budget2 <= staging_bytes(a.c_out) || (budget2 - staging_bytes(a.c_out)) / blk2 < want) T = 1;
@@ -1018,12 +1341,12 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.tmem_cols = cols;
   const int row_bytes = bk * 2;
   const size_t block_bytes = (size_t)T * TILE_M * row_bytes + (((size_t)a.c_out * row_bytes + 1023) & ~(size_t)1023);
-  const size_t budget = 227 * 1024 - 1024 - tail_bytes(T);
+  const size_t budget = 227 * 1024 - 1024 - tail_bytes(T, lean);
   // blocks per stage: measured on B200, carrying several blocks per stage (fewer, coarser stages) is not faster than
   // a deep ring of single-block stages -- the kernel is bound by L2 traffic, not by the per-stage hand-shake.
   // (round 2: with the weight warp, the per-stage hand-shake of the gather warps is the bound on the fine levels --
   // profiles/r02_conv_knockouts.txt -- so stages carry up to LIDAL_NB_MAX blocks wherever >= 3 such stages still fit)
-  static const int nb_max = getenv("LIDAL_NB_MAX") ? atoi(getenv("LIDAL_NB_MAX")) : 2;
+  static const int nb_max = getenv("LIDAL_NB_MAX") ? atoi(getenv("LIDAL_NB_MAX")) : 1;   // 1: the trimmed single-block gather path (round 2, second half)
   static const int prod_mode_env0 = getenv("LIDAL_PROD_MODE") ? atoi(getenv("LIDAL_PROD_MODE")) : 0;
   static const int wwarp_env0 = getenv("LIDAL_WEIGHT_WARP") ? atoi(getenv("LIDAL_WEIGHT_WARP")) : 1;
   int nb = 1;
@@ -1052,7 +1375,9 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
     // short K loops (1x1 layers) are pure epilogue: a second staging buffer per warp lets the copy engine drain one
     // sub-tile while the next one is converted (single-buffered, the warp idles for the store's read latency)
     static const bool no_dbuf = getenv("LIDAL_NO_STAGE_DBUF") != nullptr;
-    if (!no_dbuf && blocks_per_tile < 5 && budget > staging_bytes(a.c_out, 2) &&
+    // (with two epilogue groups working on alternate sub-tiles / tiles a second buffer per warp buys nothing: LIDAL_STAGE_DBUF=1 for A/B)
+    static const bool want_dbuf = getenv("LIDAL_STAGE_DBUF") != nullptr;
+    if (want_dbuf && !no_dbuf && blocks_per_tile < 5 && budget > staging_bytes(a.c_out, 2) &&
         (budget - staging_bytes(a.c_out, 2)) / stage_bytes >= (size_t)want_stages)
       p.stg_bufs = 2;
     budget_eff = budget - staging_bytes(a.c_out, p.stg_bufs);
@@ -1087,7 +1412,6 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.dbg = dbg_env;
   p.prod_mode = pack8 ? 0 : prod_mode_env;
   p.zero_row = 0; p.zero_mask = 0;
-  CUtensorMap in_map = map;                      // placeholder unless the TMA gather is used
   // TMA gather producer: needs a pool of all-zero rows right behind the input (absent neighbours are fetched from there),
   // a neighbour table (k_vol > 1 or permuted rows) and row indices that fit the tensor map's int32 coordinates
   if (!pack8 && tma_gather_env && a.nbr && a.in_pad_rows >= 16 && (a.in_pad_rows & (a.in_pad_rows - 1)) == 0 &&
@@ -1111,7 +1435,17 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   p.prod_warps = stages < NUM_PROD_THREADS / 32 ? stages : NUM_PROD_THREADS / 32;
   static const bool static_tiles = getenv("LIDAL_STATIC_TILES") != nullptr;   // A/B switch
   p.sched = static_tiles ? nullptr : (unsigned*)a.sched_ws;   // caller-owned, zeroed once, private to this stream
-  const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T) + (p.staged ? staging_bytes(a.c_out, p.stg_bufs) : 0) + 1024;
+  p.lean = lean;
+  p.tile_masks = a.tile_masks;
+  p.idx_bytes = (int)idx_bytes(T, lean);
+  static const int lean_arrive_env = getenv("LIDAL_LEAN_ARRIVE") ? atoi(getenv("LIDAL_LEAN_ARRIVE")) : 0;
+  static const int lean_lag_env = getenv("LIDAL_LEAN_LAG") ? atoi(getenv("LIDAL_LEAN_LAG")) : 3;
+  p.lean_arrive = (lean == 1 && lean_arrive_env && stages >= 3) ? 1 : 0;
+  p.lean_lag = stages - 2 < lean_lag_env ? stages - 2 : lean_lag_env;
+  if (p.lean_lag < 1) p.lean_lag = 1;
+  if (p.lean_lag > 3) p.lean_lag = 3;
+  if (lean) p.sched = nullptr;                   // static snake schedule: every role derives the tile sequence itself
+  const size_t smem = (size_t)stages * stage_bytes + tail_bytes(T, lean) + (p.staged ? staging_bytes(a.c_out, p.stg_bufs) : 0) + 1024;
   int64_t tiles = (a.n_out + (int64_t)T * TILE_M - 1) / ((int64_t)T * TILE_M);
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (grid < 1) grid = 1;
@@ -1143,12 +1477,12 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
 #undef LB_TC_LAUNCH
   LB_LAUNCH_CHECK();
   if ((DBG(p) & 128) && p.sched) {
-    unsigned long long h[12];
+    unsigned long long h[22];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, p.sched + 16, sizeof(h), cudaMemcpyDeviceToHost);
     cudaMemset(p.sched + 16, 0, sizeof(h));
-    fprintf(stderr, "[conv dbg] k=%d cin=%d cout=%d n=%lld T=%d stages=%d | mma: total %llu wait_full %llu wait_tempty %llu stages %llu | prod0: total %llu wait_empty %llu barA %llu barB %llu tiles %llu | epi0: total %llu wait_tstart %llu wait_tfull %llu\n",
-            a.k_vol, a.c_in, a.c_out, (long long)a.n_out, T, stages, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11]);
+    fprintf(stderr, "[conv dbg] k=%d cin=%d cout=%d n=%lld T=%d stages=%d | mma: total %llu wait_full %llu wait_tempty %llu stages %llu | prod0: total %llu wait_empty %llu barA %llu barB %llu tiles %llu | epi0: total %llu wait_tstart %llu wait_tfull %llu | fill latency (issue->landed, MMA blocked) %llu / %llu | drain latency (commit->free, gather blocked) %llu / %llu | mma segments: fence %llu issue %llu commit %llu | gather segments: ldgsts %llu close %llu\n",
+            a.k_vol, a.c_in, a.c_out, (long long)a.n_out, T, stages, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[15], h[13], h[14], h[16], h[17], h[18], h[19], h[20]);
   }
   return LB_OK;
 }

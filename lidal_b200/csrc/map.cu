@@ -825,6 +825,45 @@ extern "C" int lb_kmap_sort_by_mask_ld(const int32_t* nbr, int64_t nbr_ld, int64
   return LB_OK;
 }
 
+// ------------------------------------------------------------------------------------------ per-tile offset masks
+namespace lb {
+// one warp per 128-row group: lane l owns rows 4 l .. 4 l + 3 (one 16-byte load per offset when the table rows are aligned)
+__global__ void kmap_tile_masks_kernel(const int* __restrict__ nbr, int64_t ld, int64_t n, int k, uint32_t* __restrict__ out,
+                                       int64_t groups, int vec_ok) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += warps) {
+    const int64_t o = g * 128 + lane * 4;
+    uint32_t m = 0;
+    for (int j = 0; j < k; ++j) {
+      const int* src = nbr + (int64_t)j * ld + o;
+      bool any = false;
+      if (vec_ok && o + 3 < n) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(src));
+        any = (v.x >= 0) | (v.y >= 0) | (v.z >= 0) | (v.w >= 0);
+      } else {
+        for (int u = 0; u < 4; ++u)
+          if (o + u < n && __ldg(src + u) >= 0) any = true;
+      }
+      m |= (uint32_t)any << j;
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (lane == 0) out[g] = m;
+  }
+}
+}  // namespace lb
+extern "C" int lb_kmap_tile_masks(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, uint32_t* tile_masks, void* stream) {
+  LB_CHECK_ARG(n_out >= 0 && k > 0 && k <= 32 && nbr_ld >= n_out, "bad arguments");
+  if (n_out == 0) return LB_OK;
+  LB_CHECK_ARG(nbr && tile_masks, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int64_t groups = (n_out + 127) / 128;
+  const int vec_ok = ((nbr_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(nbr) & 15) == 0) ? 1 : 0;
+  kmap_tile_masks_kernel<<<grid_for(groups * 32, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, tile_masks, groups, vec_ok); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
 // ------------------------------------------------------------------------------------------ hash group-by (engine)
 // Groups equal keys without sorting: the group of a key is owned by its smallest row (atomicMin in the table), groups
 // are numbered in order of their owner row (exclusive scan) -> deterministic, first-occurrence order.

@@ -93,7 +93,8 @@ class _Conv:
             self.w = F.pack_weight(w.float(), dtype)
         self.relu = relu
 
-    def __call__(self, x, nbr, n_out, out=None, residual=None, out_dtype=None, relu_first=False):
+    def __call__(self, x, nbr, n_out, out=None, residual=None, out_dtype=None, relu_first=False, no_lean=False):
+        tile_masks = getattr(nbr, "tile_masks", None)
         nbr, out_rows = nbr if isinstance(nbr, tuple) else (nbr, None)
         out_dtype = out_dtype or x.dtype
         if out is None:
@@ -112,9 +113,10 @@ class _Conv:
         a.act_dtype, a.out_dtype = L.DT_OF[x.dtype], L.DT_OF[out.dtype]
         a.flags = ((L.LB_CONV_RELU if self.relu else 0) | (L.LB_CONV_RELU_FIRST if relu_first else 0)
                    | (L.LB_CONV_PACK8 if self.pack8 else 0) | (L.LB_CONV_TILE128 if FORCE_TILE128 else 0)
-                   | (L.LB_CONV_NO_STAGED if NO_STAGED else 0))
+                   | (L.LB_CONV_NO_STAGED if NO_STAGED else 0) | (L.LB_CONV_NO_LEAN if no_lean else 0))
         a.sched_ws = L.conv_sched_ws()
         a.in_pad_rows = _pad_rows(x) if nbr is not None else 0
+        a.tile_masks = tile_masks.data_ptr() if tile_masks is not None else None
         trace = F.CONV_TRACE
         ev = trace.begin() if trace is not None else None
         L.check(L.lib().lb_conv_fwd(C.byref(a), L.stream()))
@@ -143,6 +145,7 @@ import os as _os
 FORCE_TILE128 = bool(int(_os.environ.get('LIDAL_TILE128', '0')))   # A/B switch: 128-row CTA tiles everywhere
 NO_STAGED = bool(int(_os.environ.get('LIDAL_NO_STAGED', '0')))       # A/B switch: per-thread epilogue stores
 SORT_MAPS = True        # group rows by neighbour mask (tile-level offset skipping); False = natural row order
+TILE_MASKS = bool(int(_os.environ.get('LIDAL_TILE_MASKS', '1')))    # A/B switch: per-tile offset masks (prologue-free conv producer)
 
 
 def _offsets(ks, stride, dev):
@@ -236,6 +239,24 @@ def _counters(dev) -> _HostCounters:
     return _COUNTERS[key]
 
 
+class SortedMap(tuple):
+    """(nbr_sorted, perm) of a mask-sorted kernel map, plus ``tile_masks``: the active-offset mask of every 128-row group
+    (lb_kmap_tile_masks), which lets lb_conv_fwd run without its per-tile prologue."""
+
+    def __new__(cls, table, perm, tile_masks=None):
+        self = super().__new__(cls, (table, perm))
+        self.tile_masks = tile_masks
+        return self
+
+
+def tile_masks_of(table):
+    """uint32 (stored as int32) [ceil(n / 128)]: bit k = some row of the 128-row group has a neighbour at offset k."""
+    k, n = table.shape
+    tm = torch.empty(max((n + 127) // 128, 1), dtype=torch.int, device=table.device)
+    L.check(L.lib().lb_kmap_tile_masks(L.ptr(table), table.stride(0), n, k, L.ptr(tm), L.stream()))
+    return tm
+
+
 def _mask_sorted(nbr):
     """(nbr_sorted, perm): rows grouped by neighbour mask so 128-row tiles skip absent offsets (lb_kmap_sort_by_mask)."""
     k, n = nbr.shape
@@ -246,7 +267,7 @@ def _mask_sorted(nbr):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=nbr.device)
     L.check(L.lib().lb_kmap_sort_by_mask_ld(L.ptr(nbr), nbr.stride(0), n, k, L.ptr(perm), L.ptr(out), ld, L.ptr(ws), nbytes,
                                             L.stream()))
-    return out, perm
+    return SortedMap(out, perm, tile_masks_of(out) if TILE_MASKS else None)
 
 
 class Maps:
@@ -548,6 +569,8 @@ class Prepared:
             for item in group:
                 for t in (item if isinstance(item, tuple) else (item,)):
                     yield t._base if t._base is not None else t
+                if getattr(item, "tile_masks", None) is not None:
+                    yield item.tile_masks
         for t in (self.feats, self.zc):
             if t is not None:
                 yield t

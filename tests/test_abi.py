@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_python_binding_covers_header():
     assert sorted(_lib.SIGNATURES) == declared_symbols()
-    assert _lib.lib().lb_abi_version() == 2
+    assert _lib.lib().lb_abi_version() == 3
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -55,7 +55,7 @@ def test_struct_layouts_match_header(tmp_path):
         assert got[(cname, "sizeof")] == ctypes.sizeof(ct), cname
         for fname, _t in ct._fields_:
             assert got[(cname, fname)] == getattr(ct, fname).offset, (cname, fname)
-    assert got[("lb_conv_args", "sizeof")] == 168 and got[("lb_frame_ref", "sizeof")] == 32
+    assert got[("lb_conv_args", "sizeof")] == 176 and got[("lb_frame_ref", "sizeof")] == 32
 
 
 def test_no_cpu_fallback():
