@@ -24,6 +24,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Batches differ by a few per cent in voxel count, so PyTorch's caching allocator kept splitting cached blocks for slightly
+# smaller requests and then had to cudaMalloc for the next slightly larger one -- three cudaMalloc calls per 20 steps, each
+# blocking the launch loop for 10-110 ms on a busy GPU (profiles/r02_host_stalls.txt).  Size classes of 1/8 octave make the
+# blocks of consecutive batches interchangeable; must be set before the first CUDA allocation.
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:8")
 
 import numpy as np
 import torch
@@ -421,20 +426,46 @@ def main():
         stream_pipe = StreamPipeline(eng)        # maps of batch i+1 are built on a side stream while batch i's network runs
     step = (lambda c, f: stream_pipe.submit(c, f, wait_main=False)) if stream_pipe is not None else run   # resident inputs: complete
     clk = ClockSampler(local_rank)               # NVML attached before warm-up
+    # allocator priming (untimed, before the W warm-up steps): every distinct batch twice, so that the caching allocator's
+    # per-stream pools hold the resident set of the rotation and no cudaMalloc lands in the timed region
+    for i in range(2 * len(resident)):
+        step(*resident[i % len(resident)])
     for i in range(args.warmup):
         step(*resident[i % len(resident)])
     barrier()
 
+    # The timed regions are short (K steps of ~8 ms): one generation-2 pass of Python's cyclic garbage collector over the
+    # process's object graph (~0.1-0.2 s here) inside such a window doubled the measured step time in about one run out of
+    # seven.  The launch loop creates no reference cycles, so the collector is parked for the timed regions (objects are
+    # still freed by reference counting) -- what a serving loop does as well; per-step host times are recorded so that a
+    # host-side stall would show up in the JSON line (`host_loop`).
+    import gc
+    gc.collect()
+    gc.freeze()
+    gc.disable()
+    host_t = []
+
     # ---- value: inputs resident in HBM
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.lib().lb_launch_count()
+    worst = {"ms": 0.0}
+    mem0 = torch.cuda.memory_stats(dev)
     with clk:
         barrier()
         e0.record()
         for i in range(args.steps):
+            t_h = time.perf_counter()
             step(*resident[i % len(resident)])
+            dt = time.perf_counter() - t_h
+            host_t.append(dt)
+            if dt * 1e3 > worst["ms"] and stream_pipe is not None:
+                worst = {"ms": dt * 1e3, "step": i, "prepare_forward_retire_ms": [round(v, 2) for v in stream_pipe.last_host_ms]}
         e1.record()
         barrier()
+    mem1 = torch.cuda.memory_stats(dev)
+    host_value = sorted(host_t)
+    worst["cudaMalloc_in_region"] = mem1["num_device_alloc"] - mem0["num_device_alloc"]
+    worst["cudaFree_in_region"] = mem1["num_device_free"] - mem0["num_device_free"]
     launches = int(L.lib().lb_launch_count() - launches0)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -451,8 +482,11 @@ def main():
         barrier()
         e0.record()
         n_done = 0
+        host_t = []
         for i in range(args.steps):
+            t_h = time.perf_counter()
             n_done += len(pipe.submit(*host[i % len(host)]))      # H2D (pinned) + forward + D2H of the logits, pipelined
+            host_t.append(time.perf_counter() - t_h)
         n_done += len(pipe.collect())
         e1.record()
         barrier()
@@ -473,6 +507,9 @@ def main():
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms2.item())
+    gc.enable()
+    gc.unfreeze()
+    host_e2e = sorted(host_t)
     h2d = int(np.mean([c.numel() * 4 + f.numel() * 4 for c, f in host]))
     d2h = int(np.mean(n_vox)) * N_CLS * 4
 
@@ -486,6 +523,10 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clk.summary(),
         "voxels_per_step": int(np.mean(n_vox)),
+        "host_loop": {"value_step_ms_median": 1e3 * host_value[len(host_value) // 2], "value_step_ms_max": 1e3 * host_value[-1],
+                      "e2e_step_ms_median": 1e3 * host_e2e[len(host_e2e) // 2], "e2e_step_ms_max": 1e3 * host_e2e[-1],
+                      "value_worst_step": worst,
+                      "note": "host wall time per submit; cyclic GC parked during the timed regions"},
     }
 
     lidal = None

@@ -91,6 +91,7 @@ struct TcParams {
                            // cp.async.wait_group + a writer-side proxy fence
   int lean_lag;            // stages a warp keeps unpublished (1..3, < stages - 1)
   int idx_bytes;           // shared memory reserved for s_idx (0 in lean mode: the bytes go to the ring)
+  int fastpro;             // short per-tile prologue: offset masks from tile_masks, index rows staged unchecked (see the gather warps)
 };
 
 // Bottleneck-hunting switches (knock-outs, cycle accounting) exist only in a -DLIDAL_CONV_DEBUG build: in the production
@@ -446,8 +447,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     constexpr int ITEMS = (KMAX * R4 + NUM_PROD_THREADS - 1) / NUM_PROD_THREADS;
     int4 nb_reg[ITEMS];
     const bool vec_ok = p.nbr && (p.nbr_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.nbr) & 15) == 0;
+    // Short prologue (p.fastpro: the caller supplied the tile-mask table, so the table is one this library built and its
+    // entries are -1 or valid rows): the tile's offset mask is ONE prefetched word instead of compares, a warp reduction, a
+    // shared-memory atomic and a re-read; the index rows of full tiles are fetched with per-thread constant offsets (running
+    // pointer, no division, no bounds tests) and staged as they are.  ~60 instructions per tile instead of ~350 -- on the
+    // 32-channel layers the prologue was longer than the tile's main loop.
+    constexpr int KJ = NUM_PROD_THREADS / R4;             // offsets advanced per work item
+    const int k_t = t / R4;                               // offset of this thread's item 0
+    const int64_t f_step = (int64_t)KJ * p.nbr_ld;        // ints between consecutive items of a thread
+    const int* f_base = p.nbr ? p.nbr + (int64_t)k_t * p.nbr_ld + (t % R4) * 4 : nullptr;
+    int* const st_base = s_idx + k_t * TM + (t % R4) * 4;
+    uint32_t mask_next = 0;                               // fastpro: mask of the tile whose indices sit in nb_reg
+    const int n_groups128_p = (int)((n_out + TILE_M - 1) / TILE_M);
+    auto table_mask = [&](int64_t tile) -> uint32_t {
+      uint32_t m = __ldg(p.tile_masks + tile * T);
+      if (T == 2 && tile * 2 + 1 < n_groups128_p) m |= __ldg(p.tile_masks + tile * 2 + 1);
+      if (p.k_vol < 32) m &= (1u << p.k_vol) - 1u;
+      return m;
+    };
     auto fetch_indices = [&](int64_t tile) {
       const int64_t o0 = tile * TM;
+      if (p.fastpro) {
+        mask_next = table_mask(tile);
+        if (o0 + TM <= n_out) {                           // full tile: no bounds tests
+          const int* src = f_base + o0;
+#pragma unroll
+          for (int j = 0; j < ITEMS; ++j) {
+            if (k_t + j * KJ < KMAX && k_t + j * KJ < p.k_vol) nb_reg[j] = __ldg(reinterpret_cast<const int4*>(src));
+            src += f_step;
+          }
+          return;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         const int q = t + j * NUM_PROD_THREADS;
@@ -491,6 +522,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");
       if (dbg_me) { DBG_ADD(6, clock64() - dbg_t); DBG_ADD(8, 1); }
       uint32_t my_bits = 0;
+      if (p.fastpro) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+          if (k_t + j * KJ < KMAX && k_t + j * KJ < p.k_vol) *reinterpret_cast<int4*>(st_base + j * KJ * TM) = nb_reg[j];
+      } else
 #pragma unroll
       for (int j = 0; j < ITEMS; ++j) {
         const int q = t + j * NUM_PROD_THREADS;
@@ -510,8 +546,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
           if (ox | oy | oz | ow) my_bits |= 1u << k;
         }
       }
-      const uint32_t my_mask = __reduce_or_sync(0xffffffffu, my_bits);   // one warp reduction instead of a vote per offset
-      if (lane == 0 && my_mask) atomicOr(&s_mask[par], my_mask);
+      if (!p.fastpro) {
+        const uint32_t my_mask = __reduce_or_sync(0xffffffffu, my_bits);   // one warp reduction instead of a vote per offset
+        if (lane == 0 && my_mask) atomicOr(&s_mask[par], my_mask);
+      }
       if (t == 0) {
         s_mask[par ^ 1] = 0;
         const int64_t nx = p.sched ? (int64_t)gridDim.x + ahead : cur + gridDim.x;
@@ -522,7 +560,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
       dbg_t = dbg_me ? clock64() : 0;
       asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");
       if (dbg_me) DBG_ADD(7, clock64() - dbg_t);
-      uint32_t mask = __reduce_or_sync(0xffffffffu, s_mask[par]);   // same value in every lane; REDUX makes it provably uniform
+      uint32_t mask = __reduce_or_sync(0xffffffffu, p.fastpro ? mask_next : s_mask[par]);   // same value in every lane; REDUX makes it provably uniform
       if (mask == 0) mask = 1;                            // keep the pipeline uniform: one all-zero k-block
       const int nx = (int)__reduce_or_sync(0xffffffffu, (uint32_t)s_next[0]);   // stable until barrier (A) of the next tile
       if (nx >= 0) fetch_indices(tile_of(nx));
@@ -792,13 +830,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap w_map, const __grid_constant_
     const uint32_t ring_u32 = st_u32;
     int64_t cur = blockIdx.x;
     uint32_t par = 0;
+    const int n_groups128_w = (int)((n_out + TILE_M - 1) / TILE_M);
+    auto table_mask = [&](int64_t tile) -> uint32_t {
+      uint32_t m = __ldg(p.tile_masks + tile * T);
+      if (T == 2 && tile * 2 + 1 < n_groups128_w) m |= __ldg(p.tile_masks + tile * 2 + 1);
+      if (p.k_vol < 32) m &= (1u << p.k_vol) - 1u;
+      return m;
+    };
+    uint32_t mask_w = (p.fastpro && cur < num_tiles) ? table_mask(tile_of(cur)) : 0u;   // fastpro: mask of the current tile, fetched a tile ahead
     for (; cur < num_tiles; par ^= 1) {
       const int64_t tile = tile_of(cur);
       asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");   // (A)
       asm volatile("bar.sync 1, %0;" ::"n"(PROD_BAR_THREADS) : "memory");   // (B)
-      uint32_t mask = __reduce_or_sync(0xffffffffu, s_mask[par]);
+      uint32_t mask = __reduce_or_sync(0xffffffffu, p.fastpro ? mask_w : s_mask[par]);
       if (mask == 0) mask = 1;
       const int nx = (int)__reduce_or_sync(0xffffffffu, (uint32_t)s_next[0]);
+      if (p.fastpro && nx >= 0) mask_w = table_mask(tile_of(nx));
       if (p.wwarp) {
         int remaining = __popc(mask) * kc_blocks;         // blocks of this tile
         const int cur_word = (int)((uint32_t)tile | ((uint32_t)remaining << 24));
@@ -1346,7 +1393,7 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   // a deep ring of single-block stages -- the kernel is bound by L2 traffic, not by the per-stage hand-shake.
   // (round 2: with the weight warp, the per-stage hand-shake of the gather warps is the bound on the fine levels --
   // profiles/r02_conv_knockouts.txt -- so stages carry up to LIDAL_NB_MAX blocks wherever >= 3 such stages still fit)
-  static const int nb_max = getenv("LIDAL_NB_MAX") ? atoi(getenv("LIDAL_NB_MAX")) : 1;   // 1: the trimmed single-block gather path (round 2, second half)
+  static const int nb_max = getenv("LIDAL_NB_MAX") ? atoi(getenv("LIDAL_NB_MAX")) : 2;   // measured: 1 -> 4.97, 2 -> 4.92, 3 -> 4.89 ms of conv per step
   static const int prod_mode_env0 = getenv("LIDAL_PROD_MODE") ? atoi(getenv("LIDAL_PROD_MODE")) : 0;
   static const int wwarp_env0 = getenv("LIDAL_WEIGHT_WARP") ? atoi(getenv("LIDAL_WEIGHT_WARP")) : 1;
   int nb = 1;
@@ -1436,6 +1483,9 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   static const bool static_tiles = getenv("LIDAL_STATIC_TILES") != nullptr;   // A/B switch
   p.sched = static_tiles ? nullptr : (unsigned*)a.sched_ws;   // caller-owned, zeroed once, private to this stream
   p.lean = lean;
+  static const int fastpro_env = getenv("LIDAL_FASTPRO") ? atoi(getenv("LIDAL_FASTPRO")) : 1;   // A/B switch
+  p.fastpro = (fastpro_env && !lean && !pack8 && a.nbr && a.tile_masks && !a.n_out_dev && !(a.flags & LB_CONV_NO_LEAN) &&
+               a.n_out < ((int64_t)1 << 30) && (a.nbr_ld & 3) == 0 && ((uintptr_t)a.nbr & 15) == 0) ? 1 : 0;
   p.tile_masks = a.tile_masks;
   p.idx_bytes = (int)idx_bytes(T, lean);
   static const int lean_arrive_env = getenv("LIDAL_LEAN_ARRIVE") ? atoi(getenv("LIDAL_LEAN_ARRIVE")) : 0;

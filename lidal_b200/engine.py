@@ -142,6 +142,7 @@ class _Res:
 
 _OFFSETS = {}
 import os as _os
+import time as _time
 FORCE_TILE128 = bool(int(_os.environ.get('LIDAL_TILE128', '0')))   # A/B switch: 128-row CTA tiles everywhere
 NO_STAGED = bool(int(_os.environ.get('LIDAL_NO_STAGED', '0')))       # A/B switch: per-thread epilogue stores
 SORT_MAPS = True        # group rows by neighbour mask (tile-level offset skipping); False = natural row order
@@ -578,6 +579,24 @@ class Prepared:
             yield from q
 
 
+_ALLOC_CLASSES_SET = False
+
+
+def _allocator_size_classes():
+    """Consecutive batches differ by a few per cent in size; with exact-size blocks the caching allocator keeps splitting a
+    cached block for the smaller request and calling cudaMalloc for the next larger one, and a cudaMalloc on a busy GPU blocks
+    the launch loop for 10-110 ms (profiles/r02_host_stalls.txt).  Size classes of 1/8 octave make the blocks interchangeable.
+    Respected if the user configured the allocator already (PYTORCH_CUDA_ALLOC_CONF)."""
+    global _ALLOC_CLASSES_SET
+    if _ALLOC_CLASSES_SET or _os.environ.get("PYTORCH_CUDA_ALLOC_CONF"):
+        return
+    _ALLOC_CLASSES_SET = True
+    try:
+        torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:8")
+    except Exception:          # noqa: BLE001 -- older / different allocator back ends: keep their behaviour
+        pass
+
+
 class StreamPipeline:
     """Streams batches through the engine with the host round trips off the critical path: ``prepare`` of batch i runs on a
     side stream (its row-count read-backs block the host only), ``forward`` of batch i on the caller's stream.  Because
@@ -589,6 +608,10 @@ class StreamPipeline:
         self.engine = engine
         self.prep_stream = torch.cuda.Stream(device=engine.device)
         self._live = collections.deque()
+        self.last_host_ms = (0.0, 0.0, 0.0)
+        _allocator_size_classes()
+
+
 
     def prepare(self, coords, feats, after=None, wait_main=True) -> Prepared:
         """``after``: event that makes the inputs valid (e.g. their H2D copy); else ``wait_main`` orders the side stream behind
@@ -616,10 +639,14 @@ class StreamPipeline:
             self._live.popleft()
 
     def submit(self, coords, feats, return_feat=False, after=None, wait_main=True):
+        t0 = _time.perf_counter()
         pr = self.prepare(coords, feats, after, wait_main)
+        t1 = _time.perf_counter()
         torch.cuda.current_stream(self.engine.device).wait_event(pr.ready)
         out = self.engine.forward(pr, return_feat)
+        t2 = _time.perf_counter()
         self.retire(pr)
+        self.last_host_ms = ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (_time.perf_counter() - t2) * 1e3)   # prepare, forward, retire
         return out
 
 
