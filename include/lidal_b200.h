@@ -104,6 +104,11 @@ int lb_kmap_sort_by_mask_ld(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, i
  * Built once per map and passed to every convolution that uses it (lb_conv_args.tile_masks). */
 int lb_kmap_tile_masks(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, uint32_t* tile_masks, void* stream);
 
+/* lb_kmap_sort_by_mask_ld that also emits the tile masks of the SORTED table (tile_masks uint32 [ceil(n_out / 128)], may be
+ * NULL) from the per-row masks it already holds -- 4 bytes per row instead of a second pass over the table. */
+int lb_kmap_sort_by_mask_tm(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm, int32_t* nbr_sorted,
+                            int64_t sorted_ld, uint32_t* tile_masks, void* ws, size_t ws_bytes, void* stream);
+
 /* Per-offset inverse of a neighbour table (transposed convolution / dgrad roles):
  * nbr int32 [k, nbr_ld] with values in [0, n_in) or -1  ->  nbr_t int32 [k, n_in], nbr_t[k][nbr[k][o]] = o. */
 int lb_kmap_transpose(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* nbr_t, int64_t n_in,
@@ -129,6 +134,13 @@ int lb_group_by_key(const int64_t* keys, int64_t n, int32_t* inverse, int32_t* f
 size_t lb_downsample_maps_ws_bytes(int64_t n);
 int lb_downsample_maps(const int32_t* coords, int64_t n, int tensor_stride, int32_t* out_coords, int32_t* n_out,
                        int32_t* nbr_dn, int64_t ld_dn, int32_t* nbr_up, void* ws, size_t ws_bytes, void* stream);
+
+/* Row counts of all coarser levels in one pass: counts[l-1] = number of distinct parents (coords / 2^l * 2^l, same 60-bit
+ * hash identity as lb_downsample_maps) for l = 1..levels (<= 16).  coords int32 [n,4] >= 0, any row multiplicity (points
+ * or voxels).  counts may point into pinned host memory: a caller learns the size of the whole pyramid in ONE round trip
+ * before building it (lb_downsample_maps reports the same numbers level by level). */
+size_t lb_level_counts_ws_bytes(int64_t n, int levels);
+int lb_level_counts(const int32_t* coords, int64_t n, int levels, int32_t* counts, void* ws, size_t ws_bytes, void* stream);
 
 /* Stable LSD radix sort of (uint64 key, uint32 value) pairs on bits [0, end_bit). */
 size_t lb_sort_pairs_ws_bytes(int64_t n);

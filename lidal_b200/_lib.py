@@ -53,6 +53,7 @@ SIGNATURES = {
     "lb_kmap_sort_ws_bytes": (sz, [i64]),
     "lb_kmap_sort_by_mask": (i32, [vp, i64, i64, i32, vp, vp, vp, sz, vp]),
     "lb_kmap_sort_by_mask_ld": (i32, [vp, i64, i64, i32, vp, vp, i64, vp, sz, vp]),
+    "lb_kmap_sort_by_mask_tm": (i32, [vp, i64, i64, i32, vp, vp, i64, vp, vp, sz, vp]),
     "lb_kmap_transpose": (i32, [vp, i64, i64, i32, vp, i64, vp]),
     "lb_kmap_tile_masks": (i32, [vp, i64, i64, i32, vp, vp]),
     "lb_unique_ws_bytes": (sz, [i64]),
@@ -61,6 +62,8 @@ SIGNATURES = {
     "lb_group_by_key": (i32, [vp, i64, vp, vp, vp, vp, sz, vp]),
     "lb_downsample_maps_ws_bytes": (sz, [i64]),
     "lb_downsample_maps": (i32, [vp, i64, i32, vp, vp, vp, i64, vp, vp, sz, vp]),
+    "lb_level_counts_ws_bytes": (sz, [i64, i32]),
+    "lb_level_counts": (i32, [vp, i64, i32, vp, vp, sz, vp]),
     "lb_sort_pairs_ws_bytes": (sz, [i64]),
     "lb_sort_pairs": (i32, [vp, vp, i64, i32, vp, sz, vp]),
     "lb_conv_pack_weight": (i32, [vp, i32, i32, i32, i32, vp, vp]),
@@ -143,8 +146,21 @@ def ptr(t: torch.Tensor | None):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
+def stream_handle() -> int:
+    """cudaStream_t of the current device's current stream.  Called once per launch (~240 times per step), so it takes
+    torch's C entry points directly: ``torch.cuda.current_stream()`` builds a Stream object through several Python layers
+    (~10 us per call, 2 ms of host time per step)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
+    return torch.cuda.current_stream().cuda_stream
+
+
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(stream_handle())
 
 
 _SCHED_CELLS: dict = {}
@@ -153,8 +169,8 @@ _SCHED_CELLS: dict = {}
 def conv_sched_ws():
     """The tile-scheduler scratch of lb_conv_fwd for the current (device, stream): allocated and zeroed once, then reused
     (the kernel leaves it zeroed; launches on one stream are ordered).  Returns a raw device pointer."""
-    dev = torch.cuda.current_device()
-    key = (dev, torch.cuda.current_stream().cuda_stream)
+    dev = _raw_device() if _raw_device is not None else torch.cuda.current_device()
+    key = (dev, stream_handle())
     cell = _SCHED_CELLS.get(key)
     if cell is None:
         cell = torch.zeros(lib().lb_conv_sched_ws_bytes() // 4, dtype=torch.int32, device=f"cuda:{dev}")

@@ -787,6 +787,22 @@ __global__ void ks_permute(const int* __restrict__ nbr, int64_t ld, int64_t n, i
     out[(int64_t)j * out_ld + i] = __ldg(&nbr[(int64_t)j * ld + __ldg(&perm[i])]);
   }
 }
+// tile mask g = OR of the row masks of sorted rows [128 g, 128 g + 128): one warp per group, 4 rows per lane
+__global__ void ks_tile_masks(const uint32_t* __restrict__ masks, const int* __restrict__ perm, int64_t n, int64_t groups,
+                              uint32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += warps) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = g * 128 + u * 32 + lane;
+      if (i < n) m |= __ldg(&masks[__ldg(&perm[i])]);
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (lane == 0) out[g] = m;
+  }
+}
 }  // namespace lb
 extern "C" size_t lb_kmap_sort_ws_bytes(int64_t n) {
   if (n < 1) n = 1;
@@ -796,10 +812,18 @@ extern "C" int lb_kmap_sort_by_mask(const int32_t* nbr, int64_t nbr_ld, int64_t 
                                     int32_t* nbr_sorted, void* ws, size_t ws_bytes, void* stream) {
   return lb_kmap_sort_by_mask_ld(nbr, nbr_ld, n_out, k, perm, nbr_sorted, n_out, ws, ws_bytes, stream);
 }
+extern "C" int lb_kmap_sort_by_mask_tm(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm,
+                                       int32_t* nbr_sorted, int64_t sorted_ld, uint32_t* tile_masks, void* ws, size_t ws_bytes,
+                                       void* stream);
 extern "C" int lb_kmap_sort_by_mask_ld(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm,
                                        int32_t* nbr_sorted, int64_t sorted_ld, void* ws, size_t ws_bytes, void* stream) {
+  return lb_kmap_sort_by_mask_tm(nbr, nbr_ld, n_out, k, perm, nbr_sorted, sorted_ld, nullptr, ws, ws_bytes, stream);
+}
+extern "C" int lb_kmap_sort_by_mask_tm(const int32_t* nbr, int64_t nbr_ld, int64_t n_out, int k, int32_t* perm,
+                                       int32_t* nbr_sorted, int64_t sorted_ld, uint32_t* tile_masks, void* ws, size_t ws_bytes,
+                                       void* stream) {
   LB_CHECK_ARG(n_out >= 0 && k > 0 && k <= 32 && nbr_ld >= n_out && sorted_ld >= n_out && ws, "bad arguments");
-  if (ws_bytes < lb_kmap_sort_ws_bytes(n_out)) { set_error("lb_kmap_sort_by_mask_ld: workspace too small"); return LB_ECAP; }
+  if (ws_bytes < lb_kmap_sort_ws_bytes(n_out)) { set_error("lb_kmap_sort_by_mask: workspace too small"); return LB_ECAP; }
   if (n_out == 0) return LB_OK;
   LB_CHECK_ARG(nbr && perm && nbr_sorted, "null pointer");
   cudaStream_t st = as_stream(stream);
@@ -821,6 +845,10 @@ extern "C" int lb_kmap_sort_by_mask_ld(const int32_t* nbr, int64_t nbr_ld, int64
   int rc = lb_sort_pairs(keys, (uint32_t*)perm, n_out, k - drop + chunk_bits, sort_ws, lb_sort_pairs_ws_bytes(n_out), stream);
   if (rc != LB_OK) return rc;
   ks_permute<<<grid_for(n_out * k, 256), 256, 0, st>>>(nbr, nbr_ld, n_out, k, perm, nbr_sorted, sorted_ld); LB_LAUNCHED(1);
+  if (tile_masks) {          // the row masks are still in the workspace: 4 bytes per row instead of re-reading the table
+    const int64_t groups = (n_out + 127) / 128;
+    ks_tile_masks<<<grid_for(groups * 32, 256), 256, 0, st>>>(masks, perm, n_out, groups, tile_masks); LB_LAUNCHED(1);
+  }
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -930,6 +958,64 @@ extern "C" int lb_group_by_key(const int64_t* keys, int64_t n, int32_t* inverse,
   rc = exclusive_scan_u32(flags, pos, n, (uint32_t*)n_groups, scan_ws, st);
   if (rc != LB_OK) return rc;
   gb_emit<<<g, 256, 0, st>>>(flags, pos, owner, n, inverse, first_row); LB_LAUNCHED(1);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ row counts of all levels
+// How many voxels will every coarser level have?  unique (coords / 2^l * 2^l) for l = 1..levels, counted by inserting the
+// SAME 60-bit hashes lb_downsample_maps groups by into one key-only table per level.  It lets a caller learn every row
+// count of the pyramid in ONE host round trip (before building anything) instead of one round trip per level.
+namespace lb {
+__global__ void level_counts_kernel(const int4* __restrict__ coords, int64_t n, int levels, unsigned long long* __restrict__ tables,
+                                    uint64_t cap, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_pad = (n + 31) & ~(int64_t)31;            // whole warps stay converged for the ballots
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = i < n ? __ldg(&coords[i]) : make_int4(0, 0, 0, 0);
+    for (int l = 1; l <= levels; ++l) {
+      const int s = 1 << l;
+      bool fresh = false;
+      if (i < n) {
+        const unsigned long long key = (unsigned long long)fnv60(c.x / s * s, c.y / s * s, c.z / s * s, c.w);
+        unsigned long long* t = tables + (uint64_t)(l - 1) * cap;
+        uint64_t slot = mix64(key) & (cap - 1);
+        while (true) {
+          const unsigned long long prev = atomicCAS(&t[slot], LB_EMPTY_KEY, key);
+          if (prev == LB_EMPTY_KEY) { fresh = true; break; }
+          if (prev == key) break;
+          slot = (slot + 1) & (cap - 1);
+        }
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, fresh);
+      if (lane == 0 && b) atomicAdd(&counts[l - 1], __popc(b));
+    }
+  }
+}
+__global__ void level_counts_publish(const int* __restrict__ dev_counts, int levels, int* __restrict__ out) {
+  if ((int)threadIdx.x < levels) out[threadIdx.x] = dev_counts[threadIdx.x];
+}
+}  // namespace lb
+extern "C" size_t lb_level_counts_ws_bytes(int64_t n, int levels) {
+  if (n < 1) n = 1;
+  if (levels < 1) levels = 1;
+  return (size_t)levels * table_capacity(n) * 8 + 256;
+}
+extern "C" int lb_level_counts(const int32_t* coords, int64_t n, int levels, int32_t* counts, void* ws, size_t ws_bytes,
+                               void* stream) {
+  LB_CHECK_ARG(n >= 0 && levels >= 1 && levels <= 16 && counts && ws, "bad arguments");
+  if (ws_bytes < lb_level_counts_ws_bytes(n, levels)) { set_error("lb_level_counts: workspace too small"); return LB_ECAP; }
+  cudaStream_t st = as_stream(stream);
+  const uint64_t cap = table_capacity(n);
+  int* dev_counts = (int*)ws;
+  unsigned long long* tables = (unsigned long long*)((char*)ws + 256);
+  LB_CUDA(cudaMemsetAsync(dev_counts, 0, 256, st));
+  if (n > 0) {
+    LB_CHECK_ARG(coords, "null coords");
+    LB_CUDA(cudaMemsetAsync(tables, 0xFF, (size_t)levels * cap * 8, st));
+    level_counts_kernel<<<grid_for(n, 256), 256, 0, st>>>((const int4*)coords, n, levels, tables, cap, dev_counts); LB_LAUNCHED(1);
+  }
+  level_counts_publish<<<1, 32, 0, st>>>(dev_counts, levels, counts); LB_LAUNCHED(1);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

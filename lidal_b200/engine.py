@@ -146,6 +146,7 @@ import time as _time
 FORCE_TILE128 = bool(int(_os.environ.get('LIDAL_TILE128', '0')))   # A/B switch: 128-row CTA tiles everywhere
 NO_STAGED = bool(int(_os.environ.get('LIDAL_NO_STAGED', '0')))       # A/B switch: per-thread epilogue stores
 SORT_MAPS = True        # group rows by neighbour mask (tile-level offset skipping); False = natural row order
+PREP_PRIORITY = int(_os.environ.get('LIDAL_PREP_PRIORITY', '-1'))   # CUDA stream priority of the map-construction stream (A/B: 0 = default)
 TILE_MASKS = bool(int(_os.environ.get('LIDAL_TILE_MASKS', '1')))    # A/B switch: per-tile offset masks (prologue-free conv producer)
 
 
@@ -161,7 +162,7 @@ class _HostCounters:
     one costs an event wait -- not a 4-byte D2H copy, which would queue on the copy engine behind the logits download of
     the previous step (HostPipeline) and stall map construction for milliseconds."""
 
-    def __init__(self, slots: int = 8):
+    def __init__(self, slots: int = 16):
         self.buf = torch.zeros(slots, dtype=torch.int32).pin_memory()
         self.ev = torch.cuda.Event()
 
@@ -266,18 +267,36 @@ def _mask_sorted(nbr):
     out = torch.empty((k, ld), dtype=torch.int, device=nbr.device)[:, :n]
     nbytes = L.lib().lb_kmap_sort_ws_bytes(n)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=nbr.device)
-    L.check(L.lib().lb_kmap_sort_by_mask_ld(L.ptr(nbr), nbr.stride(0), n, k, L.ptr(perm), L.ptr(out), ld, L.ptr(ws), nbytes,
-                                            L.stream()))
-    return SortedMap(out, perm, tile_masks_of(out) if TILE_MASKS else None)
+    tm = torch.empty(max((n + 127) // 128, 1), dtype=torch.int, device=nbr.device) if TILE_MASKS else None
+    L.check(L.lib().lb_kmap_sort_by_mask_tm(L.ptr(nbr), nbr.stride(0), n, k, L.ptr(perm), L.ptr(out), ld,
+                                            L.ptr(tm) if tm is not None else None, L.ptr(ws), nbytes, L.stream()))
+    return SortedMap(out, perm, tm)
+
+
+def queue_level_counts(cell_coords, cnt, slot):
+    """Queue lb_level_counts on int32 [n,4] cell coordinates (points or voxels); the 4 coarse-level row counts land in the
+    pinned slots [slot, slot + 4) of ``cnt`` and are valid after the next ``cnt.read``."""
+    n = cell_coords.shape[0]
+    nbytes = L.lib().lb_level_counts_ws_bytes(n, 4)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cell_coords.device)
+    L.check(L.lib().lb_level_counts(L.ptr(cell_coords), n, 4, cnt.ptr(slot), L.ptr(ws), nbytes, L.stream()))
+    return ws
 
 
 class Maps:
     """Coordinates and neighbour tables of the 5 resolution levels (9 kernel maps) for one batch.  Every table is kept
     as (mask-sorted table, row permutation): the conv kernel walks rows in permuted order and scatters through out_rows."""
 
-    def __init__(self, coords):
+    def __init__(self, coords, level_counts=None):
+        """``level_counts``: row counts of levels 1..4 if the caller already knows them (``level_counts_of``); otherwise
+        they are fetched here in ONE host round trip -- the construction below is then free of host synchronisation."""
         self.coords, self.n, self.nbr3, self.nbr_dn, self.nbr_up, self.tables = [coords], [coords.shape[0]], [], [], [], []
         dev = coords.device
+        if level_counts is None:
+            cnt = _counters(dev)
+            queue_level_counts(coords, cnt, 8)
+            cnt.read(8)
+            level_counts = [int(cnt.buf[8 + l]) for l in range(4)]
         for lvl in range(5):
             s = 2 ** lvl
             c = self.coords[lvl]
@@ -293,7 +312,6 @@ class Maps:
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 L.check(L.lib().lb_downsample_maps(L.ptr(c), n_c, s, L.ptr(cn_full), cnt.ptr(lvl), L.ptr(dn_full), n_c, L.ptr(up),
                                                    L.ptr(ws), nbytes, L.stream()))
-                counted = cnt.mark()
             table = F._build_table(F.sphash(c))
             self.tables.append(table)
             off3 = _offsets(3, s, dev)
@@ -305,7 +323,7 @@ class Maps:
             if lvl == 4:
                 break
             self.nbr_up.append(_mask_sorted(up) if SORT_MAPS else up)
-            m_c = cnt.read(lvl, counted)
+            m_c = level_counts[lvl]                  # known up front (lb_level_counts): no host round trip per level
             cn = cn_full[:m_c]
             dn = dn_full[:, :m_c]
             self.coords.append(cn)
@@ -407,8 +425,8 @@ class InferenceEngine:
         pr = Prepared()
         coords = coords.contiguous()
         if self.is_spvcnn:
-            pr.zc, vcoords, pr.feats = self._initial_voxelize(coords, feats)
-            m = pr.m = self._maps(vcoords)
+            pr.zc, vcoords, pr.feats, level_counts = self._initial_voxelize(coords, feats)
+            m = pr.m = self._maps(vcoords, level_counts)
             pr.q = {}
             for lvl in (0, 4, 2):
                 pr.q[lvl] = self._corner_query(pr.zc, m, lvl) + self._cell_query(pr.zc, m, lvl)
@@ -423,11 +441,11 @@ class InferenceEngine:
         return (logits, feat) if return_feat else logits
 
     @staticmethod
-    def _maps(coords):
+    def _maps(coords, level_counts=None):
         """All 9 kernel maps of a batch.  SURVEY 8d per map: 16 * N_ref + 16 * N_out + 4 * K * N_out (+ tables 24 * N_ref)."""
         box = {}
         with _stage("map_build", lambda: box["m"].algorithmic_bytes()):
-            box["m"] = Maps(coords)
+            box["m"] = Maps(coords, level_counts)
         return box["m"]
 
     def _minkunet(self, pr):
@@ -519,14 +537,17 @@ class InferenceEngine:
         nbytes = L.lib().lb_group_by_key_ws_bytes(n)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         L.check(L.lib().lb_group_by_key(L.ptr(h), n, L.ptr(inv), L.ptr(first), cnt.ptr(7), L.ptr(ws), nbytes, L.stream()))
+        cell_i = cell.int()
+        lc_ws = queue_level_counts(cell_i, cnt, 8)      # the whole pyramid's row counts ride on the same round trip as nv
         nv = cnt.read(7)
+        level_counts = [int(cnt.buf[8 + l]) for l in range(4)]
+        del lc_ws
         counts = torch.empty(nv, dtype=torch.int, device=dev)
         L.check(L.lib().lb_count(L.ptr(inv), n, L.ptr(counts), nv, L.stream()))
-        cell_i = cell.int()
         vcoords = torch.empty((nv, 4), dtype=torch.int, device=dev)     # every member of a voxel has the same floored coords
         L.check(L.lib().lb_gather_rows16(L.ptr(cell_i), L.ptr(first), nv, L.ptr(vcoords), L.stream()))
         vfeats = self._vox(feats.contiguous(), inv, counts, nv)
-        return zc, vcoords, vfeats
+        return zc, vcoords, vfeats, level_counts
 
     def _spvcnn(self, pr):
         m, vfeats = pr.m, pr.feats
@@ -606,7 +627,10 @@ class StreamPipeline:
     def __init__(self, engine: "InferenceEngine"):
         import collections
         self.engine = engine
-        self.prep_stream = torch.cuda.Stream(device=engine.device)
+        # High priority: the side stream's kernels are small and latency-bound, and the host blocks on their row counts five
+        # times per batch.  At default priority they queue behind the thread blocks of the previous batch's convolutions and
+        # prepare() took 6.5 ms of host time per step -- longer than the network itself, so the main stream starved.
+        self.prep_stream = torch.cuda.Stream(device=engine.device, priority=PREP_PRIORITY)
         self._live = collections.deque()
         self.last_host_ms = (0.0, 0.0, 0.0)
         _allocator_size_classes()

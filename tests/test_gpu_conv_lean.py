@@ -93,3 +93,12 @@ def test_lean_identity_rows_by_tma(n, cin, cout, res, f32out):
     want = (want.relu() + residual.float()) if res else want.relu()
     err = float((lean.float() - want).norm() / want.norm())
     assert err < 1e-2, err
+
+
+def test_sort_emits_the_same_tile_masks_as_the_table_pass():
+    """lb_kmap_sort_by_mask_tm derives the tile masks from the per-row masks it already holds; lb_kmap_tile_masks re-reads
+    the sorted table: both routes must agree."""
+    from lidal_b200 import engine
+    for n, k in ((50000, 27), (4097, 8), (100, 27)):
+        sm = engine._mask_sorted(random_table(n, k, seed=n + k, p_lo=0.001, p_hi=0.3))
+        assert torch.equal(sm.tile_masks, engine.tile_masks_of(sm[0]))

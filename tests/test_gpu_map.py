@@ -162,3 +162,21 @@ def test_symmetric_kernel_map_query_matches_plain(ts, small_scan):
         assert torch.equal(a, b[:, :n])
         assert int((a >= 0).sum()) > n          # non-trivial map
         assert torch.equal(a[13].long().cpu(), torch.arange(n))
+
+
+def test_level_counts_vs_numpy():
+    """lb_level_counts: distinct parents at every coarser level in one pass (points or voxels, duplicates allowed) == numpy."""
+    import ctypes as C
+    from lidal_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 777, 200000):
+        c = np.concatenate([rng.integers(0, 300, (n, 3)), rng.integers(0, 4, (n, 1))], 1).astype(np.int32)
+        if n > 10:
+            c[n // 2:] = c[: n - n // 2]                      # duplicates
+        ct = torch.from_numpy(c).cuda()
+        counts = torch.full((4,), -7, dtype=torch.int32, device="cuda")
+        nbytes = L.lib().lb_level_counts_ws_bytes(n, 4)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        L.check(L.lib().lb_level_counts(L.ptr(ct) if n else None, n, 4, L.ptr(counts), L.ptr(ws), nbytes, L.stream()))
+        want = [len(np.unique(np.concatenate([c[:, :3] // (1 << l), c[:, 3:]], 1), axis=0)) if n else 0 for l in range(1, 5)]
+        assert counts.cpu().tolist() == want

@@ -27,6 +27,22 @@ for i in range(20):
     sp.submit(*resident[i % 3], wait_main=False)
 t1 = time.perf_counter(); e1.record(); torch.cuda.synchronize()
 print(f"steady state: host loop {(t1 - t0) / 20 * 1e3:.2f} ms/step, device {e0.elapsed_time(e1) / 20:.2f} ms/step")
+# (3) device time of the two phases on their own
+prs = [sp.prepare(*resident[i], wait_main=False) for i in range(3)]
+torch.cuda.synchronize()
+e0.record()
+for i in range(20):
+    eng.forward(prs[i % 3])
+e1.record(); torch.cuda.synchronize()
+print(f"forward only: device {e0.elapsed_time(e1) / 20:.2f} ms/step")
+with torch.cuda.stream(sp.prep_stream):
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for i in range(20):
+        eng.prepare(*resident[i % 3])
+    a1.record()
+torch.cuda.synchronize()
+print(f"prepare only: device {a0.elapsed_time(a1) / 20:.2f} ms/step (includes its host round trip)")
 pr = cProfile.Profile()
 pr.enable()
 for i in range(10):
