@@ -146,6 +146,7 @@ import time as _time
 FORCE_TILE128 = bool(int(_os.environ.get('LIDAL_TILE128', '0')))   # A/B switch: 128-row CTA tiles everywhere
 NO_STAGED = bool(int(_os.environ.get('LIDAL_NO_STAGED', '0')))       # A/B switch: per-thread epilogue stores
 SORT_MAPS = True        # group rows by neighbour mask (tile-level offset skipping); False = natural row order
+RESERVE_FACTOR = float(_os.environ.get('LIDAL_PIPE_RESERVE', '4'))   # side-stream pool parked at first use, in units of one prepare()'s allocations
 PREP_PRIORITY = int(_os.environ.get('LIDAL_PREP_PRIORITY', '-1'))   # CUDA stream priority of the map-construction stream (A/B: 0 = default)
 TILE_MASKS = bool(int(_os.environ.get('LIDAL_TILE_MASKS', '1')))    # A/B switch: per-tile offset masks (prologue-free conv producer)
 
@@ -633,6 +634,8 @@ class StreamPipeline:
         self.prep_stream = torch.cuda.Stream(device=engine.device, priority=PREP_PRIORITY)
         self._live = collections.deque()
         self.last_host_ms = (0.0, 0.0, 0.0)
+        self._reserved = False
+        self._reserved_main = False
         _allocator_size_classes()
 
 
@@ -647,7 +650,20 @@ class StreamPipeline:
                 self.prep_stream.wait_event(after)          # e.g. the H2D copy of this batch
             elif wait_main:
                 self.prep_stream.wait_stream(main)          # inputs produced on the caller's stream
-            pr = self.engine.prepare(coords, feats)
+            if not self._reserved:
+                # First batch: learn what one prepare() allocates on the side stream and park a segment of RESERVE_FACTOR times
+                # that in the stream's pool.  Later batches carve their buffers out of it, so no cudaMalloc (10-600 ms on a busy
+                # GPU, profiles/r02_host_stalls.txt) can land in a steady-state step while the pool is still growing.
+                self._reserved = True
+                dev = self.engine.device
+                before = torch.cuda.memory_allocated(dev)
+                pr = self.engine.prepare(coords, feats)
+                grown = torch.cuda.memory_allocated(dev) - before
+                if grown > 0 and RESERVE_FACTOR > 0:
+                    parked = torch.empty(int(grown * RESERVE_FACTOR), dtype=torch.uint8, device=dev)
+                    del parked
+            else:
+                pr = self.engine.prepare(coords, feats)
             pr.ready = torch.cuda.Event()
             pr.ready.record(self.prep_stream)
         return pr
@@ -667,7 +683,20 @@ class StreamPipeline:
         pr = self.prepare(coords, feats, after, wait_main)
         t1 = _time.perf_counter()
         torch.cuda.current_stream(self.engine.device).wait_event(pr.ready)
-        out = self.engine.forward(pr, return_feat)
+        if not self._reserved_main and RESERVE_FACTOR > 0:
+            # same for the caller's stream: park twice the peak of one forward() in its pool (activations of consecutive batches
+            # differ by a few per cent in size; the one cudaMalloc that used to follow a few steps later cost 10-50 ms)
+            self._reserved_main = True
+            dev = self.engine.device
+            torch.cuda.reset_peak_memory_stats(dev)
+            before = torch.cuda.memory_allocated(dev)
+            out = self.engine.forward(pr, return_feat)
+            peak = torch.cuda.max_memory_allocated(dev) - before
+            if peak > 0:
+                parked = torch.empty(int(peak * 2), dtype=torch.uint8, device=dev)
+                del parked
+        else:
+            out = self.engine.forward(pr, return_feat)
         t2 = _time.perf_counter()
         self.retire(pr)
         self.last_host_ms = ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (_time.perf_counter() - t2) * 1e3)   # prepare, forward, retire
@@ -693,6 +722,7 @@ class HostPipeline:
         self._out_pool = {}
         self._in_pool = {}
         self._n_submitted = 0
+        self.last_host_ms = (0.0, 0.0, 0.0, 0.0)
 
     def _out_buffer(self, shape, slot):
         key = (slot, shape[1])
@@ -722,6 +752,7 @@ class HostPipeline:
     def submit(self, coords_host: torch.Tensor, feats_host: torch.Tensor):
         """Queue one batch (host tensors).  Returns immediately; results come back in order from ``collect``."""
         dev = self.engine.device
+        t_a = _time.perf_counter()
         slot = self._n_submitted % (self.depth + 2)
         ent = self._in_buffers(slot, coords_host, feats_host)
         n = coords_host.shape[0]
@@ -736,7 +767,9 @@ class HostPipeline:
             ready.record(self.h2d_stream)
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ready)
+        t_b = _time.perf_counter()
         logits = self.stream_pipe.submit(c, f, after=ready)   # maps of this batch are built while the previous forward runs
+        t_c = _time.perf_counter()
         computed = torch.cuda.Event()
         computed.record(cur)
         ent[2] = computed
@@ -749,9 +782,11 @@ class HostPipeline:
             done = torch.cuda.Event()
             done.record(self.d2h_stream)
         self.pending.append((out, done))
+        t_d = _time.perf_counter()
         results = []
         while len(self.pending) > self.depth:
             results.append(self._pop())
+        self.last_host_ms = ((t_b - t_a) * 1e3, (t_c - t_b) * 1e3, (t_d - t_c) * 1e3, (_time.perf_counter() - t_d) * 1e3)   # upload, engine, download queue, wait for a result
         return results
 
     def _pop(self):
