@@ -174,9 +174,12 @@ def test_downsample_maps_equal_reference_maps_up_to_row_order(oracle_ts, small_s
         # map oracle coarse row -> engine coarse row
         order = torch.argsort(key(c_c))
         to_engine = order                                                         # oracle row j == engine row order[j]
-        dn_s, perm = m.nbr_dn[lvl] if engine_sorted else (m.nbr_dn[lvl], None)
+        dn_s, perm = m.nbr_dn[lvl] if isinstance(m.nbr_dn[lvl], tuple) else (m.nbr_dn[lvl], None)
         dn = torch.empty_like(dn_s.cpu())
-        dn[:, perm.cpu().long()] = dn_s.cpu() if perm is not None else dn_s.cpu()
+        if perm is not None:
+            dn[:, perm.cpu().long()] = dn_s.cpu()
+        else:                                      # strided maps are left in natural row order (engine.SORT_DN = False)
+            dn = dn_s.cpu()
         assert torch.equal(dn[:, to_engine].long(), res)                          # child rows identical
 
 
