@@ -973,10 +973,13 @@ __global__ void level_counts_kernel(const int4* __restrict__ coords, int64_t n, 
   const int64_t n_pad = (n + 31) & ~(int64_t)31;            // whole warps stay converged for the ballots
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
     const int4 c = i < n ? __ldg(&coords[i]) : make_int4(0, 0, 0, 0);
+    // hierarchical: only the row that inserted a cell at level l - 1 carries it to level l (all rows of a cell share their
+    // parent), so the atomics shrink with the pyramid: n + n_1 + n_2 + ... instead of levels * n
+    bool alive = i < n;
     for (int l = 1; l <= levels; ++l) {
       const int s = 1 << l;
       bool fresh = false;
-      if (i < n) {
+      if (alive) {
         const unsigned long long key = (unsigned long long)fnv60(c.x / s * s, c.y / s * s, c.z / s * s, c.w);
         unsigned long long* t = tables + (uint64_t)(l - 1) * cap;
         uint64_t slot = mix64(key) & (cap - 1);
@@ -989,6 +992,7 @@ __global__ void level_counts_kernel(const int4* __restrict__ coords, int64_t n, 
       }
       const unsigned b = __ballot_sync(0xffffffffu, fresh);
       if (lane == 0 && b) atomicAdd(&counts[l - 1], __popc(b));
+      alive = fresh;
     }
   }
 }
