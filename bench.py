@@ -426,9 +426,9 @@ def main():
         stream_pipe = StreamPipeline(eng)        # maps of batch i+1 are built on a side stream while batch i's network runs
     step = (lambda c, f: stream_pipe.submit(c, f, wait_main=False)) if stream_pipe is not None else run   # resident inputs: complete
     clk = ClockSampler(local_rank)               # NVML attached before warm-up
-    # allocator priming (untimed, before the W warm-up steps): every distinct batch twice, so that the caching allocator's
+    # allocator priming (untimed, before the W warm-up steps): every distinct batch three times, so that the caching allocator's
     # per-stream pools hold the resident set of the rotation and no cudaMalloc lands in the timed region
-    for i in range(2 * len(resident)):
+    for i in range(3 * len(resident)):
         step(*resident[i % len(resident)])
     for i in range(args.warmup):
         step(*resident[i % len(resident)])
@@ -476,7 +476,8 @@ def main():
     if eng is not None:
         from lidal_b200.engine import HostPipeline
         pipe = HostPipeline(eng)
-        for i in range(3 * len(host)):                            # warm-up: allocates the pinned output ring, settles the pools
+        for i in range(5 * len(host)):                            # warm-up: allocates the pinned output ring, settles the pools
+                                                                  # (the last pool growth, one deferred logits block, comes at submit 13)
             pipe.submit(*host[i % len(host)])
         pipe.collect()
         barrier()

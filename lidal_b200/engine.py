@@ -146,7 +146,7 @@ import time as _time
 FORCE_TILE128 = bool(int(_os.environ.get('LIDAL_TILE128', '0')))   # A/B switch: 128-row CTA tiles everywhere
 NO_STAGED = bool(int(_os.environ.get('LIDAL_NO_STAGED', '0')))       # A/B switch: per-thread epilogue stores
 SORT_MAPS = True        # group rows by neighbour mask (tile-level offset skipping); False = natural row order
-RESERVE_FACTOR = float(_os.environ.get('LIDAL_PIPE_RESERVE', '4'))   # side-stream pool parked at first use, in units of one prepare()'s allocations
+RESERVE_FACTOR = float(_os.environ.get('LIDAL_PIPE_RESERVE', '6'))   # side-stream pool parked at first use, in units of one prepare()'s allocations
 PREP_PRIORITY = int(_os.environ.get('LIDAL_PREP_PRIORITY', '-1'))   # CUDA stream priority of the map-construction stream (A/B: 0 = default)
 SORT_DN = bool(int(_os.environ.get('LIDAL_SORT_DN', '0')))          # A/B switch: mask-sort the strided (k = 8) maps as well
 TILE_MASKS = bool(int(_os.environ.get('LIDAL_TILE_MASKS', '1')))    # A/B switch: per-tile offset masks (prologue-free conv producer)
@@ -657,7 +657,7 @@ class StreamPipeline:
             elif wait_main:
                 self.prep_stream.wait_stream(main)          # inputs produced on the caller's stream
             if not self._reserved:
-                # First batch: learn what one prepare() allocates on the side stream and park a segment of RESERVE_FACTOR times
+                # First batch: learn what one prepare() allocates on the side stream and park a segment of RESERVE_FACTOR (6) times
                 # that in the stream's pool.  Later batches carve their buffers out of it, so no cudaMalloc (10-600 ms on a busy
                 # GPU, profiles/r02_host_stalls.txt) can land in a steady-state step while the pool is still growing.
                 self._reserved = True
@@ -690,7 +690,7 @@ class StreamPipeline:
         t1 = _time.perf_counter()
         torch.cuda.current_stream(self.engine.device).wait_event(pr.ready)
         if not self._reserved_main and RESERVE_FACTOR > 0:
-            # same for the caller's stream: park twice the peak of one forward() in its pool (activations of consecutive batches
+            # same for the caller's stream: park RESERVE_FACTOR / 2 times the peak of one forward() in its pool (activations of consecutive batches
             # differ by a few per cent in size; the one cudaMalloc that used to follow a few steps later cost 10-50 ms)
             self._reserved_main = True
             dev = self.engine.device
@@ -699,7 +699,7 @@ class StreamPipeline:
             out = self.engine.forward(pr, return_feat)
             peak = torch.cuda.max_memory_allocated(dev) - before
             if peak > 0:
-                parked = torch.empty(int(peak * 2), dtype=torch.uint8, device=dev)
+                parked = torch.empty(int(peak * RESERVE_FACTOR / 2), dtype=torch.uint8, device=dev)
                 del parked
         else:
             out = self.engine.forward(pr, return_feat)
