@@ -276,6 +276,79 @@ def run_lidal(eng, dev, rank, world, n_frames, kind, n_cls, barrier, seed=11):
     }
 
 
+# ------------------------------------------------------------------------------------------ config 5: many NU sequences
+def run_nu_dataset(eng, dev, rank, world, n_seq, frames_per_seq, distinct, barrier, clk, seed=23):
+    """BASELINE configs[4]: nuScenes-shaped SPVCNN prob_inference + LiDAL scoring over ``n_seq`` synthetic sequences of
+    ``frames_per_seq`` frames.  Whole sequences are packed onto the ranks (pipeline.pack_sequences; sequences are independent,
+    score/sv_level/LiDAL.py:185, so there is no halo), region centres get the reference's ``idx * 1000.0`` offset (:218), one
+    all_gather of the region scores, then the global selection (replicated).  Raw scans wait in pinned host memory (H2D inside
+    the timed region).  Each rank synthesises ``distinct`` sequences and cycles through them (the frames of sequence idx are
+    those of pool[idx % distinct] with the dataset-wide region ids of idx) -- 34,000 distinct ray casts would take minutes."""
+    import torch.distributed as dist
+    from lidal_b200 import pipeline, synth
+    kind, n_cls, regions = "NU", 16, 20
+    counts = [frames_per_seq] * n_seq
+    mine = pipeline.pack_sequences(counts, world)[rank]
+    offs = pipeline.sequence_region_offsets([c * regions for c in counts])
+    n_regions_total = sum(counts) * regions
+    pool = []
+    for j in range(min(distinct, max(len(mine), 1))):            # untimed synthesis, parked on the host
+        seq = synth.GpuSequence(frames_per_seq, kind, seed=seed + 1000 * rank + j, device=dev, n_regions=regions)
+        pool.append([(raw.cpu().pin_memory(), pose, (ptr, pts)) for raw, pose, _sv, (ptr, pts) in map(seq.frame, range(frames_per_seq))])
+    slot = {idx: k % len(pool) for k, idx in enumerate(mine)}
+
+    def source(idx):
+        frames, base = pool[slot[idx]], offs[idx]
+        return lambda fid: (frames[fid][0], frames[fid][1], np.arange(regions, dtype=np.int64) + base + fid * regions, frames[fid][2])
+
+    flags0 = np.zeros(n_regions_total, int)                      # round 0: 1 % of the frames fully labelled (sk_dataloader.py:99-118)
+    n_frames = sum(counts)
+    lab = np.random.default_rng(5).choice(n_frames, max(1, n_frames // 100), replace=False)
+    flags0.reshape(n_frames, regions)[lab] = 1
+    # warm-up: two sequences per rank through the same code (allocator pools, tensor maps, the all_gather's NCCL channels)
+    wcounts = [frames_per_seq] * (2 * world)
+    wmine = pipeline.pack_sequences(wcounts, world)[rank]
+    wslot = {idx: k % len(pool) for k, idx in enumerate(wmine)}
+    wsrc = lambda idx: (lambda fid: (pool[wslot[idx]][fid][0], pool[wslot[idx]][fid][1],                      # noqa: E731
+                                     np.arange(regions, dtype=np.int64) + (idx * frames_per_seq + fid) * regions, pool[wslot[idx]][fid][2]))
+    pipeline.run_dataset_sharded(eng, wsrc, wcounts, n_cls, sum(wcounts) * regions, seed=seed, device=dev)
+    with clk:
+        barrier()
+        t0 = time.perf_counter()
+        d, e, pn, c, flags, tm = pipeline.run_dataset_sharded(eng, source, counts, n_cls, n_regions_total, seed=seed, device=dev,
+                                                              select_with=(flags0, TRAIN_POINT_NUM[kind]))
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    total = torch.tensor([tm["device_total_ms"] + tm.get("selection_ms", 0.0), wall_ms, tm["infer_and_score_ms"], tm["scoring_ms"],
+                          tm["gather_ms"], tm.get("selection_ms", 0.0)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    total = total.tolist()
+    pts = float(np.mean([f[0].shape[0] for frames in pool for f in frames]))
+    fps = n_frames / (total[0] / 1e3)
+    return {
+        "metric": "LiDAL scored frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": n_frames, "warmup": 2 * frames_per_seq,
+        "ms_per_step": total[0] / n_frames, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16 operands, f32 accumulate (network); f64 distances, f32 scores (scoring)", "data": "synthetic",
+        "config": {"workload": f"nuScenes-shaped SPVCNN prob_inference (8 TTA views) + LiDAL scoring + selection over {n_seq} sequences x "
+                               f"{frames_per_seq} frames", "classes": n_cls, "points_per_frame": pts, "regions": n_regions_total,
+                   "sharding": "whole sequences per rank, LPT bin packing by frame count; no halo; one all_gather",
+                   "distinct_sequences_per_rank": len(pool),
+                   "cache": "every frame is a different 34k-point scan of the rank's pool; prob maps / grids are written once and read by 24 neighbours"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": int(pts * 16), "d2h_bytes_per_step": regions * 72,
+                "note": "the workload is host-fed by construction: raw scans start in pinned host memory, region arrays end on the host"},
+        "frames": n_frames, "sequences": n_seq, "ms_total": total[0], "wall_ms_max": total[1],
+        "phases_ms_max_over_ranks": {"prob_inference_and_scoring": total[2], "of_which_interframe_scoring": total[3],
+                                     "region_all_gather": total[4], "selection": total[5]},
+        "selection_parts_ms_rank0": {k: tm[k] for k in ("select_pairs_ms", "select_sort_ms", "select_walk_ms", "select_path") if k in tm},
+        "collective": {"halo_ms": 0.0, "all_gather_ms": tm.get("all_gather_ms", 0.0), "all_gather_bytes_per_rank": tm.get("all_gather_bytes_per_rank", 0)},
+        "sequences_per_rank": [len(b) for b in pipeline.pack_sequences(counts, world)],
+        "selected": {"labelled": int((flags == 1).sum()), "pseudo": int((flags == 2).sum())},
+        "checks": {"sv_interds_sum": float(d.astype(np.float64).sum()), "sv_interes_sum": float(e.astype(np.float64).sum())},
+        "clocks": clk.summary(),
+    }
+
+
 # ------------------------------------------------------------------------------------------ config 4: training step
 def run_train(args, dev, rank, world, local_rank, barrier):
     """BASELINE configs[3]: MinkUNet training fwd + bwd (+ Adam) on synthetic SemanticKITTI-shaped scans, batch 2 per GPU,
@@ -361,12 +434,18 @@ def main():
     ap.add_argument("--kind", default="SK", choices=["SK", "NU"], help="scan shape: SemanticKITTI-like (19 classes) or nuScenes-like (16)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
-                    help="infer: SPVCNN inference scans/s + LiDAL frames/s (BASELINE configs[1], [2]); train: MinkUNet training step, DDP (configs[3])")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "nu"],
+                    help="infer: SPVCNN inference scans/s + LiDAL frames/s (BASELINE configs[1], [2]); train: MinkUNet training step, DDP "
+                         "(configs[3]); nu: nuScenes-shaped inference + LiDAL scoring over many sequences (configs[4])")
+    ap.add_argument("--nu-sequences", type=int, default=850)
+    ap.add_argument("--nu-frames", type=int, default=40, help="frames per sequence (>= 25: the reference's window rule)")
+    ap.add_argument("--nu-distinct", type=int, default=8, help="distinct synthetic sequences per rank (cycled)")
     ap.add_argument("--no-lidal", action="store_true", help="skip the LiDAL scored-frames/s workload (BASELINE configs[2])")
     ap.add_argument("--lidal-frames", type=int, default=1000)
     args = ap.parse_args()
     global KIND, N_CLS
+    if args.workload == "nu":
+        args.kind = "NU"
     KIND, N_CLS = args.kind, (19 if args.kind == "SK" else 16)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -408,6 +487,23 @@ def main():
         except ImportError:
             path = "compat"
     run, eng = build_runner(args.model, path, dev)
+
+    if args.workload == "nu":
+        if eng is None or args.model != "spvcnn":
+            raise SystemExit("--workload nu runs SPVCNN through the engine path")
+
+        def barrier_nu():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        line = run_nu_dataset(eng, dev, rank, world, args.nu_sequences, max(args.nu_frames, 25), args.nu_distinct, barrier_nu,
+                              ClockSampler(local_rank))
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     batches = make_batches(rank)
     host = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(f).pin_memory()) for c, f, _ in batches]

@@ -8,6 +8,9 @@ data-path collective; the only exchanges are
 * ONE all_gather of the per-region scores before the global greedy selection (LiDAL.py:208-218 -> :230).
 
 ``frame_shard`` is the reference's split (dataset/sk_dataloader.py:196-198): contiguous ceil(N / G) chunks.
+A dataset of many short sequences (nuScenes: 850 scenes of ~40 frames, BASELINE configs[4]) is sharded by WHOLE sequences
+instead (``pack_sequences``: sequences are independent, LiDAL.py:185, so there is no halo at all), and the same single
+all_gather follows.
 The scorer is injected so the same orchestration runs on the CUDA scorer (lidal_b200.score) and, in the world-size-2
 gloo test, on the CPU oracle.
 """
@@ -41,6 +44,31 @@ def needed_frames(own: range, n_frames: int, nei_num: int = 24) -> list[int]:
     for f in own:
         need.update(neighbour_ids(f, n_frames, nei_num))
     return sorted(need)
+
+
+def pack_sequences(frame_counts: Sequence[int], world: int) -> list[list[int]]:
+    """Whole sequences -> ranks (many-sequence datasets): longest-processing-time greedy bin packing by
+    frame count -- sequences in descending length (ties: lower index first) each go to the currently least loaded rank (ties:
+    lower rank).  Deterministic, so every rank computes the same assignment without communication.  Returns, per rank, its
+    sequence indices in ascending order (= ``train_split`` order, the order LiDAL.py:185 visits them in)."""
+    world = max(int(world), 1)
+    load = [0] * world
+    bins: list[list[int]] = [[] for _ in range(world)]
+    for idx in sorted(range(len(frame_counts)), key=lambda i: (-int(frame_counts[i]), i)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        bins[r].append(idx)
+        load[r] += int(frame_counts[idx])
+    return [sorted(b) for b in bins]
+
+
+def sequence_region_offsets(region_counts: Sequence[int]) -> list[int]:
+    """First global region id of every sequence when ``sv_id`` runs through the dataset in ``train_split`` order
+    (dataset/prepare_supervoxel_kmeans_sk.py:67-69 numbers regions across frames and sequences without gaps)."""
+    out, acc = [], 0
+    for n in region_counts:
+        out.append(acc)
+        acc += int(n)
+    return out
 
 
 def _p2p(tensor_of: Callable[[int], torch.Tensor], alloc: Callable[[int], torch.Tensor], sends, recvs, group=None):
@@ -136,6 +164,32 @@ def score_sequence_sharded(frames: dict, n_points, n_cls, n_frames, regions: dic
         ids.append(np.asarray(sv_id)); ds.append(d); es.append(e); ns.append(pn); cs.append(c)
     cat = lambda xs, shape: np.concatenate(xs) if xs else np.zeros(shape)   # noqa: E731
     return gather_region_scores(cat(ids, 0), cat(ds, 0), cat(es, 0), cat(ns, 0), cat(cs, (0, 3)), n_regions_total, device)
+
+
+def score_sequences_sharded(frame_counts: Sequence[int], score_sequence: Callable, n_regions_total: int, device="cpu",
+                            timings: dict | None = None):
+    """Many-sequence datasets (LiDAL.py:185-218 over ``train_split``): whole sequences are packed onto the ranks
+    (``pack_sequences``), each rank scores its sequences with no exchange at all, adds the reference's ``idx * 1000.0``
+    to the region centres of sequence ``idx`` (LiDAL.py:218; float32 + Python float stays float32) and the per-region
+    rows meet in the one all_gather.  ``score_sequence(idx) -> (sv_id, d, e, pnums, centres)`` for ALL frames of sequence
+    ``idx`` (numpy arrays or tensors on ``device``).  Returns the global per-region arrays on every rank."""
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+    mine = pack_sequences(frame_counts, world)[rank]
+    ids, ds, es, ns, cs = [], [], [], [], []
+    for idx in mine:
+        sv_id, d, e, pn, c = score_sequence(idx)
+        if torch.is_tensor(c):
+            c = c.to(torch.float32) + idx * 1000.0
+        else:
+            c = np.asarray(c, np.float32) + idx * 1000.0
+        ids.append(sv_id); ds.append(d); es.append(e); ns.append(pn); cs.append(c)
+    if ids and all(torch.is_tensor(x) for x in ids + ds + es + ns + cs):
+        packed = [torch.cat(xs) for xs in (ids, ds, es, ns, cs)]
+    else:
+        as_np = lambda x: x.cpu().numpy() if torch.is_tensor(x) else np.asarray(x)      # noqa: E731
+        cat = lambda xs, shape: np.concatenate([as_np(x) for x in xs]) if xs else np.zeros(shape)   # noqa: E731
+        packed = [cat(ids, 0), cat(ds, 0), cat(es, 0), cat(ns, 0), cat(cs, (0, 3))]
+    return gather_region_scores(*packed, n_regions_total, device, timings)
 
 
 def cuda_score_frame(n_frames: int, nei_num=24, dis_thresh=0.1, device="cuda"):
@@ -245,6 +299,86 @@ def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: i
         timings["selection_ms"] = (time.perf_counter() - h0) * 1e3
     if keep_scorer:
         timings["scorer"] = scorer
+    return out + (flags, timings)
+
+
+def run_dataset_sharded(engine, sequence_source: Callable, frame_counts: Sequence[int], n_cls: int, n_regions_total: int,
+                        seed=0, inf_reps=8, nei_num=24, dis_thresh=0.1, device="cuda", select_with=None):
+    """BASELINE configs[4] (nuScenes-shaped: many short sequences) on the ranks of the default process group (or one GPU):
+
+      whole sequences are packed onto the ranks (``pack_sequences``)  ->  per own sequence, per frame: H2D of the raw scan,
+      pose registration, 8-view prob_inference, resident prob map + hash grid; then inter-frame scoring + region means of
+      the sequence and its frames are dropped  ->  ``idx * 1000.0`` on the centres (LiDAL.py:218)  ->  ONE all_gather of the
+      region scores  ->  (optional) the global selection, replicated.
+
+    ``sequence_source(idx) -> frame_source`` with ``frame_source(fid)`` as for ``run_sequence_sharded``.  Sequences do not
+    interact (LiDAL.py:185), so there is no halo and no collective before the all_gather.
+    Returns (sv_interds, sv_interes, sv_pnums, sv_centers, flags or None, timings dict [ms])."""
+    import time
+    from . import score, voxelizer
+    from .engine import StreamPipeline
+    dev = torch.device(device)
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_initialized() else (1, 0)
+    mine = pack_sequences(frame_counts, world)[rank]
+    ev = lambda: torch.cuda.Event(enable_timing=True)          # noqa: E731
+    t0, t1, t2 = ev(), ev(), ev()
+    timings: dict = {"sequences_total": len(frame_counts), "sequences_own": len(mine), "world": world,
+                     "frames_total": int(sum(frame_counts)), "frames_own": int(sum(frame_counts[i] for i in mine))}
+    sp = StreamPipeline(engine)
+    main = torch.cuda.current_stream(dev)
+    sp.prep_stream.wait_stream(main)
+    score_ms = []
+
+    def score_sequence(idx):
+        n_frames = int(frame_counts[idx])
+        frame_source = sequence_source(idx)
+        scorer = score.SequenceScorer(dev, nei_num, dis_thresh, n_total=n_frames)
+        for fid in range(n_frames):
+            raw, pose, sv_id, regions = frame_source(fid)
+            with torch.cuda.stream(sp.prep_stream):             # coordinate-only work on the side stream (see run_sequence_sharded)
+                raw_dev = torch.as_tensor(raw).to(dev, non_blocking=True)
+                xyz = score.register_points(raw_dev, pose)
+                coords, feats, inverse = voxelizer.tta_batch_gpu(raw_dev, seed=seed + idx * 100003 + fid, inf_reps=inf_reps)
+            pr = sp.prepare(coords, feats, wait_main=False)
+            main.wait_event(pr.ready)
+            prob, _pred = score.tta_tail(engine.forward(pr), inverse, inf_reps)
+            scorer.add_frame(xyz, prob, sv_id, regions, fid=fid)
+            sp.retire(pr, raw_dev, coords, feats, inverse)
+        s0, s1 = ev(), ev()
+        s0.record()
+        out = scorer.score_frames_device(list(range(n_frames)))
+        s1.record()
+        score_ms.append((s0, s1))
+        # the sequence's coordinates (allocated on the side stream), prob maps and grids go back to the allocator once the
+        # scoring kernels queued above have finished
+        sp.retire(list(scorer.frames.values()))
+        scorer.frames.clear()
+        return out
+
+    t0.record()
+    local_timings: dict = {}
+    mine_out = []
+    for idx in mine:
+        sv_id, d, e, pn, c = score_sequence(idx)
+        mine_out.append((torch.as_tensor(np.asarray(sv_id)).to(dev) if not torch.is_tensor(sv_id) else sv_id, d, e, pn,
+                         c.to(torch.float32) + idx * 1000.0))
+    t1.record()
+    if mine_out:
+        packed = [torch.cat([m[j] for m in mine_out]) for j in range(5)]
+    else:
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)      # noqa: E731
+        packed = [z(0), z(0), z(0), z(0), z(0, 3)]
+    out = gather_region_scores(*packed, n_regions_total, dev, local_timings)
+    t2.record()
+    torch.cuda.synchronize(dev)
+    timings.update(local_timings)
+    timings.update(infer_and_score_ms=t0.elapsed_time(t1), scoring_ms=float(sum(a.elapsed_time(b) for a, b in score_ms)),
+                   gather_ms=t1.elapsed_time(t2), device_total_ms=t0.elapsed_time(t2))
+    flags = None
+    if select_with is not None:
+        h0 = time.perf_counter()
+        flags = score.select_regions(select_with[0], out[0], out[1], out[2], out[3], select_with[1], device=dev, timings=timings)
+        timings["selection_ms"] = (time.perf_counter() - h0) * 1e3
     return out + (flags, timings)
 
 

@@ -86,3 +86,82 @@ def test_two_rank_sharded_scoring_equals_single_process(tmp_path):
         got = np.load(tmp_path / f"rank{r}.npz")
         assert np.array_equal(got["d"], d) and np.array_equal(got["e"], e)
         assert np.array_equal(got["n"], pn) and np.array_equal(got["c"], c)
+
+
+# ------------------------------------------------------------------ many-sequence datasets: whole sequences per rank
+SEQ_LENGTHS = [27, 25, 30, 26]          # the reference's window rule needs >= 25 frames per sequence (LiDAL.py:41-42)
+
+
+def _dataset_case():
+    """Four short NU-shaped sequences with dataset-wide region ids (prepare_supervoxel_kmeans_sk.py:67-69)."""
+    from lidal_b200 import synth
+    seqs, nxt = [], 0
+    for s, n in enumerate(SEQ_LENGTHS):
+        seq = synth.make_sequence(n, "NU", seed=20 + s, sv_id_start=nxt, max_points=200, step=0.15)
+        nxt = int(seq.sv_id[-1][-1]) + 1
+        probs = [synth.synthetic_probs(seq.xyz[i], 16, 1000 * s + i) for i in range(n)]
+        seqs.append((seq, probs))
+    return seqs, nxt
+
+
+def _oracle_score_sequence(seqs):
+    import lidal_scoring as orc
+
+    def score(idx):
+        seq, probs = seqs[idx]
+        trees = orc.build_trees(seq.xyz)
+        outs = [orc.score_frame(f, probs, seq.xyz, trees, seq.sv_id[f], seq.sv2point[f]) for f in range(seq.n_frames)]
+        return tuple(np.concatenate([o[j] for o in outs]) for j in range(5))
+    return score
+
+
+def _dataset_worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lidal_b200 import pipeline
+    seqs, n_regions = _dataset_case()
+    out = pipeline.score_sequences_sharded(SEQ_LENGTHS, _oracle_score_sequence(seqs), n_regions)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), d=out[0], e=out[1], n=out[2], c=out[3])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pack_sequences():
+    from lidal_b200 import pipeline
+    assert pipeline.pack_sequences([7, 5, 9, 4], 2) == [[2, 3], [0, 1]]            # 9 -> r0, 7 -> r1, 5 -> r1 (7 < 9), 4 -> r0: loads 13 / 12
+    assert pipeline.pack_sequences([3, 3, 3], 1) == [[0, 1, 2]]
+    assert pipeline.pack_sequences([], 4) == [[], [], [], []]
+    assert pipeline.pack_sequences([5, 1], 4) == [[0], [1], [], []]                # more ranks than sequences: idle ranks
+    rng = np.random.default_rng(0)
+    counts = rng.integers(30, 50, 850).tolist()                                     # nuScenes-shaped: 850 scenes of ~40 frames
+    bins = pipeline.pack_sequences(counts, 8)
+    assert sorted(i for b in bins for i in b) == list(range(850))                   # every sequence exactly once
+    loads = [sum(counts[i] for i in b) for b in bins]
+    assert max(loads) - min(loads) <= max(counts)                                   # LPT: within one sequence of balanced
+    assert max(loads) <= 1.01 * sum(counts) / 8
+    assert all(b == sorted(b) for b in bins)
+    assert pipeline.sequence_region_offsets([4, 0, 6]) == [0, 4, 4]
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sequence_packing_equals_reference_loop(tmp_path):
+    """LiDAL.py:185-218 over several sequences (centres offset by idx * 1000.0) == the 2-rank whole-sequence sharding."""
+    sys.path[:0] = [os.path.join(ROOT, "oracle")]
+    mp.spawn(_dataset_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    seqs, n_regions = _dataset_case()
+    score = _oracle_score_sequence(seqs)
+    d, e = np.zeros(n_regions, np.float32), np.zeros(n_regions, np.float32)
+    pn, c = np.zeros(n_regions, int), np.zeros((n_regions, 3), np.float32)
+    for idx in range(len(seqs)):                                                    # the reference's loop, one process
+        sv_id, sd, se, sn, sc = score(idx)
+        d[sv_id], e[sv_id], pn[sv_id] = sd, se, sn
+        c[sv_id] = sc + idx * 1000.0                                                # LiDAL.py:218
+    assert c[:, 0].max() > 2900.0
+    for r in range(2):
+        got = np.load(tmp_path / f"rank{r}.npz")
+        assert np.array_equal(got["d"], d) and np.array_equal(got["e"], e)
+        assert np.array_equal(got["n"], pn) and np.array_equal(got["c"], c)
+    from lidal_b200 import pipeline                                                  # world size 1 (no process group): same arrays
+    one = pipeline.score_sequences_sharded(SEQ_LENGTHS, score, n_regions)
+    assert np.array_equal(one[0], d) and np.array_equal(one[3], c)
