@@ -229,3 +229,29 @@ def test_host_pipeline_matches_direct_calls(small_scan):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_accelerate_is_the_engine_behind_the_reference_call(small_scan):
+    """engine.accelerate(model): the reference's own call ``logits, out_feat = model(SparseTensor(feats, coords))``
+    (score/prob_inference.py:97) under no_grad returns exactly what InferenceEngine returns; a weight update is picked up."""
+    import lidal_b200.compat as ts
+    from lidal_b200.engine import InferenceEngine, accelerate
+    from lidal_b200.network import SPVCNN, seeded_state_dict
+    coords, feats, _ = small_scan
+    model = SPVCNN(16, ts)
+    model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
+    model = accelerate(model.cuda().eval())
+    c, f = torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda()
+    want_logits, want_feat = InferenceEngine(model)(c, f, return_feat=True)
+    with torch.no_grad():
+        logits, feat = model(ts.SparseTensor(f, c))
+        again, _ = model(ts.SparseTensor(f, c))                      # second call: cached engine
+    assert logits.dtype == feat.dtype == torch.float32 and feat.shape == (coords.shape[0], 96)
+    assert torch.equal(logits, want_logits) and torch.equal(feat, want_feat.float()) and torch.equal(again, logits)
+    slow = model(ts.SparseTensor(f, c))[0]                            # autograd on: the module-by-module compat forward
+    assert slow.requires_grad
+    assert float((slow.detach() - logits).norm() / logits.norm()) < 3e-2
+    with torch.no_grad():
+        model.classifier[0].bias.add_(1.0)                            # in-place update bumps _version: engine rebuilt
+        moved, _ = model(ts.SparseTensor(f, c))
+    torch.testing.assert_close(moved, logits + 1.0, rtol=1e-5, atol=1e-4)

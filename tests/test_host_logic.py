@@ -121,3 +121,31 @@ def test_native_walk_equals_python_replay_and_golden(golden):
         got = _native_both_passes(sv_flags.astype(int), d, e, pn, c, tpn)
         assert np.array_equal(want, scan) and np.array_equal(got, want), seed
         assert (got == 1).sum() > 0 and (got == 2).sum() > 0
+
+
+def test_accelerate_keeps_the_module_contract(oracle_ts, small_scan):
+    """engine.accelerate(model) must leave the object a caller of the reference holds intact: same class, same state_dict
+    keys, and the original (autograd-correct) forward whenever the module trains or autograd is on.  (The fused eval path
+    itself needs the GPU: tests/test_gpu_engine.py.)"""
+    import torch
+    from lidal_b200.engine import accelerate
+    from lidal_b200.network import MinkUNet, seeded_state_dict
+    coords, feats, _ = small_scan
+    model = MinkUNet(19, oracle_ts)
+    model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
+    model.eval()
+    keys = list(model.state_dict().keys())
+    x = lambda: oracle_ts.SparseTensor(torch.from_numpy(feats[:400]), torch.from_numpy(coords[:400]))     # noqa: E731
+    want = model(x())[0]                                               # autograd enabled: the module-by-module forward
+    same = accelerate(model)
+    assert same is model and type(model) is MinkUNet and accelerate(model) is model                      # in place, idempotent
+    assert list(model.state_dict().keys()) == keys
+    got = model(x())[0]
+    assert got.requires_grad and torch.equal(got, want)                # grad mode: original forward, bit for bit
+    model.train()
+    assert model(x())[0].requires_grad
+    model.eval()
+    model.lidal_engine_invalidate()
+    wrapped = torch.nn.Sequential()                                    # a DDP-like wrapper: `.module` is unwrapped
+    wrapped.module = MinkUNet(19, oracle_ts).eval()
+    assert accelerate(wrapped) is wrapped and wrapped.module._lidal_accelerated
