@@ -1389,10 +1389,9 @@ int conv_tc_launch(const lb_conv_args& a, cudaStream_t st) {
   const int row_bytes = bk * 2;
   const size_t block_bytes = (size_t)T * TILE_M * row_bytes + (((size_t)a.c_out * row_bytes + 1023) & ~(size_t)1023);
   const size_t budget = 227 * 1024 - 1024 - tail_bytes(T, lean);
-  // blocks per stage: measured on B200, carrying several blocks per stage (fewer, coarser stages) is not faster than
-  // a deep ring of single-block stages -- the kernel is bound by L2 traffic, not by the per-stage hand-shake.
-  // (round 2: with the weight warp, the per-stage hand-shake of the gather warps is the bound on the fine levels --
-  // profiles/r02_conv_knockouts.txt -- so stages carry up to LIDAL_NB_MAX blocks wherever >= 3 such stages still fit)
+  // blocks per stage: the loop slot free -> gather issue -> data landed -> MMA -> slot free is a chain of latencies, and on
+  // the fine levels the per-stage hand-shake of the gather warps is part of it (profiles/r02_conv_knockouts.txt,
+  // r02_conv_lean_modes.txt), so stages carry up to LIDAL_NB_MAX blocks wherever >= 3 such stages still fit.
   static const int nb_max = getenv("LIDAL_NB_MAX") ? atoi(getenv("LIDAL_NB_MAX")) : 2;   // measured: 1 -> 4.97, 2 -> 4.92, 3 -> 4.89 ms of conv per step
   static const int prod_mode_env0 = getenv("LIDAL_PROD_MODE") ? atoi(getenv("LIDAL_PROD_MODE")) : 0;
   static const int wwarp_env0 = getenv("LIDAL_WEIGHT_WARP") ? atoi(getenv("LIDAL_WEIGHT_WARP")) : 1;
