@@ -38,7 +38,7 @@ def build_variant(out: str, extra_flags) -> str:
     for pr in procs:
         if pr.wait() != 0:
             raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", out, *objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", out, *objs, "-lcudart"])
     return out
 
 
@@ -61,7 +61,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart"])
     with open(os.path.join(HERE, "csrc", "_obj", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -227,7 +227,8 @@ def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: i
       the region scores  ->  (optional) the global selection, replicated on every rank (it is sequential and tiny).
 
     frame_source(fid) -> (raw f32 [Np,4] host (pinned) or device, pose 4x4 float64, sv_id int64 [R], regions) with regions the
-    reference's ``sv2point`` lists or a device CSR pair.  select_with = (sv_flags, train_point_num) runs ``select_regions``.
+    reference's ``sv2point`` lists or a device CSR pair.  Pinned host scans are uploaded on the side stream and overlap the
+    previous frame's network; a device-resident scan makes the side stream wait for the caller's stream first (no overlap).  select_with = (sv_flags, train_point_num) runs ``select_regions``.
     Returns (sv_interds, sv_interes, sv_pnums, sv_centers, flags or None, timings dict [ms, device events; host for selection])."""
     import time
     from . import score
@@ -246,6 +247,8 @@ def run_sequence_sharded(engine, frame_source: Callable, n_frames: int, n_cls: i
     t[0].record()
     for fid in own:
         raw, pose, sv_id, regions = frame_source(fid)
+        if torch.is_tensor(raw) and raw.is_cuda:
+            sp.prep_stream.wait_stream(main)                     # a device-resident scan was produced on the caller's stream
         # coordinate-only work of frame i (upload, registration, TTA voxelizer, kernel maps: all the host round trips) on the
         # side stream, while the GPU is still busy with the network of frame i-1 on the main stream
         with torch.cuda.stream(sp.prep_stream):
@@ -335,6 +338,8 @@ def run_dataset_sharded(engine, sequence_source: Callable, frame_counts: Sequenc
         scorer = score.SequenceScorer(dev, nei_num, dis_thresh, n_total=n_frames)
         for fid in range(n_frames):
             raw, pose, sv_id, regions = frame_source(fid)
+            if torch.is_tensor(raw) and raw.is_cuda:
+                sp.prep_stream.wait_stream(main)                 # a device-resident scan was produced on the caller's stream
             with torch.cuda.stream(sp.prep_stream):             # coordinate-only work on the side stream (see run_sequence_sharded)
                 raw_dev = torch.as_tensor(raw).to(dev, non_blocking=True)
                 xyz = score.register_points(raw_dev, pose)
