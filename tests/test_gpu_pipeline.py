@@ -10,6 +10,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 N_CLS = 16
+# Two runs of SPVCNN on the same frame agree to rounding, not bit for bit: point_to_voxel sums a voxel's points in the order a
+# counting sort with an atomic cursor lists them (csrc/frame.cu, segment_order) -- like the reference's atomicAdd voxelize,
+# "neither order is canonical" -- so a 16-bit mean can flip its last bit and move a region score by ~1 ulp.
+SCORE_TOL = dict(rtol=2e-3, atol=1e-7)
 SEQ_LENGTHS = [26, 25]            # the reference's window rule needs >= 25 frames per sequence (LiDAL.py:41-42)
 REGIONS = 20
 
@@ -50,8 +54,9 @@ def test_sequence_driver_equals_composition(engine):
     d, e, pn, c, flags, tm = pipeline.run_sequence_sharded(engine, seq.frame, seq.n_frames, N_CLS, n_regions, seed=5, device=dev)
     assert flags is None and tm["frames_own"] == seq.n_frames
     for sv_id, sd, se, sn, sc in _compose(engine, seq, 5, dev):
-        assert np.array_equal(d[sv_id], sd) and np.array_equal(e[sv_id], se)
-        assert np.array_equal(pn[sv_id], sn) and np.array_equal(c[sv_id], sc)
+        np.testing.assert_allclose(d[sv_id], sd, **SCORE_TOL)
+        np.testing.assert_allclose(e[sv_id], se, **SCORE_TOL)
+        assert np.array_equal(pn[sv_id], sn) and np.array_equal(c[sv_id], sc)     # integer counts / float64 registration: exact
     assert np.isfinite(d).all() and (e > 0).any() and int(pn.sum()) > 0
 
 
@@ -72,9 +77,11 @@ def test_dataset_driver_equals_reference_loop(engine):
         for sv_id, sd, se, sn, sc in _compose(engine, seq, 5 + idx * 100003, dev):
             D[sv_id], E[sv_id], PN[sv_id] = sd, se, sn
             C[sv_id] = sc + idx * 1000.0                                          # LiDAL.py:218
-    assert np.array_equal(d, D) and np.array_equal(e, E) and np.array_equal(pn, PN) and np.array_equal(c, C)
+    np.testing.assert_allclose(d, D, **SCORE_TOL)
+    np.testing.assert_allclose(e, E, **SCORE_TOL)
+    assert np.array_equal(pn, PN) and np.array_equal(c, C)
     assert C[SEQ_LENGTHS[0] * REGIONS:, 0].min() > 900.0
-    # the replicated selection saw the same arrays the oracle would: flags bit-equal to the CPU restatement of LiDAL.py:230-325
+    # the replicated selection on the driver's own arrays: flags bit-equal to the CPU restatement of LiDAL.py:230-325
     import lidal_scoring as orc
-    want = orc.select_regions(flags0, D, E, PN, C, 40 * int(3e4) * 100)
-    assert np.array_equal(flags, want)
+    want = orc.select_regions(flags0, d, e, pn, c, 40 * int(3e4) * 100)
+    assert np.array_equal(flags, want) and (flags == 1).sum() > REGIONS
