@@ -236,9 +236,9 @@ def test_accelerate_is_the_engine_behind_the_reference_call(small_scan):
     (score/prob_inference.py:97) under no_grad returns exactly what InferenceEngine returns; a weight update is picked up."""
     import lidal_b200.compat as ts
     from lidal_b200.engine import InferenceEngine, accelerate
-    from lidal_b200.network import SPVCNN, seeded_state_dict
+    from lidal_b200.network import MinkUNet, seeded_state_dict
     coords, feats, _ = small_scan
-    model = SPVCNN(16, ts)
+    model = MinkUNet(19, ts)          # bit-reproducible run to run (SPVCNN's point_to_voxel sums in atomic order: rounding only)
     model.load_state_dict(seeded_state_dict(model.state_dict()), strict=True)
     model = accelerate(model.cuda().eval())
     c, f = torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda()
