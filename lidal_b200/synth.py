@@ -22,6 +22,7 @@ Nothing here is performance critical; it is host-side numpy.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -221,6 +222,42 @@ def region_table(n_frames: int, seed: int = 0, regions_per_frame: int = 20, labe
     lab = rng.choice(n_frames, max(1, int(round(labelled_frac * n_frames))), replace=False)
     flags[np.isin(frame, lab)] = 1
     return flags, interds, interes, pnums.astype(int), centers
+
+
+def write_scoring_tree(root: str, model_name: str = "SPVCNN", lengths=None, max_points: int = 300, n_cls: int = 19, seed: int = 40,
+                       dataset_name: str = "SK"):
+    """A synthetic ``Processing_files/<dataset>/`` tree in the reference's formats for round r_id = 1 -- what
+    ``python -m score.sv_level.LiDAL`` reads (score/sv_level/LiDAL.py:152-197): per frame a flag file
+    (sv_flag/KMeans/0r/<seq>/<frame>.npy), a prob map (prob_map/<model>/fr/0r/...), a pickled sklearn KDTree of the registered
+    points (kdtree/<seq>/<frame>.pickle, dataset/prepare_kdtree_sk.py:83-88) and a pickled ``(sv_id, sv2point)``
+    (super_voxel/KMeans/<seq>/<frame>.pickle, dataset/prepare_supervoxel_kmeans_sk.py:60-74).  ``lengths`` maps sequence
+    names to frame counts; region ids run through the dataset in that order.  Returns the number of regions."""
+    import pickle
+    from sklearn.neighbors import KDTree
+    lengths = lengths or {"00": 26, "01": 25}
+    base = os.path.join(root, "Processing_files", dataset_name)
+    rng = np.random.default_rng(seed)
+    nxt = 0
+    for s, (seq_id, n) in enumerate(lengths.items()):
+        seq = make_sequence(n, "NU", seed=seed + s, sv_id_start=nxt, max_points=max_points, step=0.6)
+        nxt = int(seq.sv_id[-1][-1]) + 1
+        dirs = {k: os.path.join(base, *v, seq_id) for k, v in dict(
+            flag=("sv_flag", "KMeans", "0r"), prob=("prob_map", model_name, "fr", "0r"), kd=("kdtree",), sv=("super_voxel", "KMeans")).items()}
+        for d in dirs.values():
+            os.makedirs(d, exist_ok=True)
+        for i in range(n):
+            name = f"{i:06d}"
+            flags = np.zeros(len(seq.sv_id[i]))
+            if i == 3 * s:
+                flags[:] = 1                                     # one fully labelled frame per sequence
+            flags[rng.random(len(flags)) < 0.05] = 2             # stale pseudo labels (reset at LiDAL.py:286)
+            np.save(os.path.join(dirs["flag"], name + ".npy"), flags)
+            np.save(os.path.join(dirs["prob"], name + ".npy"), synthetic_probs(seq.xyz[i], n_cls, 7000 + 100 * s + i))
+            with open(os.path.join(dirs["kd"], name + ".pickle"), "wb") as f:
+                pickle.dump(KDTree(seq.xyz[i]), f)
+            with open(os.path.join(dirs["sv"], name + ".pickle"), "wb") as f:
+                pickle.dump((seq.sv_id[i], seq.sv2point[i]), f)
+    return nxt
 
 
 # ------------------------------------------------------------------------------------------- device-side generator

@@ -147,3 +147,34 @@ def select_regions(sv_flags, sv_interds, sv_interes, sv_pnums, sv_centers, train
             sv_flags[sv_id] = 2
             added_ids.add(sv_id)
     return sv_flags
+
+
+def score_dataset(sequences, nei_num=24, dis_thresh=0.1, n_regions_total=None, sv_pnums=None, sv_centers=None):
+    """LiDAL.py:163-222 on the reference's file formats: per sequence (in train_split order) every frame's ``worker_func``
+    result is scattered into the global arrays by ``sv_id``; centres get ``idx * 1000.0`` (:218); cached ``sv_pnums`` /
+    ``sv_centers`` are reused when given (``sv_pre``, :171-175).  ``sequences``: [(prob_files, kdtree_files, sv_info_files)].
+    Returns (sv_interds f32, sv_interes f32, sv_pnums int, sv_centers f32 [.,3], sv_pre)."""
+    import pickle
+    sv_pre = sv_pnums is not None and sv_centers is not None
+    sv_interds = np.zeros(n_regions_total, np.float32)
+    sv_interes = np.zeros(n_regions_total, np.float32)
+    if not sv_pre:
+        sv_pnums = np.zeros(n_regions_total, int)
+        sv_centers = np.zeros((n_regions_total, 3), np.float32)
+    for idx, (prob_files, kdtree_files, sv_info_files) in enumerate(sequences):
+        assert len(prob_files) == len(kdtree_files) == len(sv_info_files)
+        probs = [np.load(p) for p in prob_files]
+        trees = []
+        for k in kdtree_files:
+            with open(k, "rb") as f:
+                trees.append(pickle.load(f))
+        xyz = [np.asarray(t.data) for t in trees]
+        for fid, s in enumerate(sv_info_files):
+            with open(s, "rb") as f:
+                sv_id, sv2point = pickle.load(f)
+            ids, d, e, pn, c = score_frame(fid, probs, xyz, trees, sv_id, sv2point, nei_num, dis_thresh)
+            sv_interds[ids], sv_interes[ids] = d, e
+            if not sv_pre:
+                sv_pnums[ids] = pn
+                sv_centers[ids] = c + idx * 1000.0
+    return sv_interds, sv_interes, sv_pnums, sv_centers, sv_pre

@@ -15,6 +15,10 @@ What it pins:
                  KD-tree pickle), ``score.frame_level.segment_entropy.worker_func`` and ``score.sv_level.ReDAL.worker_func``
                  on synthetic files == oracle.lidal_extra.{register_points, segment_entropy, redal_worker} (exact).
 
+  cli.npz        the reference's own command line ``python -m score.sv_level.LiDAL --dataset_name SK --model_name SPVCNN --r_id 1``
+                 run unmodified in a synthetic Processing_files/ tree == lidal_b200.score.cli.run on the oracle: every
+                 sv_flag/*.npy file and the sv_pnums / sv_centers cache byte-identical.
+
 Run:  python tests/golden/make_golden.py
 """
 import hashlib
@@ -274,7 +278,50 @@ def gen_extra():
     print(f"extra.npz: reference process_frame / segment_entropy / ReDAL worker == oracle on {n} points; sege={sege_ref:.6f}")
 
 
+def gen_cli():
+    """The reference's own command line, `python -m score.sv_level.LiDAL --dataset_name SK --model_name SPVCNN --r_id 1`
+    (README.md:115), run UNMODIFIED as a subprocess in a synthetic Processing_files/ tree (synth.write_scoring_tree; two of
+    the ten SemanticKITTI train sequences populated, the others empty -- the reference handles that), against
+    lidal_b200.score.cli.run on the pinned oracle: the sv_flag/*.npy files and the cached sv_pnums / sv_centers it writes
+    must be byte-identical.  The concatenated outputs are committed as cli.npz."""
+    import glob
+    import subprocess
+    from lidal_b200.score import cli
+    params = dict(model_name="SPVCNN", lengths={"00": 26, "01": 25}, max_points=300, n_cls=19, seed=40)
+    with tempfile.TemporaryDirectory() as d_ref, tempfile.TemporaryDirectory() as d_mine:
+        n_regions = synth.write_scoring_tree(d_ref, **params)
+        assert synth.write_scoring_tree(d_mine, **params) == n_regions
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([REF, os.path.join(ROOT, "oracle", "_stubs")]))
+        out = subprocess.run([sys.executable, "-m", "score.sv_level.LiDAL", "--dataset_name", "SK", "--model_name", "SPVCNN", "--r_id", "1"],
+                             cwd=d_ref, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=1800)
+        assert out.returncode == 0, out.stderr[-3000:]
+        flags, paths = cli.run("SK", "SPVCNN", 1, root=d_mine, score_dataset=orc.score_dataset, select_regions=orc.select_regions,
+                               verbose=False)
+        rel = lambda root: sorted(os.path.relpath(p, root) for p in glob.glob(f"{root}/Processing_files/SK/sv_flag/KMeans/SPVCNN/LiDAL/1r/*/*.npy"))  # noqa: E731
+        assert rel(d_ref) == rel(d_mine) and len(rel(d_ref)) == sum(params["lengths"].values())
+        per_frame = []
+        for r in rel(d_ref):
+            a, b = np.load(os.path.join(d_ref, r)), np.load(os.path.join(d_mine, r))
+            assert a.dtype == b.dtype and np.array_equal(a, b), r
+            per_frame.append(a)
+        stats = {}
+        for name in ("sv_pnums", "sv_centers"):
+            a = np.load(f"{d_ref}/Processing_files/SK/super_voxel/KMeans/{name}.npy")
+            b = np.load(f"{d_mine}/Processing_files/SK/super_voxel/KMeans/{name}.npy")
+            assert a.dtype == b.dtype and np.array_equal(a, b), name
+            stats[name] = a
+        for seq_id in cli.SK_TRAIN_SPLIT:                      # the reference creates every sequence's output folder (LiDAL.py:157-159)
+            assert os.path.isdir(f"{d_ref}/Processing_files/SK/sv_flag/KMeans/SPVCNN/LiDAL/1r/{seq_id}")
+            assert os.path.isdir(f"{d_mine}/Processing_files/SK/sv_flag/KMeans/SPVCNN/LiDAL/1r/{seq_id}")
+    out_flags = np.concatenate(per_frame)
+    assert np.array_equal(out_flags, flags)
+    np.savez_compressed(f"{OUT}/cli.npz", params=np.array(list(params.items()), dtype=object), n_regions=n_regions,
+                        flags=out_flags, frame_sizes=np.array([len(a) for a in per_frame]), **stats, allow_pickle=True)
+    print(f"cli.npz: reference `python -m score.sv_level.LiDAL` == lidal_b200.score.cli.run on the oracle; {n_regions} regions, "
+          f"labelled {int((out_flags == 1).sum())}, pseudo {int((out_flags == 2).sum())}")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets", "voxelizer", "extra"]
+    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets", "voxelizer", "extra", "cli"]
     for w in which:
         globals()[f"gen_{w}"]()
