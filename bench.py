@@ -231,7 +231,7 @@ def cpu_lidal_sample(cores: int, kind: str, n_cls: int, scan_seconds: float, inf
     ids = list(range(12, 12 + n_score))
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(n_score) as pool:
-        res = pool.map_async(_cpu_score_one, ids).get(timeout=600)
+        res = pool.map_async(_cpu_score_one, ids).get(timeout=240)     # ~15 s per frame and core; bounded so the arm cannot hang
     wall = time.perf_counter() - t0
     _CPU_SEQ.clear()
     score_s = wall / n_score                                    # per frame at n_score-way parallelism
