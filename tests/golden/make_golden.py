@@ -278,6 +278,45 @@ def gen_extra():
     print(f"extra.npz: reference process_frame / segment_entropy / ReDAL worker == oracle on {n} points; sege={sege_ref:.6f}")
 
 
+def gen_shard():
+    """The reference's own score-mode data loader (dataset/sk_dataloader.py:185-198, unmodified) on a tree of empty .bin
+    files: which frames rank r of G gets == lidal_b200.pipeline.frame_shard (the split every sharded driver uses)."""
+    import torch.distributed as dist
+    from dataset.sk_dataloader import SK_Dataloader
+    from lidal_b200 import pipeline
+    cases = [(1000, 1), (1000, 2), (1000, 4), (1000, 8), (1003, 8), (10, 4), (7, 8), (25, 3)]
+    cwd = os.getcwd()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29653")
+    dist.init_process_group("gloo", rank=0, world_size=1)           # SK_Dataloader.__init__ calls dist.barrier() when gpu_num > 1
+    rows = []
+    try:
+        for n, world in cases:
+            with tempfile.TemporaryDirectory() as d:
+                os.makedirs(f"{d}/Processing_files")
+                per = [n - n // 2, n // 2]                          # two of the train sequences hold the frames
+                for seq_id, k in zip(("00", "01"), per):
+                    os.makedirs(f"{d}/Semantic_kitti/dataset/sequences/{seq_id}/velodyne")
+                    for i in range(k):
+                        open(f"{d}/Semantic_kitti/dataset/sequences/{seq_id}/velodyne/{i:06d}.bin", "wb").close()
+                os.chdir(d)
+                try:
+                    with redirect_stdout(io.StringIO()):
+                        every = list(SK_Dataloader(gpu_num=1, gpu_rank=0, num_workers=0).score_data_loader(inf_reps=8).dataset.lidar_files[::8])
+                        assert len(every) == n
+                        for rank in range(world):
+                            files = list(SK_Dataloader(gpu_num=world, gpu_rank=rank, num_workers=0).score_data_loader(inf_reps=8).dataset.lidar_files[::8])
+                            got = [every.index(f) for f in files]
+                            mine = pipeline.frame_shard(n, world, rank)
+                            assert got == list(mine), (n, world, rank)
+                            rows.append((n, world, rank, mine.start, mine.stop))
+                finally:
+                    os.chdir(cwd)
+    finally:
+        dist.destroy_process_group()
+    np.savez_compressed(f"{OUT}/shard.npz", rows=np.array(rows, dtype=np.int64))
+    print(f"shard.npz: reference score_data_loader split == pipeline.frame_shard on {len(cases)} (frames, ranks) cases, {len(rows)} shards")
+
+
 def gen_cli():
     """The reference's own command line, `python -m score.sv_level.LiDAL --dataset_name SK --model_name SPVCNN --r_id 1`
     (README.md:115), run UNMODIFIED as a subprocess in a synthetic Processing_files/ tree (synth.write_scoring_tree; two of
@@ -322,6 +361,6 @@ def gen_cli():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets", "voxelizer", "extra", "cli"]
+    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets", "voxelizer", "extra", "cli", "shard"]
     for w in which:
         globals()[f"gen_{w}"]()

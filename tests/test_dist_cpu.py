@@ -70,6 +70,18 @@ def test_frame_shard_and_needs():
     assert pipeline.needed_frames(range(0, 5), 1000) == list(range(0, 25))  # sequence start: reflected window
 
 
+def test_frame_shard_equals_the_reference_data_loader(golden):
+    """tests/golden/shard.npz: the frames the reference's own SK_Dataloader(gpu_num, gpu_rank).score_data_loader hands to each
+    rank (dataset/sk_dataloader.py:196-198, run unmodified in the build container)."""
+    from lidal_b200 import pipeline
+    rows = golden["shard"]["rows"]
+    assert len(rows) == 38
+    for n, world, rank, start, stop in rows.tolist():
+        own = pipeline.frame_shard(n, world, rank)
+        assert (own.start, own.stop) == (start, stop), (n, world, rank)
+        assert all(pipeline.owner_of(f, n, world) == rank for f in own)
+
+
 @pytest.mark.timeout(300)
 def test_two_rank_sharded_scoring_equals_single_process(tmp_path):
     sys.path[:0] = [os.path.join(ROOT, "oracle")]
