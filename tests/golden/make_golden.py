@@ -278,6 +278,39 @@ def gen_extra():
     print(f"extra.npz: reference process_frame / segment_entropy / ReDAL worker == oracle on {n} points; sege={sege_ref:.6f}")
 
 
+def tail_inputs(seed=77, reps=8, n_pts=700, n_cls=19):
+    """Ragged TTA views: per view its own voxel count, every point of the scan mapped into every view (collate_fn :216-218,230)."""
+    rng = np.random.default_rng(seed)
+    n_vox = [int(v) for v in rng.integers(400, 600, reps)]
+    logits = (rng.normal(size=(sum(n_vox), n_cls)) * 3).astype(np.float32)
+    feat = rng.normal(size=(sum(n_vox), 96)).astype(np.float32)
+    inverse = np.concatenate([rng.integers(0, nv, n_pts) + off for nv, off in zip(n_vox, np.cumsum([0] + n_vox[:-1]))]).astype(np.int64)
+    return logits, feat, inverse, reps
+
+
+def gen_tail():
+    """The reference's own inference tail -- score/prob_inference.py:99-118 exec'd unmodified (the model call above it needs
+    CUDA, these lines do not): gather by inverse index, softmax, mean over the TTA views, argmax, out_feat mean ==
+    oracle.lidal_scoring.tta_tail / oracle.lidal_extra.outfeat_mean (exact)."""
+    import types
+    import torch
+    import lidal_extra as ox
+    src = open(f"{REF}/score/prob_inference.py").read().split("\n")
+    block = "\n".join(line[12:] if line.startswith(" " * 12) else line.strip() for line in src[98:118])      # lines 99..118
+    assert block.lstrip().startswith("# Project to original points") and "out_feat = np.mean(out_feat, axis=0)" in block
+    logits, feat, inverse, reps = tail_inputs()
+    ns = dict(torch=torch, np=np, logits_v_b=torch.from_numpy(logits), out_feat_v_b=torch.from_numpy(feat),
+              batch={"inverse_indices_b": torch.from_numpy(inverse)}, args=types.SimpleNamespace(r_id=0, metric_name="LiDAL", inf_reps=reps))
+    exec(compile(block, "prob_inference.py[99:118]", "exec"), ns)
+    prob, pred = orc.tta_tail(logits, inverse, reps)
+    of = ox.outfeat_mean(feat, inverse, reps)
+    for name, a, b in (("prob", ns["prob_map_mean"], prob), ("pred", ns["pred"], pred), ("out_feat", ns["out_feat"], of)):
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), name
+    np.savez_compressed(f"{OUT}/tail.npz", input_sha=sha(logits, feat, inverse), prob_sha=sha(ns["prob_map_mean"]), prob_head=ns["prob_map_mean"][:64],
+                        pred=ns["pred"].astype(np.int16), out_feat_head=ns["out_feat"][:64], out_feat_sha=sha(ns["out_feat"]))
+    print(f"tail.npz: reference prob_inference.py:99-118 == oracle tta_tail / outfeat_mean on {reps} views x {len(pred)} points")
+
+
 def gen_shard():
     """The reference's own score-mode data loader (dataset/sk_dataloader.py:185-198, unmodified) on a tree of empty .bin
     files: which frames rank r of G gets == lidal_b200.pipeline.frame_shard (the split every sharded driver uses)."""
@@ -361,6 +394,6 @@ def gen_cli():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets", "voxelizer", "extra", "cli", "shard"]
+    which = sys.argv[1:] or ["hash", "scoring", "selection", "nets", "voxelizer", "extra", "cli", "shard", "tail"]
     for w in which:
         globals()[f"gen_{w}"]()

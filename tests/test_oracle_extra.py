@@ -45,3 +45,22 @@ def test_register_segment_entropy_redal_match_reference(golden):
     assert ox.segment_entropy(pred, seq.sv2point[f], int(g["n_cls"])) == float(g["segment_entropy"])
     out = ox.redal_worker(prob, outfeat, g["curvature"].astype(np.float32), seq.sv_id[f], seq.sv2point[f], False)
     assert np.array_equal(out[1], g["redal_scores"]) and np.array_equal(out[2], g["redal_feats"]) and np.array_equal(out[3], g["redal_pnums"])
+
+
+def test_tta_tail_matches_reference_lines(golden):
+    """tail.npz: score/prob_inference.py:99-118 exec'd unmodified in the build container (gather by inverse index, softmax,
+    mean over the TTA views, argmax, out_feat mean) == the oracle's tta_tail / outfeat_mean, bit for bit."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import lidal_extra as ox
+    import lidal_scoring as orc
+    from make_golden import tail_inputs
+    g = golden["tail"]
+    logits, feat, inverse, reps = tail_inputs()
+    assert sha(logits, feat, inverse) == str(g["input_sha"])
+    prob, pred = orc.tta_tail(logits, inverse, reps)
+    assert prob.dtype == np.float32 and sha(prob) == str(g["prob_sha"]) and np.array_equal(prob[:64], g["prob_head"])
+    assert pred.dtype == np.int64 and np.array_equal(pred, g["pred"].astype(np.int64))
+    of = ox.outfeat_mean(feat, inverse, reps)
+    assert of.dtype == np.float32 and sha(of) == str(g["out_feat_sha"]) and np.array_equal(of[:64], g["out_feat_head"])
